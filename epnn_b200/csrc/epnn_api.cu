@@ -1,0 +1,667 @@
+// C-ABI of libepnn_b200.so: context, weight upload, workspace management and the launch sequence.
+// See include/epnn_b200.h for the contract of every entry point and the reference code it replaces.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "epnn_internal.cuh"
+
+#define EPNN_VERSION_STR "epnn_b200 0.1.0 sm_100a"
+
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct PackedOffsets {           // element offsets into the packed device weight buffer (same for float/double)
+    struct Step { size_t Ah64, Aq64, Ax64, Cw, b1, W2, b2, W3, b3; };
+    std::vector<Step> msg, pas;
+    size_t U1, c1, U2, c2, U3, c3;
+    size_t total;
+};
+
+struct epnn_ctx {
+    int device = 0, T = 0, n_x = 0, n_species = 0, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    int precision = 32, timing = 0, keep_hidden = 0;
+    int64_t chunk_atoms = 4 * 1024 * 1024;
+    PackedOffsets po;
+    float* wf = nullptr;         // packed weights, float
+    double* wd = nullptr;        // packed weights, double
+    std::vector<DevBuf> bufs;    // grow-only workspaces, indexed by enum below
+    int* d_flags = nullptr;      // [0] error bits, [1..4] totals (nnz, P, n_rg_small, n_rg_large)
+    int* h_flags = nullptr;      // pinned mirror
+    int64_t hidden_atoms = 0;    // atoms covered by the retained hidden state
+    int hidden_precision = 32;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+enum {
+    B_XYZ, B_SPECIES, B_OFF, B_Q, B_NPAD, B_ATOMSYS, B_DEG, B_DEGU, B_ROWPTR, B_USTART, B_COL, B_PID, B_PI, B_PJ, B_PD,
+    B_E, B_NEAR, B_RGS, B_RGL, B_H, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTS, B_CNTL, B_RGSOFF, B_RGLOFF,
+    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_COUNT
+};
+
+static int fail(epnn_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define CU(c, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _e = (call);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return fail((c), _e == cudaErrorMemoryAllocation ? EPNN_E_NOMEM : EPNN_E_CUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(_e), __FILE__, __LINE__);                                  \
+    } while (0)
+
+static int ensure(epnn_ctx* c, int which, size_t bytes, void** out) {
+    DevBuf& b = c->bufs[which];
+    if (bytes > b.cap) {
+        if (b.p) { CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        CU(c, cudaMalloc(&b.p, want));
+        b.cap = want;
+    }
+    *out = b.p;
+    return EPNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+static const double Z9[8] = {1, 6, 7, 8, 9, 16, 17, 35};            // infer.py:13-30
+static const double Z10[9] = {1, 6, 7, 8, 9, 15, 16, 17, 35};       // charge_gn.py:9-28
+
+static size_t expected_floats(int T, int n_x) {
+    const size_t K = 2 * (size_t)(n_x + 49) + 48;
+    const size_t msg = K * 32 + 32 + 32 * 32 + 32 + 32 * 32 + 32;
+    const size_t upd = 80 * 32 + 32 + 32 * 32 + 32 + 32 * 48 + 48;
+    const size_t pas = K * 32 + 32 + 32 * 32 + 32 + 32 + 1;
+    return T * msg + upd + T * pas;
+}
+
+static size_t take(size_t& cur, size_t n) { size_t o = cur; cur += (n + 7) & ~(size_t)7; return o; }
+
+// Split one first-layer kernel W1[K][32] (+b1) into the per-atom / per-pair blocks.
+static void pack_step(std::vector<double>& P, const PackedOffsets::Step& o, const float* W1, const float* b1, int n_x,
+                      const double* Z, int n_species) {
+    const int F = n_x + 49;
+    for (int k = 0; k < 48; ++k)
+        for (int c = 0; c < 32; ++c) {
+            P[o.Ah64 + k * 64 + c] = W1[(n_x + k) * 32 + c];
+            P[o.Ah64 + k * 64 + 32 + c] = W1[(F + n_x + k) * 32 + c];
+            P[o.Cw + k * 32 + c] = W1[(2 * F + k) * 32 + c];
+        }
+    for (int c = 0; c < 32; ++c) {
+        P[o.Aq64 + c] = W1[(n_x + 48) * 32 + c];
+        P[o.Aq64 + 32 + c] = W1[(F + n_x + 48) * 32 + c];
+        P[o.b1 + c] = b1[c];
+    }
+    for (int s = 0; s < n_species; ++s)
+        for (int c = 0; c < 32; ++c) {
+            P[o.Ax64 + s * 64 + c] = Z[s] * (double)W1[c] + (double)W1[(1 + s) * 32 + c];
+            P[o.Ax64 + s * 64 + 32 + c] = Z[s] * (double)W1[F * 32 + c] + (double)W1[(F + 1 + s) * 32 + c] + (double)b1[c];
+        }
+}
+
+template <typename R> static StepW<R> step_view(const R* base, const PackedOffsets::Step& o) {
+    StepW<R> s;
+    s.Ah64 = base + o.Ah64; s.Aq64 = base + o.Aq64; s.Ax64 = base + o.Ax64; s.Cw = base + o.Cw; s.b1 = base + o.b1;
+    s.W2 = base + o.W2; s.b2 = base + o.b2; s.W3 = base + o.W3; s.b3 = base + o.b3;
+    return s;
+}
+template <typename R> static UpdW<R> upd_view(const R* base, const PackedOffsets& po) {
+    UpdW<R> u;
+    u.U1 = base + po.U1; u.c1 = base + po.c1; u.U2 = base + po.U2; u.c2 = base + po.c2; u.U3 = base + po.U3; u.c3 = base + po.c3;
+    return u;
+}
+
+extern "C" int epnn_rbf_centers(double* mu) {
+    if (!mu) return EPNN_E_INVALID;
+    // numpy.linspace(0.1, 3.0, 48): step = (stop-start)/47; y = arange(48)*step + start; y[-1] = stop
+    volatile double step = (3.0 - 0.1) / 47.0;
+    for (int k = 0; k < 48; ++k) {
+        volatile double prod = (double)k * step;      // volatile: forbid FMA contraction of k*step + start
+        mu[k] = prod + 0.1;
+    }
+    mu[47] = 3.0;
+    return EPNN_OK;
+}
+
+extern "C" const char* epnn_version(void) { return EPNN_VERSION_STR; }
+
+extern "C" const char* epnn_last_error(const epnn_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_floats, epnn_ctx** out) {
+    if (!out) return fail(nullptr, EPNN_E_INVALID, "epnn_create: out is NULL");
+    *out = nullptr;
+    if (!w) return fail(nullptr, EPNN_E_INVALID, "epnn_create: packed_weights is NULL");
+    if (T < 1 || T > 64) return fail(nullptr, EPNN_E_INVALID, "epnn_create: T=%d out of range", T);
+    if (n_x != 9 && n_x != 10) return fail(nullptr, EPNN_E_INVALID, "epnn_create: n_x must be 9 or 10 (got %d)", n_x);
+    if (n_floats != expected_floats(T, n_x))
+        return fail(nullptr, EPNN_E_INVALID, "epnn_create: expected %zu packed floats for T=%d n_x=%d, got %zu",
+                    expected_floats(T, n_x), T, n_x, n_floats);
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, EPNN_E_CUDA, "epnn_create: no usable CUDA device (%s); this library has no CPU fallback",
+                    ce == cudaSuccess ? "device count is 0" : cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(nullptr, EPNN_E_INVALID, "epnn_create: device %d not in [0,%d)", device, ndev);
+
+    epnn_ctx* c = new (std::nothrow) epnn_ctx();
+    if (!c) return fail(nullptr, EPNN_E_NOMEM, "epnn_create: out of host memory");
+    c->device = device; c->T = T; c->n_x = n_x; c->n_species = n_x - 1;
+    c->bufs.resize(B_COUNT);
+#define CUC(call)                                                                                               \
+    do {                                                                                                        \
+        cudaError_t _e = (call);                                                                                \
+        if (_e != cudaSuccess) {                                                                                \
+            int rc = fail(nullptr, EPNN_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_e));               \
+            epnn_destroy(c);                                                                                    \
+            return rc;                                                                                          \
+        }                                                                                                       \
+    } while (0)
+    CUC(cudaSetDevice(device));
+    CUC(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaMalloc(&c->d_flags, 8 * sizeof(int)));
+    CUC(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
+    double mu[48];
+    epnn_rbf_centers(mu);
+    CUC(upload_rbf_centers(mu));
+
+    // ---- pack
+    PackedOffsets& po = c->po;
+    size_t cur = 0;
+    auto step_offsets = [&](bool is_pass) {
+        PackedOffsets::Step o;
+        o.Ah64 = take(cur, 48 * 64); o.Aq64 = take(cur, 64); o.Ax64 = take(cur, MAX_SPECIES * 64); o.Cw = take(cur, 48 * 32);
+        o.b1 = take(cur, 32); o.W2 = take(cur, 32 * 32); o.b2 = take(cur, 32);
+        o.W3 = take(cur, is_pass ? 32 : 32 * 32); o.b3 = take(cur, is_pass ? 1 : 32);
+        return o;
+    };
+    for (int t = 0; t < T; ++t) po.msg.push_back(step_offsets(false));
+    po.U1 = take(cur, 80 * 32); po.c1 = take(cur, 32); po.U2 = take(cur, 32 * 32); po.c2 = take(cur, 32);
+    po.U3 = take(cur, 32 * 48); po.c3 = take(cur, 48);
+    for (int t = 0; t < T; ++t) po.pas.push_back(step_offsets(true));
+    po.total = cur;
+    std::vector<double> P(po.total, 0.0);
+    const int K = 2 * (n_x + 49) + 48;
+    const double* Z = n_x == 9 ? Z9 : Z10;
+    const float* r = w;
+    auto copy = [&](size_t off, size_t n) { for (size_t i = 0; i < n; ++i) P[off + i] = r[i]; r += n; };
+    for (int t = 0; t < T; ++t) {
+        const float* W1 = r; const float* b1 = r + (size_t)K * 32;
+        pack_step(P, po.msg[t], W1, b1, n_x, Z, c->n_species);
+        r += (size_t)K * 32 + 32;
+        copy(po.msg[t].W2, 32 * 32); copy(po.msg[t].b2, 32); copy(po.msg[t].W3, 32 * 32); copy(po.msg[t].b3, 32);
+    }
+    copy(po.U1, 80 * 32); copy(po.c1, 32); copy(po.U2, 32 * 32); copy(po.c2, 32); copy(po.U3, 32 * 48); copy(po.c3, 48);
+    for (int t = 0; t < T; ++t) {
+        const float* W1 = r; const float* b1 = r + (size_t)K * 32;
+        pack_step(P, po.pas[t], W1, b1, n_x, Z, c->n_species);
+        r += (size_t)K * 32 + 32;
+        copy(po.pas[t].W2, 32 * 32); copy(po.pas[t].b2, 32); copy(po.pas[t].W3, 32); copy(po.pas[t].b3, 1);
+    }
+    std::vector<float> Pf(po.total);
+    for (size_t i = 0; i < po.total; ++i) Pf[i] = (float)P[i];
+    CUC(cudaMalloc(&c->wf, po.total * sizeof(float)));
+    CUC(cudaMalloc(&c->wd, po.total * sizeof(double)));
+    CUC(cudaMemcpy(c->wf, Pf.data(), po.total * sizeof(float), cudaMemcpyHostToDevice));
+    CUC(cudaMemcpy(c->wd, P.data(), po.total * sizeof(double), cudaMemcpyHostToDevice));
+#undef CUC
+    *out = c;
+    return EPNN_OK;
+}
+
+extern "C" void epnn_destroy(epnn_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (DevBuf& b : c->bufs) if (b.p) cudaFree(b.p);
+    if (c->wf) cudaFree(c->wf);
+    if (c->wd) cudaFree(c->wd);
+    if (c->d_flags) cudaFree(c->d_flags);
+    if (c->h_flags) cudaFreeHost(c->h_flags);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int epnn_set_option(epnn_ctx* c, const char* key, double value) {
+    if (!c || !key) return EPNN_E_INVALID;
+    const std::string k(key);
+    if (k == "precision") {
+        if (value != 32 && value != 64) return fail(c, EPNN_E_INVALID, "precision must be 32 or 64");
+        c->precision = (int)value;
+    } else if (k == "timing") c->timing = value != 0;
+    else if (k == "keep_hidden") c->keep_hidden = value != 0;
+    else if (k == "chunk_atoms") {
+        if (value < 64) return fail(c, EPNN_E_INVALID, "chunk_atoms must be >= 64");
+        c->chunk_atoms = (int64_t)value;
+    } else return fail(c, EPNN_E_INVALID, "unknown option '%s'", key);
+    return EPNN_OK;
+}
+
+extern "C" int epnn_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return EPNN_E_INVALID;
+    return cudaMallocHost(ptr, bytes ? bytes : 1) == cudaSuccess ? EPNN_OK : EPNN_E_NOMEM;
+}
+extern "C" int epnn_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? EPNN_OK : EPNN_E_CUDA; }
+
+// ------------------------------------------------------------------------------------------------
+// Per-system prep: rebased offsets, default npad, validation, row-group counts.
+__global__ void sys_prep_kernel(int n_sys, const int* __restrict__ off_in, int base, int* __restrict__ off_out,
+                                const int* __restrict__ npad_in, int* __restrict__ npad_out,
+                                int* __restrict__ cnt_small, int* __restrict__ cnt_large, int* __restrict__ flags) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_sys) return;
+    const int o = off_in[s] - base;
+    off_out[s] = o;
+    if (s == n_sys) return;
+    const int n = off_in[s + 1] - off_in[s];
+    int np = npad_in ? npad_in[s] : n;
+    if (np < n || n <= 0) { atomicOr(flags, n <= 0 ? 2 : 1); np = n; }
+    npad_out[s] = np;
+    const int g = (n + 3) >> 2;
+    cnt_small[s] = n <= SMALL_MAX ? g : 0;
+    cnt_large[s] = n <= SMALL_MAX ? 0 : g;
+}
+
+__global__ void rg_fill_kernel(int n_sys, const int* __restrict__ off, const int* __restrict__ rgs_off,
+                               const int* __restrict__ rgl_off, int* __restrict__ rg_small, int* __restrict__ rg_large) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_sys) return;
+    const int a0 = off[s], a1 = off[s + 1];
+    const bool small = (a1 - a0) <= SMALL_MAX;
+    int* dst = small ? rg_small + rgs_off[s] : rg_large + rgl_off[s];
+    int k = 0;
+    for (int i = a0; i < a1; i += 4) dst[k++] = i;
+}
+
+__global__ void species_check_kernel(int n, const int* __restrict__ species, int n_species, int* __restrict__ flags) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (species[i] < 0 || species[i] >= n_species)) atomicOr(flags, 4);
+}
+
+__global__ void collect_totals_kernel(const int* rowptr, const int* ustart, int n_atoms, const int* rgs_off,
+                                      const int* rgl_off, int n_sys, int* flags) {
+    flags[1] = rowptr[n_atoms]; flags[2] = ustart[n_atoms]; flags[3] = rgs_off[n_sys]; flags[4] = rgl_off[n_sys];
+}
+
+struct Timer {
+    bool on; cudaStream_t st; std::vector<cudaEvent_t> ev; std::vector<int> tag;
+    void mark(int t) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); tag.push_back(t); }
+    void finish(epnn_stats* s) {
+        if (!on) return;
+        if (s && !ev.empty()) {
+            cudaEventSynchronize(ev.back());
+            for (size_t i = 1; i < ev.size(); ++i) {
+                float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+                switch (tag[i]) {
+                    case 1: s->ms_h2d += ms; break; case 2: s->ms_neighbor += ms; break; case 3: s->ms_gnn_pair += ms; break;
+                    case 4: s->ms_gnn_atom += ms; break; case 5: s->ms_epn_pair += ms; break; case 6: s->ms_epn_atom += ms; break;
+                    case 7: s->ms_d2h += ms; break; default: break;
+                }
+                s->ms_total += ms;
+            }
+        }
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        ev.clear(); tag.clear();
+    }
+};
+
+// One chunk, device-resident inputs: d_off_in = slice of the caller's GLOBAL offsets (n_sys+1), base = its first value.
+template <typename R>
+static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int* d_off_in, int base, const float* d_xyz,
+                     const int* d_species, const float* d_Q, const int* d_npad_in, float* d_out32, double* d_out64,
+                     epnn_stats* stats, Timer& tm, int* n_launch, bool neighbors_only, Workspace* ws_out) {
+    cudaStream_t st = c->stream;
+    Workspace w;
+    memset(&w, 0, sizeof(w));
+    w.n_atoms = n_atoms; w.n_sys = n_sys; w.sm_count = c->sm_count;
+    w.xyz = d_xyz; w.species = d_species; w.Qsys = d_Q;
+    void* p;
+    int rc;
+#define ENS(which, bytes, field, type) do { if ((rc = ensure(c, which, (bytes), &p)) != EPNN_OK) return rc; field = (type)p; } while (0)
+    int *off_local, *npad_local, *cnt_s, *cnt_l, *rgs_off, *rgl_off, *scantmp;
+    ENS(B_OFF, sizeof(int) * ((size_t)n_sys + 1), off_local, int*);
+    ENS(B_NPAD, sizeof(int) * ((size_t)n_sys + 1), npad_local, int*);
+    ENS(B_CNTS, sizeof(int) * ((size_t)n_sys + 1), cnt_s, int*);
+    ENS(B_CNTL, sizeof(int) * ((size_t)n_sys + 1), cnt_l, int*);
+    ENS(B_RGSOFF, sizeof(int) * ((size_t)n_sys + 1), rgs_off, int*);
+    ENS(B_RGLOFF, sizeof(int) * ((size_t)n_sys + 1), rgl_off, int*);
+    const size_t nmax = (size_t)(n_atoms > n_sys ? n_atoms : n_sys);
+    ENS(B_SCANTMP, sizeof(int) * (nmax / 1024 + 2), scantmp, int*);
+    ENS(B_ATOMSYS, sizeof(int) * (size_t)n_atoms, w.atom_sys, int*);
+    ENS(B_DEG, sizeof(int) * (size_t)n_atoms, w.deg, int*);
+    ENS(B_DEGU, sizeof(int) * (size_t)n_atoms, w.degU, int*);
+    ENS(B_ROWPTR, sizeof(int) * ((size_t)n_atoms + 1), w.rowptr, int*);
+    ENS(B_USTART, sizeof(int) * ((size_t)n_atoms + 1), w.ustart, int*);
+    ENS(B_QD, sizeof(double) * (size_t)n_atoms, w.q, double*);
+    w.sys_off = off_local; w.npad = npad_local;
+
+    CU(c, cudaMemsetAsync(c->d_flags, 0, 8 * sizeof(int), st));
+    sys_prep_kernel<<<div_up(n_sys + 1, 256), 256, 0, st>>>(n_sys, d_off_in, base, off_local, d_npad_in, npad_local, cnt_s, cnt_l, c->d_flags);
+    species_check_kernel<<<div_up(n_atoms, 256), 256, 0, st>>>(n_atoms, d_species, c->n_species, c->d_flags);
+    *n_launch += 2;
+    CU(c, cudaGetLastError());
+    CU(c, launch_scan_i32(cnt_s, rgs_off, n_sys, scantmp, st, n_launch));
+    CU(c, launch_scan_i32(cnt_l, rgl_off, n_sys, scantmp, st, n_launch));
+    CU(c, launch_prep(w, st, n_launch));
+    CU(c, launch_nbr_count(w, st, n_launch));
+    CU(c, launch_scan_i32(w.deg, w.rowptr, n_atoms, scantmp, st, n_launch));
+    CU(c, launch_scan_i32(w.degU, w.ustart, n_atoms, scantmp, st, n_launch));
+    collect_totals_kernel<<<1, 1, 0, st>>>(w.rowptr, w.ustart, n_atoms, rgs_off, rgl_off, n_sys, c->d_flags);
+    ++*n_launch;
+    CU(c, cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    if (c->h_flags[0] & 1) return fail(c, EPNN_E_INVALID, "npad smaller than the number of atoms for at least one system");
+    if (c->h_flags[0] & 2) return fail(c, EPNN_E_INVALID, "a system with zero (or negative) atoms was passed");
+    if (c->h_flags[0] & 4) return fail(c, EPNN_E_INVALID, "species index outside the element table (n_x=%d has %d species)", c->n_x, c->n_species);
+    w.nnz = c->h_flags[1]; w.P = c->h_flags[2]; w.n_rg_small = c->h_flags[3]; w.n_rg_large = c->h_flags[4];
+    if (w.nnz < 0 || w.P < 0) return fail(c, EPNN_E_UNSUPPORTED, "neighbour list of one chunk exceeds 2^31 entries; lower chunk_atoms");
+    w.nsplit = 1;
+    if (w.n_rg_large > 0) {
+        int ns = div_up((int64_t)c->sm_count * 64, w.n_rg_large);
+        w.nsplit = ns < 1 ? 1 : (ns > 32 ? 32 : ns);
+    }
+
+    ENS(B_COL, sizeof(int) * (size_t)(w.nnz + 1), w.col, int*);
+    ENS(B_PID, sizeof(int) * (size_t)(w.nnz + 1), w.pid, int*);
+    ENS(B_PI, sizeof(int) * (size_t)(w.P + 1), w.pair_i, int*);
+    ENS(B_PJ, sizeof(int) * (size_t)(w.P + 1), w.pair_j, int*);
+    ENS(B_PD, sizeof(double) * (size_t)(w.P + 1), w.pair_D, double*);
+    ENS(B_E, sizeof(float) * ED * (size_t)(w.P + 1), w.e, float*);
+    ENS(B_NEAR, (size_t)(w.P + 16), w.near, unsigned char*);
+    ENS(B_RGS, sizeof(int) * (size_t)(w.n_rg_small + 1), w.rg_small, int*);
+    ENS(B_RGL, sizeof(int) * (size_t)(w.n_rg_large + 1), w.rg_large, int*);
+    rg_fill_kernel<<<div_up(n_sys, 256), 256, 0, st>>>(n_sys, off_local, rgs_off, rgl_off, w.rg_small, w.rg_large);
+    ++*n_launch;
+    CU(c, cudaGetLastError());
+    CU(c, launch_nbr_fill(w, st, n_launch));
+    tm.mark(2);
+    if (stats) {
+        stats->n_pairs_e += w.P;
+        stats->n_row_groups += w.n_rg_small + w.n_rg_large;
+    }
+    if (ws_out) *ws_out = w;
+    if (neighbors_only) return EPNN_OK;
+
+    ENS(B_H, sizeof(R) * HD * (size_t)n_atoms, w.h, void*);
+    ENS(B_S, sizeof(R) * HID * (size_t)n_atoms * w.nsplit, w.S, void*);
+    ENS(B_U, sizeof(R) * HID * (size_t)n_atoms, w.u, void*);
+    ENS(B_V, sizeof(R) * HID * (size_t)n_atoms, w.v, void*);
+    ENS(B_DELTA, sizeof(R) * (size_t)(w.P + 1), w.delta, void*);
+#undef ENS
+    CU(c, cudaMemsetAsync(w.h, 0, sizeof(R) * HD * (size_t)n_atoms, st));
+
+    const R* wb = sizeof(R) == 4 ? (const R*)c->wf : (const R*)c->wd;
+    const UpdW<R> upd = upd_view<R>(wb, c->po);
+    std::vector<StepW<R>> msg(c->T), pas(c->T);
+    for (int t = 0; t < c->T; ++t) { msg[t] = step_view<R>(wb, c->po.msg[t]); pas[t] = step_view<R>(wb, c->po.pas[t]); }
+
+    // ---- GNN layer: T message-passing steps (charge_gn.py:60-74)
+    CU(c, launch_atom<R>(w, ATOM_PROJECT, nullptr, nullptr, &msg[0], 1, nullptr, nullptr, st, n_launch));
+    tm.mark(4);
+    for (int t = 0; t < c->T; ++t) {
+        CU(c, launch_gnn_pair<R>(w, msg[t], st, n_launch));
+        tm.mark(3);
+        const StepW<R>* next = t + 1 < c->T ? &msg[t + 1] : &pas[0];
+        CU(c, launch_atom<R>(w, ATOM_UPDATE | ATOM_PROJECT, &msg[t], &upd, next, 0, nullptr, nullptr, st, n_launch));
+        tm.mark(t + 1 < c->T ? 4 : 6);
+    }
+    // ---- EPN layer: T electron-passing passes (charge_gn.py:98-118)
+    for (int t = 0; t < c->T; ++t) {
+        CU(c, launch_epn_pair<R>(w, pas[t], st, n_launch));
+        tm.mark(5);
+        if (t + 1 < c->T)
+            CU(c, launch_atom<R>(w, ATOM_QUPDATE | ATOM_PROJECT, nullptr, nullptr, &pas[t + 1], 0, nullptr, nullptr, st, n_launch));
+        else
+            CU(c, launch_atom<R>(w, ATOM_QUPDATE | ATOM_OUTPUT, nullptr, nullptr, nullptr, 0, d_out32, d_out64, st, n_launch));
+        tm.mark(6);
+    }
+    c->hidden_atoms = n_atoms;
+    c->hidden_precision = sizeof(R) == 4 ? 32 : 64;
+    return EPNN_OK;
+}
+
+__global__ void count_near_kernel(int64_t P, const unsigned char* __restrict__ near, unsigned long long* out) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = p < P ? near[p] : 0;
+    const unsigned b = __ballot_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (unsigned long long)__popc(b));
+}
+
+// Splits [0, n_sys) into chunks of at most chunk_atoms atoms (a single larger system gets its own chunk).
+static void plan_chunks(const int32_t* off, int64_t n_sys, int64_t chunk_atoms, std::vector<int64_t>& bounds) {
+    bounds.clear();
+    bounds.push_back(0);
+    int64_t s = 0;
+    while (s < n_sys) {
+        int64_t e = s + 1;
+        while (e < n_sys && (int64_t)off[e + 1] - off[s] <= chunk_atoms) ++e;
+        bounds.push_back(e);
+        s = e;
+    }
+}
+
+static int validate_offsets(epnn_ctx* c, int64_t n_sys, const int32_t* off) {
+    if (n_sys < 0) return fail(c, EPNN_E_INVALID, "n_sys is negative");
+    if (n_sys > 0 && !off) return fail(c, EPNN_E_INVALID, "atom_offsets is NULL");
+    if (n_sys > 0 && off[0] != 0) return fail(c, EPNN_E_INVALID, "atom_offsets[0] must be 0");
+    for (int64_t s = 0; s < n_sys; ++s)
+        if (off[s + 1] <= off[s]) return fail(c, EPNN_E_INVALID, "system %lld has no atoms (offsets must be strictly increasing)", (long long)s);
+    return EPNN_OK;
+}
+
+static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_io, const float* xyz, const int32_t* species,
+                      const float* Q, const int32_t* npad_host, float* q_out, double* q_out64, epnn_stats* stats) {
+    if (!c) return EPNN_E_INVALID;
+    int rc = validate_offsets(c, n_sys, off);
+    if (rc != EPNN_OK) return rc;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (n_sys == 0) return EPNN_OK;
+    if (!xyz || !species || !Q || (!q_out && !q_out64)) return fail(c, EPNN_E_INVALID, "NULL input/output pointer");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    std::vector<int64_t> bounds;
+    plan_chunks(off, n_sys, c->chunk_atoms, bounds);
+    Timer tm{c->timing != 0, st, {}, {}};
+    int n_launch = 0;
+    unsigned long long* d_near_count = nullptr;
+    void* p;
+    if ((rc = ensure(c, B_MISC, 64, &p)) != EPNN_OK) return rc;
+    d_near_count = (unsigned long long*)p;
+    CU(c, cudaMemsetAsync(d_near_count, 0, sizeof(unsigned long long), st));
+    tm.mark(0);
+    for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
+        const int64_t s0 = bounds[ci], s1 = bounds[ci + 1];
+        const int ns = (int)(s1 - s0);
+        const int a0 = off[s0], a1 = off[s1];
+        const int na = a1 - a0;
+        // offsets (and npad) always come from the host: they drive launch geometry
+        int* d_off; int* d_npad_in = nullptr;
+        if ((rc = ensure(c, B_OFFIN, sizeof(int) * ((size_t)ns + 1) * 2 + 64, &p)) != EPNN_OK) return rc;
+        d_off = (int*)p;
+        CU(c, cudaMemcpyAsync(d_off, off + s0, sizeof(int) * ((size_t)ns + 1), cudaMemcpyHostToDevice, st));
+        if (npad_host) {
+            d_npad_in = d_off + ns + 1;
+            CU(c, cudaMemcpyAsync(d_npad_in, npad_host + s0, sizeof(int) * (size_t)ns, cudaMemcpyHostToDevice, st));
+        }
+        const float* d_xyz; const int* d_species; const float* d_Q; float* d_o32 = nullptr; double* d_o64 = nullptr;
+        if (host_io) {
+            float* bx; int* bs; float* bq;
+            if ((rc = ensure(c, B_XYZ, sizeof(float) * 3 * (size_t)na, &p)) != EPNN_OK) return rc; bx = (float*)p;
+            if ((rc = ensure(c, B_SPECIES, sizeof(int) * (size_t)na, &p)) != EPNN_OK) return rc; bs = (int*)p;
+            if ((rc = ensure(c, B_Q, sizeof(float) * (size_t)ns, &p)) != EPNN_OK) return rc; bq = (float*)p;
+            CU(c, cudaMemcpyAsync(bx, xyz + 3 * (size_t)a0, sizeof(float) * 3 * (size_t)na, cudaMemcpyHostToDevice, st));
+            CU(c, cudaMemcpyAsync(bs, species + a0, sizeof(int) * (size_t)na, cudaMemcpyHostToDevice, st));
+            CU(c, cudaMemcpyAsync(bq, Q + s0, sizeof(float) * (size_t)ns, cudaMemcpyHostToDevice, st));
+            d_xyz = bx; d_species = bs; d_Q = bq;
+            if (q_out) { if ((rc = ensure(c, B_OUT32, sizeof(float) * (size_t)na, &p)) != EPNN_OK) return rc; d_o32 = (float*)p; }
+            if (q_out64) { if ((rc = ensure(c, B_OUT64, sizeof(double) * (size_t)na, &p)) != EPNN_OK) return rc; d_o64 = (double*)p; }
+        } else {
+            d_xyz = xyz + 3 * (size_t)a0; d_species = species + a0; d_Q = Q + s0;
+            d_o32 = q_out ? q_out + a0 : nullptr; d_o64 = q_out64 ? q_out64 + a0 : nullptr;
+        }
+        tm.mark(1);
+        Workspace w;
+        if (c->precision == 64)
+            rc = run_chunk<double>(c, ns, na, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
+        else
+            rc = run_chunk<float>(c, ns, na, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
+        if (rc != EPNN_OK) return rc;
+        if (stats && w.P > 0) {
+            count_near_kernel<<<div_up(w.P, 256), 256, 0, st>>>(w.P, w.near, d_near_count);
+            ++n_launch;
+        }
+        if (host_io) {
+            if (q_out) CU(c, cudaMemcpyAsync(q_out + a0, d_o32, sizeof(float) * (size_t)na, cudaMemcpyDeviceToHost, st));
+            if (q_out64) CU(c, cudaMemcpyAsync(q_out64 + a0, d_o64, sizeof(double) * (size_t)na, cudaMemcpyDeviceToHost, st));
+            // the staging buffers are reused by the next chunk: wait for the copies
+            CU(c, cudaStreamSynchronize(st));
+        }
+        tm.mark(7);
+    }
+    CU(c, cudaStreamSynchronize(st));
+    if (stats) {
+        unsigned long long nn = 0;
+        CU(c, cudaMemcpy(&nn, d_near_count, sizeof(nn), cudaMemcpyDeviceToHost));
+        stats->n_pairs_near = (int64_t)nn;
+        stats->n_systems = n_sys; stats->n_atoms = off[n_sys]; stats->n_chunks = (int64_t)bounds.size() - 1;
+        stats->n_launches = n_launch;
+    }
+    tm.finish(stats);
+    if (bounds.size() != 2) c->hidden_atoms = 0;       // hidden state only meaningful for single-chunk calls
+    return EPNN_OK;
+}
+
+extern "C" int epnn_infer_batch(epnn_ctx* c, int64_t n_sys, const int32_t* off, const float* xyz, const int32_t* species,
+                                const float* Q, const int32_t* npad, float* q_out, double* q_out64, epnn_stats* stats) {
+    return infer_impl(c, n_sys, off, true, xyz, species, Q, npad, q_out, q_out64, stats);
+}
+
+extern "C" int epnn_infer_batch_dev(epnn_ctx* c, int64_t n_sys, const int32_t* off_host, const float* xyz_dev,
+                                    const int32_t* species_dev, const float* Q_dev, const int32_t* npad_host,
+                                    float* q_out_dev, double* q_out64_dev, epnn_stats* stats) {
+    return infer_impl(c, n_sys, off_host, false, xyz_dev, species_dev, Q_dev, npad_host, q_out_dev, q_out64_dev, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int epnn_neighbors(epnn_ctx* c, int64_t n_sys, const int32_t* off, const float* xyz, int which,
+                              int32_t* rowptr, int32_t* col, int64_t col_capacity, int64_t* nnz_out) {
+    if (!c) return EPNN_E_INVALID;
+    int rc = validate_offsets(c, n_sys, off);
+    if (rc != EPNN_OK) return rc;
+    if (!rowptr || !nnz_out || (which != 0 && which != 1)) return fail(c, EPNN_E_INVALID, "bad argument to epnn_neighbors");
+    *nnz_out = 0;
+    rowptr[0] = 0;
+    if (n_sys == 0) return EPNN_OK;
+    if (!xyz) return fail(c, EPNN_E_INVALID, "xyz is NULL");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    std::vector<int64_t> bounds;
+    plan_chunks(off, n_sys, c->chunk_atoms, bounds);
+    Timer tm{false, st, {}, {}};
+    int n_launch = 0;
+    int64_t written = 0;
+    bool overflow = false;
+    std::vector<int> h_rowptr, h_col, h_pid;
+    std::vector<unsigned char> h_near;
+    for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
+        const int64_t s0 = bounds[ci], s1 = bounds[ci + 1];
+        const int ns = (int)(s1 - s0), a0 = off[s0], na = off[s1] - off[s0];
+        void* p;
+        if ((rc = ensure(c, B_OFFIN, sizeof(int) * ((size_t)ns + 1) * 2 + 64, &p)) != EPNN_OK) return rc;
+        int* d_off = (int*)p;
+        CU(c, cudaMemcpyAsync(d_off, off + s0, sizeof(int) * ((size_t)ns + 1), cudaMemcpyHostToDevice, st));
+        float* bx; int* bs; float* bq;
+        if ((rc = ensure(c, B_XYZ, sizeof(float) * 3 * (size_t)na, &p)) != EPNN_OK) return rc; bx = (float*)p;
+        if ((rc = ensure(c, B_SPECIES, sizeof(int) * (size_t)na, &p)) != EPNN_OK) return rc; bs = (int*)p;
+        if ((rc = ensure(c, B_Q, sizeof(float) * (size_t)ns, &p)) != EPNN_OK) return rc; bq = (float*)p;
+        CU(c, cudaMemcpyAsync(bx, xyz + 3 * (size_t)a0, sizeof(float) * 3 * (size_t)na, cudaMemcpyHostToDevice, st));
+        CU(c, cudaMemsetAsync(bs, 0, sizeof(int) * (size_t)na, st));
+        CU(c, cudaMemsetAsync(bq, 0, sizeof(float) * (size_t)ns, st));
+        Workspace w;
+        rc = run_chunk<float>(c, ns, na, d_off, a0, bx, bs, bq, nullptr, nullptr, nullptr, nullptr, tm, &n_launch, true, &w);
+        if (rc != EPNN_OK) return rc;
+        h_rowptr.resize((size_t)na + 1); h_col.resize((size_t)w.nnz + 1); h_pid.resize((size_t)w.nnz + 1); h_near.resize((size_t)w.P + 1);
+        CU(c, cudaMemcpyAsync(h_rowptr.data(), w.rowptr, sizeof(int) * ((size_t)na + 1), cudaMemcpyDeviceToHost, st));
+        if (w.nnz) {
+            CU(c, cudaMemcpyAsync(h_col.data(), w.col, sizeof(int) * (size_t)w.nnz, cudaMemcpyDeviceToHost, st));
+            CU(c, cudaMemcpyAsync(h_pid.data(), w.pid, sizeof(int) * (size_t)w.nnz, cudaMemcpyDeviceToHost, st));
+            CU(c, cudaMemcpyAsync(h_near.data(), w.near, (size_t)w.P, cudaMemcpyDeviceToHost, st));
+        }
+        CU(c, cudaStreamSynchronize(st));
+        for (int i = 0; i < na; ++i) {
+            for (int k = h_rowptr[i]; k < h_rowptr[i + 1]; ++k) {
+                if (which == 0 && !h_near[h_pid[k]]) continue;
+                if (written < col_capacity && col) col[written] = h_col[k] + a0; else overflow = true;
+                ++written;
+            }
+            rowptr[(size_t)a0 + i + 1] = (int32_t)written;
+        }
+    }
+    *nnz_out = written;
+    if (overflow) return fail(c, EPNN_E_CAPACITY, "col_capacity %lld too small for %lld entries", (long long)col_capacity, (long long)written);
+    return EPNN_OK;
+}
+
+extern "C" int epnn_init_edges(epnn_ctx* c, int32_t n, const float* xyz, float* e_out) {
+    if (!c) return EPNN_E_INVALID;
+    if (n < 0 || (n > 0 && (!xyz || !e_out))) return fail(c, EPNN_E_INVALID, "bad argument to epnn_init_edges");
+    if (n == 0) return EPNN_OK;
+    CU(c, cudaSetDevice(c->device));
+    void* p; int rc;
+    if ((rc = ensure(c, B_XYZ, sizeof(float) * 3 * (size_t)n, &p)) != EPNN_OK) return rc;
+    float* dx = (float*)p;
+    const size_t tot = (size_t)n * n * ED;
+    if ((rc = ensure(c, B_E, sizeof(float) * tot, &p)) != EPNN_OK) return rc;
+    float* de = (float*)p;
+    CU(c, cudaMemcpyAsync(dx, xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CU(c, launch_edges_dense(n, dx, de, c->stream));
+    CU(c, cudaMemcpyAsync(e_out, de, sizeof(float) * tot, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return EPNN_OK;
+}
+
+__global__ void d2f_kernel(const double* in, float* out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+extern "C" int epnn_get_hidden(epnn_ctx* c, float* h_out, int64_t n_floats) {
+    if (!c || !h_out) return EPNN_E_INVALID;
+    if (c->hidden_atoms == 0) return fail(c, EPNN_E_INVALID, "no hidden state retained (needs a preceding single-chunk epnn_infer_batch)");
+    if (n_floats != c->hidden_atoms * HD) return fail(c, EPNN_E_INVALID, "expected %lld floats", (long long)(c->hidden_atoms * HD));
+    CU(c, cudaSetDevice(c->device));
+    if (c->hidden_precision == 32) {
+        CU(c, cudaMemcpy(h_out, c->bufs[B_H].p, sizeof(float) * (size_t)n_floats, cudaMemcpyDeviceToHost));
+    } else {
+        void* p; int rc;
+        if ((rc = ensure(c, B_OUT32, sizeof(float) * (size_t)n_floats, &p)) != EPNN_OK) return rc;
+        d2f_kernel<<<div_up(n_floats, 256), 256, 0, c->stream>>>((const double*)c->bufs[B_H].p, (float*)p, n_floats);
+        CU(c, cudaGetLastError());
+        CU(c, cudaMemcpyAsync(h_out, p, sizeof(float) * (size_t)n_floats, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    return EPNN_OK;
+}
+
+// Implemented in epnn_dense.cu once the compat kernels land; until then fail loudly (never silently fall back).
+extern "C" int epnn_infer_dense(epnn_ctx* c, int32_t B, int32_t N, const float* h, const float* e, const float* x,
+                                const float* q, const float* mask, float* q_out) {
+    (void)B; (void)N; (void)h; (void)e; (void)x; (void)q; (void)mask; (void)q_out;
+    return fail(c, EPNN_E_UNSUPPORTED, "epnn_infer_dense is not implemented yet");
+}

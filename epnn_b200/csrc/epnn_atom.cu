@@ -1,0 +1,259 @@
+// Per-atom kernel: everything between two pair kernels, fused.
+//
+//   ATOM_UPDATE  finishes message-passing step t (reference charge_gn.py:70-74):
+//                  M_i = W3^T S_i + npad * b3        (linear last message layer hoisted out of sum_j)
+//                  h_i = update_fn([h_i | M_i])      80 -> 32 relu -> 32 relu -> 48
+//                (node_mask is 1 for every atom that exists here; padded atoms are never materialised)
+//   ATOM_QUPDATE finishes electron-passing pass t (charge_gn.py:116-118):
+//                  q_i += sum over the CSR row of i, in column order, of sign(j - i) * delta_pair
+//                fixed order, FP64, no atomics: deterministic, and sum_i q_i is conserved by construction.
+//   ATOM_PROJECT first-layer projections for the next pair kernel:
+//                  u_i = A^T [x_i|h_i|q_i],  v_i = B^T [x_i|h_i|q_i] + b1
+//                with the one-hot x part folded into a per-species table.
+//   ATOM_OUTPUT  q -> float32 / float64 output buffers.
+//
+// Work unit = one warp on a tile of 32 consecutive atoms; the dense layers run through tile_gemm.
+#include "epnn_internal.cuh"
+
+template <typename R> struct AtomArgs {
+    int n_atoms, mode, nsplit, h_is_zero;
+    const int* atom_sys; const int* sys_off; const int* npad; const int* species;
+    const R* Spart; R* h; const R* W3; const R* b3; UpdW<R> upd;
+    const int* rowptr; const int* col; const int* pid; const R* delta; double* q;
+    const R* Ah64; const R* Aq64; const R* Ax64; R* u; R* v;
+    float* q_out; double* q_out64;
+};
+
+#define ATOM_W_UPD (HID * HID + HID + UPD_IN * HID + HID + HID * HID + HID + HID * HD + HD)   // 6288
+#define ATOM_W_PROJ (HD * 64 + 64 + MAX_SPECIES * 64)                                       // 4160
+#define ATOM_TILE (32 * UPD_IN + 32 * HID)                                                  // 3584 per warp
+
+template <typename R, int NW>
+__global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    R* sW3 = reinterpret_cast<R*>(smem_raw);   // [32][32]
+    R* sb3 = sW3 + HID * HID;                  // [32]
+    R* sU1 = sb3 + HID;                        // [80][32]
+    R* sc1 = sU1 + UPD_IN * HID;               // [32]
+    R* sU2 = sc1 + HID;                        // [32][32]
+    R* sc2 = sU2 + HID * HID;                  // [32]
+    R* sU3 = sc2 + HID;                        // [32][48]
+    R* sc3 = sU3 + HID * HD;                   // [48]
+    R* sAh = sc3 + HD;                         // [48][64]
+    R* sAq = sAh + HD * 64;                    // [64]
+    R* sAx = sAq + 64;                         // [MAX_SPECIES][64]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    R* T80 = sAx + MAX_SPECIES * 64 + warp * ATOM_TILE;    // [32][80]; later [32][48] + [32][32]
+    R* T32 = T80 + 32 * UPD_IN;                            // [32][32]
+    R* T32b = T80 + 32 * HD;                               // aliases the tail of T80 once U1 has been applied
+    R* slot_q = sAx + MAX_SPECIES * 64 + NW * ATOM_TILE + warp * 64;   // [32]
+    R* slot_np = slot_q + 32;                                         // [32] npad as real
+    int* slot_sp = reinterpret_cast<int*>(sAx + MAX_SPECIES * 64 + NW * ATOM_TILE + NW * 64) + warp * 64;   // [32]
+    int* slot_ns = slot_sp + 32;                                      // [32] number of S partial planes
+
+    const bool do_upd = a.mode & ATOM_UPDATE, do_q = a.mode & ATOM_QUPDATE, do_proj = a.mode & ATOM_PROJECT;
+    if (do_upd) {
+        for (int t = threadIdx.x; t < HID * HID; t += NW * 32) { sW3[t] = a.W3[t]; sU2[t] = a.upd.U2[t]; }
+        for (int t = threadIdx.x; t < UPD_IN * HID; t += NW * 32) sU1[t] = a.upd.U1[t];
+        for (int t = threadIdx.x; t < HID * HD; t += NW * 32) sU3[t] = a.upd.U3[t];
+        if (threadIdx.x < HID) { sb3[threadIdx.x] = a.b3[threadIdx.x]; sc1[threadIdx.x] = a.upd.c1[threadIdx.x]; sc2[threadIdx.x] = a.upd.c2[threadIdx.x]; }
+        if (threadIdx.x < HD) sc3[threadIdx.x] = a.upd.c3[threadIdx.x];
+    }
+    if (do_proj) {
+        for (int t = threadIdx.x; t < HD * 64; t += NW * 32) sAh[t] = a.Ah64[t];
+        for (int t = threadIdx.x; t < MAX_SPECIES * 64; t += NW * 32) sAx[t] = a.Ax64[t];
+        if (threadIdx.x < 64) sAq[threadIdx.x] = a.Aq64[threadIdx.x];
+    }
+    __syncthreads();
+
+    const int pg = lane >> 3, og = lane & 7;
+    const int n_tiles = (a.n_atoms + 31) / 32;
+    R acc[8][4];
+
+    for (int tile = blockIdx.x * NW + warp; tile < n_tiles; tile += gridDim.x * NW) {
+        const int base = tile * 32;
+        const int me = base + lane;
+        const bool me_ok = me < a.n_atoms;
+        // ---------------- per-slot scalars (lane = slot)
+        {
+            int sp = 0, ns = 1; R npf = R(0);
+            double qv = 0.0;
+            if (me_ok) {
+                const int sys = a.atom_sys[me];
+                const int nat = a.sys_off[sys + 1] - a.sys_off[sys];
+                sp = a.species[me];
+                ns = nat > SMALL_MAX ? a.nsplit : 1;
+                npf = (R)a.npad[sys];
+                qv = a.q[me];
+                if (do_q) {
+                    const int r0 = a.rowptr[me], r1 = a.rowptr[me + 1];
+                    for (int k = r0; k < r1; ++k) {          // fixed (ascending column) order
+                        const double d = (double)a.delta[a.pid[k]];
+                        qv += a.col[k] > me ? d : -d;
+                    }
+                    a.q[me] = qv;
+                }
+                if (a.mode & ATOM_OUTPUT) {
+                    if (a.q_out) a.q_out[me] = (float)qv;
+                    if (a.q_out64) a.q_out64[me] = qv;
+                }
+            }
+            slot_sp[lane] = sp; slot_ns[lane] = ns; slot_np[lane] = npf; slot_q[lane] = (R)qv;
+        }
+        __syncwarp();
+        if (!do_upd && !do_proj) continue;
+
+        if (do_upd) {
+            // (1) S tile (sum of the partial planes in fixed order)
+#pragma unroll 2
+            for (int f = lane; f < 32 * (HID / 4); f += 32) {
+                const int sl = f >> 3, ch = f & 7;
+                const int at = base + sl;
+                Vec4<R> sv = vzero<R>();
+                if (at < a.n_atoms) {
+                    const int ns = slot_ns[sl];
+                    for (int sp = 0; sp < ns; ++sp)
+                        sv = vadd(sv, ldv(a.Spart + ((int64_t)sp * a.n_atoms + at) * HID + ch * 4));
+                }
+                stv(T32 + tile_off(sl, ch, HID), sv);
+            }
+            // (3a) h part of the [h | M] tile
+#pragma unroll 4
+            for (int f = lane; f < 32 * (HD / 4); f += 32) {
+                const int sl = f / (HD / 4), ch = f - sl * (HD / 4);
+                const int at = base + sl;
+                Vec4<R> hv = vzero<R>();
+                if (at < a.n_atoms) hv = ldv(a.h + (int64_t)at * HD + ch * 4);
+                stv(T80 + tile_off(sl, ch, UPD_IN), hv);
+            }
+            __syncwarp();
+            // (2) M = W3^T S + npad * b3
+            zero_acc(acc);
+            tile_gemm<R, HID, HID>(T32, sW3, og * 4, acc, pg);
+            {
+                const Vec4<R> b3v = ldv(sb3 + og * 4);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const R np = slot_np[pg * 8 + s];
+                    Vec4<R> m;
+                    m.x = fma(np, b3v.x, acc[s][0]); m.y = fma(np, b3v.y, acc[s][1]);
+                    m.z = fma(np, b3v.z, acc[s][2]); m.w = fma(np, b3v.w, acc[s][3]);
+                    stv(T80 + tile_off(pg * 8 + s, HD / 4 + og, UPD_IN), m);      // (3b) M part
+                }
+            }
+            __syncwarp();
+            // (4) layer 1: 80 -> 32, relu
+            zero_acc(acc);
+            tile_gemm<R, UPD_IN, HID>(T80, sU1, og * 4, acc, pg);
+            {
+                const Vec4<R> cv = ldv(sc1 + og * 4);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    Vec4<R> z; z.x = relu(acc[s][0] + cv.x); z.y = relu(acc[s][1] + cv.y); z.z = relu(acc[s][2] + cv.z); z.w = relu(acc[s][3] + cv.w);
+                    stv(T32 + tile_off(pg * 8 + s, og, HID), z);
+                }
+            }
+            __syncwarp();
+            // (5) layer 2: 32 -> 32, relu   (T80 is dead now; T32b aliases its tail)
+            zero_acc(acc);
+            tile_gemm<R, HID, HID>(T32, sU2, og * 4, acc, pg);
+            {
+                const Vec4<R> cv = ldv(sc2 + og * 4);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    Vec4<R> z; z.x = relu(acc[s][0] + cv.x); z.y = relu(acc[s][1] + cv.y); z.z = relu(acc[s][2] + cv.z); z.w = relu(acc[s][3] + cv.w);
+                    stv(T32b + tile_off(pg * 8 + s, og, HID), z);
+                }
+            }
+            __syncwarp();
+            // (6) layer 3: 32 -> 48, linear; columns 0..31 then 32..47 (computed by every og, written by og < 4)
+            zero_acc(acc);
+            tile_gemm<R, HID, HD>(T32b, sU3, og * 4, acc, pg);
+            {
+                const Vec4<R> cv = ldv(sc3 + og * 4);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    Vec4<R> hv; hv.x = acc[s][0] + cv.x; hv.y = acc[s][1] + cv.y; hv.z = acc[s][2] + cv.z; hv.w = acc[s][3] + cv.w;
+                    const int at = base + pg * 8 + s;
+                    if (at < a.n_atoms) stv(a.h + (int64_t)at * HD + og * 4, hv);
+                    stv(T80 + tile_off(pg * 8 + s, og, HD), hv);           // [32][48] tile for the projection
+                }
+            }
+            zero_acc(acc);
+            tile_gemm<R, HID, HD>(T32b, sU3, HID + (og & 3) * 4, acc, pg);
+            if (og < 4) {
+                const Vec4<R> cv = ldv(sc3 + HID + og * 4);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    Vec4<R> hv; hv.x = acc[s][0] + cv.x; hv.y = acc[s][1] + cv.y; hv.z = acc[s][2] + cv.z; hv.w = acc[s][3] + cv.w;
+                    const int at = base + pg * 8 + s;
+                    if (at < a.n_atoms) stv(a.h + (int64_t)at * HD + HID + og * 4, hv);
+                    stv(T80 + tile_off(pg * 8 + s, 8 + og, HD), hv);
+                }
+            }
+            __syncwarp();
+        } else if (do_proj && !a.h_is_zero) {
+#pragma unroll 4
+            for (int f = lane; f < 32 * (HD / 4); f += 32) {
+                const int sl = f / (HD / 4), ch = f - sl * (HD / 4);
+                const int at = base + sl;
+                Vec4<R> hv = vzero<R>();
+                if (at < a.n_atoms) hv = ldv(a.h + (int64_t)at * HD + ch * 4);
+                stv(T80 + tile_off(sl, ch, HD), hv);
+            }
+            __syncwarp();
+        }
+
+        if (do_proj) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {           // half 0 -> u (a_i block), half 1 -> v (a_j block, + b1)
+                zero_acc(acc);
+                if (!a.h_is_zero) tile_gemm<R, HD, 64>(T80, sAh, half * HID + og * 4, acc, pg);
+                const Vec4<R> aq = ldv(sAq + half * HID + og * 4);
+                R* dst = half == 0 ? a.u : a.v;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int at = base + pg * 8 + s;
+                    if (at < a.n_atoms) {
+                        const Vec4<R> ax = ldv(sAx + slot_sp[pg * 8 + s] * 64 + half * HID + og * 4);
+                        const R qv = slot_q[pg * 8 + s];
+                        Vec4<R> o;
+                        o.x = acc[s][0] + fma(qv, aq.x, ax.x); o.y = acc[s][1] + fma(qv, aq.y, ax.y);
+                        o.z = acc[s][2] + fma(qv, aq.z, ax.z); o.w = acc[s][3] + fma(qv, aq.w, ax.w);
+                        stv(dst + (int64_t)at * HID + og * 4, o);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <typename R>
+cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd, const StepW<R>* next,
+                        int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl) {
+    if (w.n_atoms == 0) return cudaSuccess;
+    constexpr int NW = sizeof(R) == 4 ? 8 : 4;
+    AtomArgs<R> aa;
+    memset(&aa, 0, sizeof(aa));
+    aa.n_atoms = w.n_atoms; aa.mode = mode; aa.nsplit = w.nsplit; aa.h_is_zero = h_is_zero;
+    aa.atom_sys = w.atom_sys; aa.sys_off = w.sys_off; aa.npad = w.npad; aa.species = w.species;
+    aa.Spart = (const R*)w.S; aa.h = (R*)w.h;
+    if (mode & ATOM_UPDATE) { aa.W3 = prev->W3; aa.b3 = prev->b3; aa.upd = *upd; }
+    aa.rowptr = w.rowptr; aa.col = w.col; aa.pid = w.pid; aa.delta = (const R*)w.delta; aa.q = w.q;
+    if (mode & ATOM_PROJECT) { aa.Ah64 = next->Ah64; aa.Aq64 = next->Aq64; aa.Ax64 = next->Ax64; }
+    aa.u = (R*)w.u; aa.v = (R*)w.v; aa.q_out = q_out; aa.q_out64 = q_out64;
+    const size_t smem = sizeof(R) * (ATOM_W_UPD + ATOM_W_PROJ + (size_t)NW * ATOM_TILE + NW * 64) + sizeof(int) * NW * 64;
+    cudaError_t e = cudaFuncSetAttribute(atom_kernel<R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int grid = div_up(div_up(w.n_atoms, 32), NW);
+    if (grid > w.sm_count) grid = w.sm_count;
+    atom_kernel<R, NW><<<grid, NW * 32, smem, st>>>(aa);
+    ++*nl;
+    return cudaGetLastError();
+}
+
+template cudaError_t launch_atom<float>(const Workspace&, int, const StepW<float>*, const UpdW<float>*, const StepW<float>*,
+                                        int, float*, double*, cudaStream_t, int*);
+template cudaError_t launch_atom<double>(const Workspace&, int, const StepW<double>*, const UpdW<double>*, const StepW<double>*,
+                                         int, float*, double*, cudaStream_t, int*);

@@ -1,0 +1,266 @@
+// Message-passing pair kernel of the GNN layer.
+//
+// Replaces, per step t, reference charge_gn.py:62-70 (GNN_layer.call): build the (N*N, K) pair-input
+// tensor, run message_fns[t] on ALL N^2 pairs and reduce_sum over j without a mask.  Here, exactly
+// (SURVEY.md 7.2):
+//     S_i = sum_{j real, incl. j = i} relu(W2^T relu(u_i + v_j + C^T e_ij) + b2)
+//           + (npad - n) * relu(W2^T relu(u_i + b1) + b2)            (padded atoms: a_j = 0, e = 0)
+// with u = A^T a, v = B^T a + b1 from the per-atom kernel and C^T e_ij only for pairs with e != 0.
+// The linear last layer (W3, b3) is applied per atom afterwards (epnn_atom.cu).
+//
+// Work unit = one warp on a "row group" of 4 consecutive atoms i of one system.  A tile is
+// 4 rows x 8 j-slots = 32 pair slots; thread (pg, og) owns row pg and hidden columns og*4..og*4+3,
+// so the sum over j stays in registers (FP64 accumulators) and is written once: no atomics, fixed order.
+//   near phase : 8 CSR neighbours per row at a time; C^T e via tile_gemm<48>, then tile_gemm<32>
+//   far phase  : SMALL systems (n <= 64): the complement of the row's neighbour bitmask (incl. self) and
+//                the weighted pad slot, 8 at a time;  LARGE systems: 8 consecutive j with e != 0 members
+//                masked out, the j range optionally split across warps (partial sums, fixed order).
+#include "epnn_internal.cuh"
+
+template <typename R> struct GnnArgs {
+    const int* rg_atom; int n_units; int nsplit; int n_atoms;
+    const int* atom_sys; const int* sys_off; const int* npad;
+    const int* rowptr; const int* col; const int* pid;
+    const float* e;
+    const R* u; const R* v;
+    const R* Cw; const R* W2; const R* b2; const R* b1;
+    R* S;
+};
+
+__device__ __forceinline__ int kth_set_bit64(unsigned long long m, int k) {   // k-th (0-based) set bit; k < popc(m)
+    const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+    const int pl = __popc(lo);
+    return k < pl ? (int)__fns(lo, 0, k + 1) : 32 + (int)__fns(hi, 0, k - pl + 1);
+}
+
+template <typename R, bool LARGE, int NW>
+__global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kernel(const GnnArgs<R> a) {
+    extern __shared__ __align__(32) unsigned char smem_raw[];
+    R* sC = reinterpret_cast<R*>(smem_raw);          // [48][32]
+    R* sW2 = sC + ED * HID;                          // [32][32]
+    R* sb2 = sW2 + HID * HID;                        // [32]
+    R* sb1 = sb2 + HID;                              // [32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    R* at1 = sb1 + HID + warp * (32 * ED + 32 * HID);   // [32][48] swizzled
+    R* at2 = at1 + 32 * ED;                             // [32][32] swizzled
+    int* slot_j = reinterpret_cast<int*>(sb1 + HID + NW * (32 * ED + 32 * HID)) + warp * 64;
+    int* slot_p = slot_j + 32;
+
+    for (int t = threadIdx.x; t < ED * HID; t += NW * 32) sC[t] = a.Cw[t];
+    for (int t = threadIdx.x; t < HID * HID; t += NW * 32) sW2[t] = a.W2[t];
+    if (threadIdx.x < HID) { sb2[threadIdx.x] = a.b2[threadIdx.x]; sb1[threadIdx.x] = a.b1[threadIdx.x]; }
+    __syncthreads();
+
+    const int pg = lane >> 3, og = lane & 7;
+    const Vec4<R> b2v = ldv(sb2 + og * 4);
+    const Vec4<R> b1v = ldv(sb1 + og * 4);
+
+    for (int unit = blockIdx.x * NW + warp; unit < a.n_units; unit += gridDim.x * NW) {
+        const int rg = LARGE ? unit / a.nsplit : unit;
+        const int split = LARGE ? unit - rg * a.nsplit : 0;
+        const int i0 = a.rg_atom[rg];
+        const int sys = a.atom_sys[i0];
+        const int a0 = a.sys_off[sys], a1 = a.sys_off[sys + 1];
+        const int n = a1 - a0;
+        const int padn = a.npad[sys] - n;
+        const bool rowok = i0 + pg < a1;
+        const int i = rowok ? i0 + pg : i0;
+        const int rp0 = a.rowptr[i];
+        const int rp1 = rowok ? a.rowptr[i + 1] : rp0;
+        const int deg = rp1 - rp0;
+        const Vec4<R> ur = rowok ? ldv(a.u + (int64_t)i * HID + og * 4) : vzero<R>();
+        double rs0 = 0.0, rs1 = 0.0, rs2 = 0.0, rs3 = 0.0;
+        R acc[8][4];
+
+        // ---------------------------------------------------------------- near phase
+        if (split == 0) {
+            int maxdeg = deg;
+            maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, 8));
+            maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, 16));
+            for (int b0 = 0; b0 < maxdeg; b0 += 8) {
+                {
+                    const int k = b0 + og;
+                    int j = -2, p = -1;
+                    if (k < deg) { j = a.col[rp0 + k]; p = a.pid[rp0 + k]; }
+                    slot_j[lane] = j; slot_p[lane] = p;
+                }
+                __syncwarp();
+#pragma unroll 4
+                for (int f = lane; f < 32 * (ED / 4); f += 32) {       // stage e rows, 12 chunks per slot
+                    const int sl = f / (ED / 4), ch = f - sl * (ED / 4);
+                    const int pp = slot_p[sl];
+                    Vec4<R> ev = vzero<R>();
+                    if (pp >= 0) ev = cvt4<R>(__ldg(reinterpret_cast<const float4*>(a.e + (int64_t)pp * ED) + ch));
+                    stv(at1 + tile_off(sl, ch, ED), ev);
+                }
+                __syncwarp();
+                zero_acc(acc);
+                tile_gemm<R, ED, HID>(at1, sC, og * 4, acc, pg);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int jj = slot_j[pg * 8 + s];
+                    Vec4<R> z = vzero<R>();
+                    if (jj >= 0) {
+                        const Vec4<R> vj = ldv(a.v + (int64_t)jj * HID + og * 4);
+                        z.x = relu(acc[s][0] + ur.x + vj.x); z.y = relu(acc[s][1] + ur.y + vj.y);
+                        z.z = relu(acc[s][2] + ur.z + vj.z); z.w = relu(acc[s][3] + ur.w + vj.w);
+                    }
+                    stv(at2 + tile_off(pg * 8 + s, og, HID), z);
+                }
+                __syncwarp();
+                zero_acc(acc);
+                tile_gemm<R, HID, HID>(at2, sW2, og * 4, acc, pg);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    if (slot_j[pg * 8 + s] >= 0) {
+                        rs0 += (double)relu(acc[s][0] + b2v.x); rs1 += (double)relu(acc[s][1] + b2v.y);
+                        rs2 += (double)relu(acc[s][2] + b2v.z); rs3 += (double)relu(acc[s][3] + b2v.w);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---------------------------------------------------------------- far phase
+        if (!LARGE) {
+            unsigned long long emask = 0ull;
+            for (int k = rp0; k < rp1; ++k) emask |= 1ull << (a.col[k] - a0);
+            const unsigned long long all = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
+            const unsigned long long farm = rowok ? (~emask & all) : 0ull;     // includes the self pair
+            const int nfar = __popcll(farm);
+            const bool has_pad = rowok && padn > 0;
+            int maxslots = nfar + (has_pad ? 1 : 0);
+            maxslots = max(maxslots, __shfl_xor_sync(0xffffffffu, maxslots, 8));
+            maxslots = max(maxslots, __shfl_xor_sync(0xffffffffu, maxslots, 16));
+            const R padw = (R)padn;
+            for (int b0 = 0; b0 < maxslots; b0 += 8) {
+                {
+                    const int k = b0 + og;
+                    int j = -2;
+                    if (k < nfar) j = a0 + kth_set_bit64(farm, k);
+                    else if (k == nfar && has_pad) j = -1;
+                    slot_j[lane] = j;
+                }
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int jj = slot_j[pg * 8 + s];
+                    Vec4<R> z = vzero<R>();
+                    if (jj >= -1) {
+                        const Vec4<R> vj = jj >= 0 ? ldv(a.v + (int64_t)jj * HID + og * 4) : b1v;
+                        z.x = relu(ur.x + vj.x); z.y = relu(ur.y + vj.y); z.z = relu(ur.z + vj.z); z.w = relu(ur.w + vj.w);
+                    }
+                    stv(at2 + tile_off(pg * 8 + s, og, HID), z);
+                }
+                __syncwarp();
+                zero_acc(acc);
+                tile_gemm<R, HID, HID>(at2, sW2, og * 4, acc, pg);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int jj = slot_j[pg * 8 + s];
+                    if (jj >= -1) {
+                        const R wgt = jj >= 0 ? R(1) : padw;
+                        rs0 += (double)(wgt * relu(acc[s][0] + b2v.x)); rs1 += (double)(wgt * relu(acc[s][1] + b2v.y));
+                        rs2 += (double)(wgt * relu(acc[s][2] + b2v.z)); rs3 += (double)(wgt * relu(acc[s][3] + b2v.w));
+                    }
+                }
+                __syncwarp();
+            }
+        } else {
+            int clen = (n + a.nsplit - 1) / a.nsplit;
+            clen = (clen + 7) & ~7;
+            const int jlo = min(a1, a0 + split * clen), jhi = min(a1, jlo + clen);
+            int ptr = rp0;
+            while (ptr < rp1 && a.col[ptr] < jlo) ++ptr;
+            for (int jb = jlo; jb < jhi; jb += 8) {
+                unsigned m = 0u;
+                while (ptr < rp1 && a.col[ptr] < jb + 8) { m |= 1u << (a.col[ptr] - jb); ++ptr; }
+                unsigned okm = 0u;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const int j = jb + s;
+                    const bool ok = rowok && j < jhi && !((m >> s) & 1u);
+                    Vec4<R> z = vzero<R>();
+                    if (ok) {
+                        okm |= 1u << s;
+                        const Vec4<R> vj = ldv(a.v + (int64_t)j * HID + og * 4);
+                        z.x = relu(ur.x + vj.x); z.y = relu(ur.y + vj.y); z.z = relu(ur.z + vj.z); z.w = relu(ur.w + vj.w);
+                    }
+                    stv(at2 + tile_off(pg * 8 + s, og, HID), z);
+                }
+                __syncwarp();
+                zero_acc(acc);
+                tile_gemm<R, HID, HID>(at2, sW2, og * 4, acc, pg);
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    if ((okm >> s) & 1u) {
+                        rs0 += (double)relu(acc[s][0] + b2v.x); rs1 += (double)relu(acc[s][1] + b2v.y);
+                        rs2 += (double)relu(acc[s][2] + b2v.z); rs3 += (double)relu(acc[s][3] + b2v.w);
+                    }
+                }
+                __syncwarp();
+            }
+            if (split == 0 && padn > 0) {           // weighted pad pseudo-pair, one slot per row
+                Vec4<R> z = vzero<R>();
+                if (rowok) { z.x = relu(ur.x + b1v.x); z.y = relu(ur.y + b1v.y); z.z = relu(ur.z + b1v.z); z.w = relu(ur.w + b1v.w); }
+#pragma unroll
+                for (int s = 0; s < 8; ++s) stv(at2 + tile_off(pg * 8 + s, og, HID), s == 0 ? z : vzero<R>());
+                __syncwarp();
+                zero_acc(acc);
+                tile_gemm<R, HID, HID>(at2, sW2, og * 4, acc, pg);
+                if (rowok) {
+                    const R wgt = (R)padn;
+                    rs0 += (double)(wgt * relu(acc[0][0] + b2v.x)); rs1 += (double)(wgt * relu(acc[0][1] + b2v.y));
+                    rs2 += (double)(wgt * relu(acc[0][2] + b2v.z)); rs3 += (double)(wgt * relu(acc[0][3] + b2v.w));
+                }
+                __syncwarp();
+            }
+        }
+
+        if (rowok) {
+            Vec4<R> out; out.x = (R)rs0; out.y = (R)rs1; out.z = (R)rs2; out.w = (R)rs3;
+            stv(a.S + ((int64_t)split * a.n_atoms + i) * HID + og * 4, out);
+        }
+    }
+}
+
+template <typename R> static size_t gnn_smem_bytes(int nw) {
+    return sizeof(R) * (ED * HID + HID * HID + 2 * HID + (size_t)nw * (32 * ED + 32 * HID)) + sizeof(int) * nw * 64;
+}
+
+template <typename R, bool LARGE, int NW>
+static cudaError_t launch_one(const GnnArgs<R>& ga, int sm_count, cudaStream_t st) {
+    const size_t smem = gnn_smem_bytes<R>(NW);
+    cudaError_t e = cudaFuncSetAttribute(gnn_pair_kernel<R, LARGE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int per_sm = sizeof(R) == 4 ? 2 : 1;
+    int grid = div_up(ga.n_units, NW);
+    if (grid > sm_count * per_sm) grid = sm_count * per_sm;      // persistent: warps stride over the units
+    gnn_pair_kernel<R, LARGE, NW><<<grid, NW * 32, smem, st>>>(ga);
+    return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* nl) {
+    GnnArgs<R> ga;
+    ga.n_atoms = w.n_atoms; ga.atom_sys = w.atom_sys; ga.sys_off = w.sys_off; ga.npad = w.npad;
+    ga.rowptr = w.rowptr; ga.col = w.col; ga.pid = w.pid; ga.e = w.e;
+    ga.u = (const R*)w.u; ga.v = (const R*)w.v; ga.Cw = sw.Cw; ga.W2 = sw.W2; ga.b2 = sw.b2; ga.b1 = sw.b1;
+    ga.S = (R*)w.S;
+    cudaError_t e = cudaSuccess;
+    if (w.n_rg_small > 0) {
+        ga.rg_atom = w.rg_small; ga.n_units = w.n_rg_small; ga.nsplit = 1;
+        e = launch_one<R, false, 8>(ga, w.sm_count, st);
+        ++*nl;
+        if (e != cudaSuccess) return e;
+    }
+    if (w.n_rg_large > 0) {
+        ga.rg_atom = w.rg_large; ga.n_units = w.n_rg_large * w.nsplit; ga.nsplit = w.nsplit;
+        e = launch_one<R, true, 8>(ga, w.sm_count, st);
+        ++*nl;
+    }
+    return e;
+}
+
+template cudaError_t launch_gnn_pair<float>(const Workspace&, const StepW<float>&, cudaStream_t, int*);
+template cudaError_t launch_gnn_pair<double>(const Workspace&, const StepW<double>&, cudaStream_t, int*);

@@ -1,0 +1,133 @@
+// Internal declarations shared by the translation units of libepnn_b200.so (not installed).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/epnn_b200.h"
+
+#define HID 32          // hidden width of message / pass MLPs
+#define HD 48           // h_dim
+#define ED 48           // e_dim
+#define UPD_IN 80       // [h | M]
+#define SMALL_MAX 64    // systems with n <= SMALL_MAX take the bitmask ("small") GNN path
+#define MAX_SPECIES 16
+
+// ------------------------------------------------------------------------------------------------
+// Vector of 4 reals: one LDS.128 / LDG.128 for float, two for double.
+template <typename R> struct alignas(4 * sizeof(R)) Vec4 { R x, y, z, w; };
+
+template <typename R> __device__ __forceinline__ Vec4<R> vzero() { Vec4<R> v; v.x = v.y = v.z = v.w = R(0); return v; }
+template <typename R> __device__ __forceinline__ Vec4<R> vadd(Vec4<R> a, Vec4<R> b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; return a; }
+template <typename R> __device__ __forceinline__ Vec4<R> vrelu(Vec4<R> a) {
+    a.x = a.x > R(0) ? a.x : R(0); a.y = a.y > R(0) ? a.y : R(0);
+    a.z = a.z > R(0) ? a.z : R(0); a.w = a.w > R(0) ? a.w : R(0); return a;
+}
+template <typename R> __device__ __forceinline__ R relu(R a) { return a > R(0) ? a : R(0); }
+template <typename R> __device__ __forceinline__ Vec4<R> ldv(const R* p) { return *reinterpret_cast<const Vec4<R>*>(p); }
+template <typename R> __device__ __forceinline__ void stv(R* p, Vec4<R> v) { *reinterpret_cast<Vec4<R>*>(p) = v; }
+template <typename R> __device__ __forceinline__ Vec4<R> cvt4(float4 f) { Vec4<R> v; v.x = R(f.x); v.y = R(f.y); v.z = R(f.z); v.w = R(f.w); return v; }
+
+// ------------------------------------------------------------------------------------------------
+// Warp-tile GEMM core used by every MLP kernel.
+//
+// One warp multiplies a tile of 32 rows ("slots": pairs or atoms) by a K x 32 weight block:
+//     acc[s][c] += sum_k  A[pg*8+s][k] * W[k][wcol+c]          s = 0..7, c = 0..3
+// Thread (pg = lane>>3, og = lane&7) owns rows pg*8..pg*8+7 and output columns wcol..wcol+3
+// (wcol = column base + og*4): an 8x4 register tile, 128 FMA per 12 LDS.128.
+//
+// The A tile lives in shared memory slot-major, row stride K, with the 4-float chunk index XOR-ed by
+// the row's pg (= row>>3): chunk' = chunk ^ (row>>3).  With that swizzle the four pg groups of a warp
+// read four different 16-byte bank groups (conflict-free), and the producers' 128-bit stores (8 lanes
+// of one pg covering 8 consecutive chunks of one row) are conflict-free as well.
+template <typename R, int K, int WLD>
+__device__ __forceinline__ void tile_gemm(const R* __restrict__ at, const R* __restrict__ W, int wcol,
+                                          R (&acc)[8][4], int pg) {
+    const R* arow = at + pg * 8 * K;
+#pragma unroll 2
+    for (int kc = 0; kc < K / 4; ++kc) {
+        const Vec4<R> w0 = ldv(W + (kc * 4 + 0) * WLD + wcol);
+        const Vec4<R> w1 = ldv(W + (kc * 4 + 1) * WLD + wcol);
+        const Vec4<R> w2 = ldv(W + (kc * 4 + 2) * WLD + wcol);
+        const Vec4<R> w3 = ldv(W + (kc * 4 + 3) * WLD + wcol);
+        const int kcs = (kc ^ pg) * 4;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const Vec4<R> a = ldv(arow + s * K + kcs);
+            acc[s][0] = fma(a.x, w0.x, acc[s][0]); acc[s][1] = fma(a.x, w0.y, acc[s][1]);
+            acc[s][2] = fma(a.x, w0.z, acc[s][2]); acc[s][3] = fma(a.x, w0.w, acc[s][3]);
+            acc[s][0] = fma(a.y, w1.x, acc[s][0]); acc[s][1] = fma(a.y, w1.y, acc[s][1]);
+            acc[s][2] = fma(a.y, w1.z, acc[s][2]); acc[s][3] = fma(a.y, w1.w, acc[s][3]);
+            acc[s][0] = fma(a.z, w2.x, acc[s][0]); acc[s][1] = fma(a.z, w2.y, acc[s][1]);
+            acc[s][2] = fma(a.z, w2.z, acc[s][2]); acc[s][3] = fma(a.z, w2.w, acc[s][3]);
+            acc[s][0] = fma(a.w, w3.x, acc[s][0]); acc[s][1] = fma(a.w, w3.y, acc[s][1]);
+            acc[s][2] = fma(a.w, w3.z, acc[s][2]); acc[s][3] = fma(a.w, w3.w, acc[s][3]);
+        }
+    }
+}
+
+template <typename R> __device__ __forceinline__ void zero_acc(R (&acc)[8][4]) {
+#pragma unroll
+    for (int s = 0; s < 8; ++s) { acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = R(0); }
+}
+
+// Address (in elements) of chunk `ch` of row `row` in a swizzled tile with row stride K.
+__device__ __forceinline__ int tile_off(int row, int ch, int K) { return row * K + ((ch ^ (row >> 3)) << 2); }
+
+// ------------------------------------------------------------------------------------------------
+// Device weight views (all row-major, precision R).  Built once in epnn_create.
+template <typename R> struct StepW {      // one message or pass MLP, first layer split per SURVEY 7.2
+    const R* Ah64;   // [48][64]  h-rows of the first layer:  cols 0..31 = a_i block (u), 32..63 = a_j block (v)
+    const R* Aq64;   // [64]      q-row
+    const R* Ax64;   // [MAX_SPECIES][64]  per-species x contribution, b1 folded into the v half
+    const R* Cw;     // [48][32]  e-rows
+    const R* b1;     // [32]      (v of a padded atom: a_j = 0, e = 0)
+    const R* W2;     // [32][32]
+    const R* b2;     // [32]
+    const R* W3;     // [32][32] (message) or [32] (pass)
+    const R* b3;     // [32] or [1]
+};
+template <typename R> struct UpdW {       // shared update MLP 80 -> 32 -> 32 -> 48
+    const R* U1; const R* c1; const R* U2; const R* c2; const R* U3; const R* c3;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Per-chunk device workspace (pointers into grow-only buffers owned by the ctx).
+struct Workspace {
+    int n_atoms, n_sys, sm_count;
+    int64_t nnz, P;                    // CSR entries of the e != 0 list; unordered pairs (nnz == 2P)
+    // inputs
+    const float* xyz; const int* species; const int* sys_off; const float* Qsys; const int* npad;
+    // derived
+    int* atom_sys;
+    int* deg; int* degU; int* rowptr; int* ustart; int* col; int* pid;
+    int* pair_i; int* pair_j; double* pair_D; float* e; unsigned char* near;
+    int* rg_small; int n_rg_small;     // first atom of every 4-row group of systems with n <= SMALL_MAX
+    int* rg_large; int n_rg_large; int nsplit;
+    void* h; void* S; void* u; void* v; void* delta;   // precision-dependent (float or double)
+    double* q;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Launchers (defined in the .cu files; every one enqueues on `st` and returns cudaGetLastError()).
+cudaError_t launch_prep(const Workspace& w, cudaStream_t st, int* n_launch);
+cudaError_t launch_nbr_count(const Workspace& w, cudaStream_t st, int* n_launch);
+cudaError_t launch_scan_i32(const int* in, int* out, int n, int* tmp, cudaStream_t st, int* n_launch);
+cudaError_t launch_nbr_fill(const Workspace& w, cudaStream_t st, int* n_launch);
+cudaError_t launch_edges_dense(int n, const float* xyz, float* e, cudaStream_t st);
+cudaError_t upload_rbf_centers(const double* mu);
+
+template <typename R> cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
+template <typename R> cudaError_t launch_epn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
+// mode bits for the per-atom kernel
+#define ATOM_UPDATE  1     // h <- update_fn([h | W3^T S + npad*b3])   (finishes a message-passing step)
+#define ATOM_QUPDATE 2     // q <- q + sum_j (+/-) delta               (finishes an electron-passing pass)
+#define ATOM_PROJECT 4     // u,v <- first-layer projections for the next pair kernel
+#define ATOM_OUTPUT  8     // write q to the output buffers
+template <typename R> cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd,
+                                              const StepW<R>* next, int h_is_zero, float* q_out, double* q_out64,
+                                              cudaStream_t st, int* n_launch);
+
+static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,273 @@
+// Neighbour list + radial descriptors.
+//
+// Replaces charge_gn.get_init_edges (reference charge_gn.py:122-163) and the is_near predicate of
+// EPN_layer.call (charge_gn.py:90-94).  The reference materialises dense (n,n,48) float64 tensors; here
+// the same arithmetic is evaluated only for pairs with D < 3.0 A (everything else is exactly zero):
+//
+//   D    = sqrt((dx^2 + dy^2) + dz^2)  in float64 from float32 coordinates, no FMA contraction
+//          (scipy.spatial.distance_matrix, charge_gn.py:124)
+//   C    = (cos(pi*D/3) + 1)/2, C = 0 for D >= 3, C = 1 for D <= 0, C_ii = 0        (:148-152)
+//   e_k  = float32(C * exp(-2 (D - mu_k)^2)),  mu = linspace(0.1, 3.0, 48)            (:123,153-161)
+//   near = max_k e_k > float32(1e-5)                                                  (:90-94)
+//
+// Output: CSR of the e != 0 set (rowptr/col ascending/pid) + per unordered pair (i<j): e[48], near flag.
+#include "epnn_internal.cuh"
+
+__constant__ double c_mu[ED];
+
+cudaError_t upload_rbf_centers(const double* mu) { return cudaMemcpyToSymbol(c_mu, mu, sizeof(double) * ED); }
+
+// float64 distance exactly as scipy computes it; intrinsics forbid FMA contraction.
+__device__ __forceinline__ double dist64(float xi, float yi, float zi, float xj, float yj, float zj) {
+    const double dx = fabs(__dsub_rn((double)xj, (double)xi));
+    const double dy = fabs(__dsub_rn((double)yj, (double)yi));
+    const double dz = fabs(__dsub_rn((double)zj, (double)zi));
+    const double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    return __dsqrt_rn(s);
+}
+
+// Cheap float32 reject: squared distance clearly above 9 (relative fp32 error of d2 is < 1e-6).
+__device__ __forceinline__ bool far_reject(float xi, float yi, float zi, float xj, float yj, float zj) {
+    const float dx = xj - xi, dy = yj - yi, dz = zj - zi;
+    return dx * dx + dy * dy + dz * dz > 9.001f;
+}
+
+__device__ __forceinline__ double cutoff_fn(double D) {
+    if (D >= 3.0) return 0.0;
+    if (D <= 0.0) return 1.0;
+    const double arg = __ddiv_rn(__dmul_rn(3.141592653589793, D), 3.0);
+    return __ddiv_rn(__dadd_rn(cos(arg), 1.0), 2.0);
+}
+
+__device__ __forceinline__ float rbf_value(double C, double D, int k) {
+    const double d = __dsub_rn(D, c_mu[k]);
+    const double g = exp(__dmul_rn(-2.0, __dmul_rn(d, d)));
+    return __double2float_rn(__dmul_rn(C, g));
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: atom -> system map (binary search over the offsets) and initial charges q0 = fl32(Q)/n.
+__global__ void prep_kernel(int n_atoms, int n_sys, const int* __restrict__ sys_off, const float* __restrict__ Qsys,
+                            int* __restrict__ atom_sys, double* __restrict__ q) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_atoms) return;
+    int lo = 0, hi = n_sys;                 // find s with off[s] <= i < off[s+1]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (sys_off[mid] <= i) lo = mid; else hi = mid;
+    }
+    atom_sys[i] = lo;
+    const int n = sys_off[lo + 1] - sys_off[lo];
+    q[i] = (double)__fdiv_rn(Qsys[lo], (float)n);      // charge_gn.py:337-338
+}
+
+cudaError_t launch_prep(const Workspace& w, cudaStream_t st, int* nl) {
+    if (w.n_atoms == 0) return cudaSuccess;
+    prep_kernel<<<div_up(w.n_atoms, 256), 256, 0, st>>>(w.n_atoms, w.n_sys, w.sys_off, w.Qsys, w.atom_sys, w.q);
+    ++*nl;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Brute-force (within a system) neighbour search: one thread per atom row, two passes (count, fill).
+// Columns come out ascending because j is scanned ascending.
+template <bool FILL>
+__global__ void nbr_kernel(int n_atoms, const int* __restrict__ atom_sys, const int* __restrict__ sys_off,
+                           const float* __restrict__ xyz, int* __restrict__ deg, int* __restrict__ degU,
+                           const int* __restrict__ rowptr, const int* __restrict__ ustart, int* __restrict__ col,
+                           int* __restrict__ pair_i, int* __restrict__ pair_j, double* __restrict__ pair_D) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_atoms) return;
+    const int s = atom_sys[i];
+    const int a0 = sys_off[s], a1 = sys_off[s + 1];
+    const float xi = xyz[3 * i], yi = xyz[3 * i + 1], zi = xyz[3 * i + 2];
+    int c = 0, cu = 0;
+    int wp = 0, wu = 0;
+    if (FILL) { wp = rowptr[i]; wu = ustart[i]; }
+    for (int j = a0; j < a1; ++j) {
+        if (j == i) continue;
+        const float xj = xyz[3 * j], yj = xyz[3 * j + 1], zj = xyz[3 * j + 2];
+        if (far_reject(xi, yi, zi, xj, yj, zj)) continue;
+        const double D = dist64(xi, yi, zi, xj, yj, zj);
+        if (D < 3.0) {
+            if (FILL) {
+                col[wp + c] = j;
+                if (j > i) { pair_i[wu + cu] = i; pair_j[wu + cu] = j; pair_D[wu + cu] = D; }
+            }
+            ++c;
+            cu += (j > i);
+        }
+    }
+    if (!FILL) { deg[i] = c; degU[i] = cu; }
+}
+
+cudaError_t launch_nbr_count(const Workspace& w, cudaStream_t st, int* nl) {
+    if (w.n_atoms == 0) return cudaSuccess;
+    nbr_kernel<false><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, w.deg, w.degU,
+                                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    ++*nl;
+    return cudaGetLastError();
+}
+
+// pid of every CSR entry: upper entries (j > i) are numbered ustart[i] + rank; lower entries (j < i)
+// look the pair up in row j's upper part (binary search; rows are sorted).
+__global__ void nbr_rev_kernel(int n_atoms, const int* __restrict__ rowptr, const int* __restrict__ ustart,
+                               const int* __restrict__ degU, const int* __restrict__ col, int* __restrict__ pid) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_atoms) return;
+    const int r0 = rowptr[i], r1 = rowptr[i + 1];
+    const int nlow = (r1 - r0) - degU[i];
+    for (int k = r0; k < r1; ++k) {
+        const int j = col[k];
+        if (k - r0 >= nlow) {
+            pid[k] = ustart[i] + (k - r0 - nlow);
+        } else {
+            const int jr1 = rowptr[j + 1];
+            int lo = jr1 - degU[j], hi = jr1 - 1;      // upper part of row j, must contain i
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (col[mid] < i) lo = mid + 1; else hi = mid;
+            }
+            pid[k] = ustart[j] + (lo - (jr1 - degU[j]));
+        }
+    }
+}
+
+// e[p][k] and near[p] for every unordered pair: 4 pairs x 48 centres per block of 192 threads.
+__global__ void edge_desc_kernel(int64_t P, const double* __restrict__ pair_D, float* __restrict__ e,
+                                 unsigned char* __restrict__ near) {
+    __shared__ int flag[4];
+    __shared__ double sC[4];
+    const int lp = threadIdx.x / ED, k = threadIdx.x - lp * ED;
+    const int64_t p = (int64_t)blockIdx.x * 4 + lp;
+    if (threadIdx.x < 4) flag[threadIdx.x] = 0;
+    double D = 0.0;
+    if (p < P) {
+        D = pair_D[p];
+        if (k == 0) sC[lp] = cutoff_fn(D);
+    }
+    __syncthreads();
+    if (p < P) {
+        const float ef = rbf_value(sC[lp], D, k);
+        e[p * ED + k] = ef;
+        if (ef > 1e-5f) flag[lp] = 1;          // benign race: every writer stores 1
+    }
+    __syncthreads();
+    if (p < P && k == 0) near[p] = (unsigned char)flag[lp];
+}
+
+cudaError_t launch_nbr_fill(const Workspace& w, cudaStream_t st, int* nl) {
+    if (w.n_atoms == 0) return cudaSuccess;
+    nbr_kernel<true><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, nullptr, nullptr,
+                                                             w.rowptr, w.ustart, w.col, w.pair_i, w.pair_j, w.pair_D);
+    ++*nl;
+    nbr_rev_kernel<<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.rowptr, w.ustart, w.degU, w.col, w.pid);
+    ++*nl;
+    if (w.P > 0) {
+        edge_desc_kernel<<<div_up(w.P, 4), 192, 0, st>>>(w.P, w.pair_D, w.e, w.near);
+        ++*nl;
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Dense (n,n,48) descriptors of one system, literal layout of get_init_edges (facade / tests).
+__global__ void edges_dense_kernel(int n, const float* __restrict__ xyz, float* __restrict__ e) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t tot = (int64_t)n * n * ED;
+    if (idx >= tot) return;
+    const int k = (int)(idx % ED);
+    const int64_t ij = idx / ED;
+    const int i = (int)(ij / n), j = (int)(ij % n);
+    float out = 0.f;
+    if (i != j) {
+        const double D = dist64(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2]);
+        const double C = cutoff_fn(D);
+        out = rbf_value(C, D, k);
+    }
+    e[idx] = out;
+}
+
+cudaError_t launch_edges_dense(int n, const float* xyz, float* e, cudaStream_t st) {
+    const int64_t tot = (int64_t)n * n * ED;
+    if (tot == 0) return cudaSuccess;
+    edges_dense_kernel<<<div_up(tot, 256), 256, 0, st>>>(n, xyz, e);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exclusive scan of int32 (out has n+1 entries; out[n] = total).  Three small kernels:
+// per-block (1024 elements) sums -> single-block scan of the block sums -> per-block rescan + offset.
+#define SCAN_BLOCK 1024
+
+__global__ void scan_block_sums(const int* __restrict__ in, int n, int* __restrict__ bsum) {
+    __shared__ int sh[32];
+    const int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    int v = i < n ? in[i] : 0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int t = sh[threadIdx.x];
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) bsum[blockIdx.x] = t;
+    }
+}
+
+__global__ void scan_single(int* __restrict__ bsum, int nb, int* __restrict__ total) {
+    // one block of 1024 threads scans nb values in strips
+    __shared__ int sh[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nb; base += SCAN_BLOCK) {
+        const int i = base + threadIdx.x;
+        const int v = i < nb ? bsum[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int t = sh[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, t, o); if (threadIdx.x >= o) t += y; }
+            sh[threadIdx.x] = t;
+        }
+        __syncthreads();
+        const int warp_prefix = (threadIdx.x >> 5) ? sh[(threadIdx.x >> 5) - 1] : 0;
+        const int incl = x + warp_prefix + carry;
+        if (i < nb) bsum[i] = incl - v;           // exclusive
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void scan_apply(const int* __restrict__ in, int n, const int* __restrict__ boff, int* __restrict__ out) {
+    __shared__ int sh[32];
+    const int i = blockIdx.x * SCAN_BLOCK + threadIdx.x;
+    const int v = i < n ? in[i] : 0;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+    if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int t = sh[threadIdx.x];
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, t, o); if (threadIdx.x >= o) t += y; }
+        sh[threadIdx.x] = t;
+    }
+    __syncthreads();
+    const int warp_prefix = (threadIdx.x >> 5) ? sh[(threadIdx.x >> 5) - 1] : 0;
+    if (i < n) out[i] = x - v + warp_prefix + boff[blockIdx.x];
+}
+
+// tmp needs div_up(n, 1024) ints.  out[n] receives the total.
+cudaError_t launch_scan_i32(const int* in, int* out, int n, int* tmp, cudaStream_t st, int* nl) {
+    if (n == 0) return cudaMemsetAsync(out, 0, sizeof(int), st);
+    const int nb = div_up(n, SCAN_BLOCK);
+    scan_block_sums<<<nb, SCAN_BLOCK, 0, st>>>(in, n, tmp);
+    scan_single<<<1, SCAN_BLOCK, 0, st>>>(tmp, nb, out + n);
+    scan_apply<<<nb, SCAN_BLOCK, 0, st>>>(in, n, tmp, out);
+    *nl += 3;
+    return cudaGetLastError();
+}

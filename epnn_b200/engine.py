@@ -1,0 +1,127 @@
+"""Engine: one libepnn_b200 context on one GPU (host-side mirror of the model object the reference
+builds with ``charge_gn.make_model(...)`` + ``load_weights`` -- reference charge_gn.py:369-391, infer.py:56-57)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+from .checkpoint import Weights
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _as(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Engine:
+    def __init__(self, weights: Weights, device: int = 0, precision: int = 32):
+        self.lib = _capi.load()
+        self.weights = weights
+        self.T, self.n_x = weights.T, weights.n_x
+        packed = weights.packed()
+        h = C.c_void_p()
+        rc = self.lib.epnn_create(device, weights.T, weights.n_x, _ptr(packed), packed.size, C.byref(h))
+        if rc != 0:
+            raise _capi.EpnnError(rc, self.lib.epnn_last_error(None).decode())
+        self._h = h
+        self.device = device
+        self.last_stats = None
+        if precision != 32:
+            self.set_option("precision", precision)
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc):
+        if rc != 0:
+            raise _capi.EpnnError(rc, self.lib.epnn_last_error(self._h).decode())
+
+    def set_option(self, key: str, value: float):
+        self._check(self.lib.epnn_set_option(self._h, key.encode(), float(value)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.epnn_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ hot path
+    def infer_batch(self, offsets, xyz, species, Q, npad=None, want_f64: bool = False, out=None):
+        """Charges for a packed batch (see epnn_infer_batch in include/epnn_b200.h).  Host numpy arrays."""
+        offsets = _as(offsets, np.int32)
+        xyz = _as(xyz, np.float32)
+        species = _as(species, np.int32)
+        Q = _as(Q, np.float32)
+        n_sys = offsets.shape[0] - 1
+        n_atoms = int(offsets[-1]) if n_sys >= 0 and offsets.size else 0
+        if xyz.size != 3 * n_atoms or species.size != n_atoms or Q.size != n_sys:
+            raise ValueError("array sizes are inconsistent with atom_offsets")
+        npad_a = None if npad is None else _as(np.broadcast_to(npad, (n_sys,)), np.int32)
+        q32 = out if out is not None else np.empty(n_atoms, np.float32)
+        q64 = np.empty(n_atoms, np.float64) if want_f64 else None
+        st = _capi.Stats()
+        self._check(self.lib.epnn_infer_batch(self._h, n_sys, _ptr(offsets), _ptr(xyz), _ptr(species), _ptr(Q),
+                                              _ptr(npad_a), _ptr(q32), _ptr(q64), C.byref(st)))
+        self.last_stats = st.as_dict()
+        return (q32, q64) if want_f64 else q32
+
+    def infer_batch_dev(self, offsets_host, xyz_dev: int, species_dev: int, Q_dev: int, npad_host, q_out_dev: int,
+                        q_out64_dev: int = 0):
+        """Device-pointer variant: the ``*_dev`` arguments are raw CUDA device addresses (ints)."""
+        offsets_host = _as(offsets_host, np.int32)
+        n_sys = offsets_host.shape[0] - 1
+        npad_a = None if npad_host is None else _as(np.broadcast_to(npad_host, (n_sys,)), np.int32)
+        st = _capi.Stats()
+        self._check(self.lib.epnn_infer_batch_dev(self._h, n_sys, _ptr(offsets_host), C.c_void_p(xyz_dev),
+                                                  C.c_void_p(species_dev), C.c_void_p(Q_dev), _ptr(npad_a),
+                                                  C.c_void_p(q_out_dev), C.c_void_p(q_out64_dev or None), C.byref(st)))
+        self.last_stats = st.as_dict()
+
+    def neighbors(self, offsets, xyz, which: int = 0):
+        """(rowptr, col) CSR of the is_near set (which=0) or the e != 0 set (which=1); global atom indices."""
+        offsets = _as(offsets, np.int32)
+        xyz = _as(xyz, np.float32)
+        n_sys = offsets.shape[0] - 1
+        n_atoms = int(offsets[-1])
+        rowptr = np.zeros(n_atoms + 1, np.int32)
+        cap = max(64, 24 * n_atoms)
+        while True:
+            col = np.empty(cap, np.int32)
+            nnz = C.c_int64(0)
+            rc = self.lib.epnn_neighbors(self._h, n_sys, _ptr(offsets), _ptr(xyz), which, _ptr(rowptr), _ptr(col), cap,
+                                         C.byref(nnz))
+            if rc == -4:
+                cap = int(nnz.value)
+                continue
+            self._check(rc)
+            return rowptr, col[:nnz.value].copy()
+
+    def init_edges(self, xyz):
+        xyz = _as(xyz, np.float32)
+        n = xyz.shape[0]
+        e = np.empty((n, n, 48), np.float32)
+        self._check(self.lib.epnn_init_edges(self._h, n, _ptr(xyz), _ptr(e)))
+        return e
+
+    def hidden(self, n_atoms: int):
+        h = np.empty((n_atoms, 48), np.float32)
+        self._check(self.lib.epnn_get_hidden(self._h, _ptr(h), h.size))
+        return h
+
+    def infer_dense(self, h, e, x, q, mask):
+        """Keras-shaped compat path (epnn_infer_dense): arrays (B,N,N,.) as gen_padded_init_state makes them."""
+        h = _as(h, np.float32); e = _as(e, np.float32); x = _as(x, np.float32); q = _as(q, np.float32)
+        mask = _as(mask, np.float32)
+        B, N = e.shape[0], e.shape[1]
+        out = np.empty((B, N), np.float32)
+        self._check(self.lib.epnn_infer_dense(self._h, B, N, _ptr(h), _ptr(e), _ptr(x), _ptr(q), _ptr(mask), _ptr(out)))
+        return out.reshape(B, N, 1)

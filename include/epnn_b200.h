@@ -1,0 +1,146 @@
+/*
+ * epnn_b200.h -- C-ABI of the B200-native EPNN charge-inference library (libepnn_b200.so).
+ *
+ * The reference (derekmetcalf/epnn) has no FFI/plugin interface: its boundary is the Python surface
+ * of charge_gn.py / infer.py.  Each entry point below names the reference code it replaces; the
+ * Python facade in epnn_b200/charge_gn.py + epnn_b200/infer.py binds these through ctypes (see
+ * INTEGRATION.md for the stub a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every function returns int: 0 = ok, negative = error (EPNN_E_*); nothing throws across the ABI;
+ *     epnn_last_error() returns the message for the last failure on that ctx (or, with ctx == NULL,
+ *     of the last failed epnn_create on this thread).
+ *   - the caller owns every buffer.  Un-suffixed entry points take HOST pointers and do their own
+ *     host<->device copies on the ctx stream; *_dev entry points take DEVICE pointers on the ctx device.
+ *   - a ctx owns its device weights, workspaces and one CUDA stream; one ctx per GPU; a ctx is not
+ *     thread-safe; distinct ctxs are independent; there is no global state.
+ *   - there is no CPU fallback: if no CUDA device is usable, epnn_create fails with EPNN_E_CUDA.
+ */
+#ifndef EPNN_B200_H
+#define EPNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPNN_OK            0
+#define EPNN_E_INVALID    -1   /* bad argument (null pointer, negative size, npad < n, species out of range, ...) */
+#define EPNN_E_CUDA       -2   /* CUDA runtime / driver failure; message holds cudaGetErrorString */
+#define EPNN_E_NOMEM      -3   /* host or device allocation failed */
+#define EPNN_E_CAPACITY   -4   /* caller-provided output buffer too small */
+#define EPNN_E_UNSUPPORTED -5  /* shape outside what the kernels were built for */
+
+#define EPNN_H_DIM 48          /* hidden width h_dim  (reference infer.py:38) */
+#define EPNN_E_DIM 48          /* radial basis size e_dim (reference infer.py:39, charge_gn.py:331) */
+#define EPNN_HID   32          /* hidden width of message/pass MLPs (reference charge_gn.py:52,84) */
+
+typedef struct epnn_ctx epnn_ctx;
+
+/* Per-call statistics (all optional).  Times are CUDA-event milliseconds on the ctx stream and are
+ * only filled when the "timing" option is on (events serialise nothing, but they are extra work). */
+typedef struct epnn_stats {
+    int64_t n_systems;
+    int64_t n_atoms;
+    int64_t n_pairs_e;        /* unordered pairs with 0 <= D < 3.0 A, i != j  (e_ij != 0 set) */
+    int64_t n_pairs_near;     /* unordered pairs in the reference's is_near set (charge_gn.py:90-94) */
+    int64_t n_row_groups;     /* GNN work units (4 atom rows each) */
+    int64_t n_chunks;         /* internal batches the call was split into */
+    int64_t n_launches;       /* kernels launched by this call */
+    float ms_total;           /* first H2D copy -> last D2H copy */
+    float ms_h2d;
+    float ms_neighbor;        /* neighbour list + radial descriptors */
+    float ms_gnn_pair;        /* sum over the T message-passing pair kernels */
+    float ms_gnn_atom;        /* per-atom update / projection kernels of the GNN layer */
+    float ms_epn_pair;        /* sum over the T electron-passing pair kernels */
+    float ms_epn_atom;        /* segmented charge reductions + projections of the EPN layer */
+    float ms_d2h;
+} epnn_stats;
+
+/* Build a context on CUDA device `device` and upload the model once.
+ * Replaces: charge_gn.make_model(layers,h_dim,T,n_elems,natom) + model.load_weights(prefix)
+ *           (reference charge_gn.py:369-391, infer.py:56-57).
+ * packed_weights (host, float32), n_floats = T*(K*32+32+32*32+32+32*32+32) + (80*32+32+32*32+32+32*48+48)
+ *           + T*(K*32+32+32*32+32+32+1) with K = 2*(n_x+49)+48, in this order, every kernel row-major (in,out):
+ *   for t in 0..T-1: message MLP t:  W1[K][32] b1[32] W2[32][32] b2[32] W3[32][32] b3[32]
+ *   update MLP:                       U1[80][32] c1[32] U2[32][32] c2[32] U3[32][48] c3[48]
+ *   for t in 0..T-1: pass MLP t:     P1[K][32] b1[32] P2[32][32] b2[32] P3[32][1]  b3[1]
+ * First-layer row order is [x_i | h_i | q_i | x_j | h_j | q_j | e_ij] (reference charge_gn.py:62-65).
+ * n_x selects the element table: 9 -> H C N O F S Cl Br (infer.py:13-30), 10 -> H C N O F P S Cl Br
+ * (charge_gn.py:9-28); per-atom features are x = [Z, onehot]. */
+int epnn_create(int device, int T, int n_x, const float* packed_weights, size_t n_floats, epnn_ctx** out);
+
+void epnn_destroy(epnn_ctx* ctx);
+
+const char* epnn_last_error(const epnn_ctx* ctx);
+
+/* Options: "precision" 32 (default, FP32 SIMT, FP64 accumulation of message sums and charges) or
+ * 64 (every kernel in FP64: the verification variant); "timing" 0/1; "chunk_atoms" (internal batch size);
+ * "keep_hidden" 0/1 (retain the final GNN hidden state for epnn_get_hidden). */
+int epnn_set_option(epnn_ctx* ctx, const char* key, double value);
+
+/* Charge inference for a packed batch of systems, host buffers.
+ * Replaces: the data-prep of charge_gn.gen_padded_init_state (charge_gn.py:292-366: featurise,
+ *           get_init_edges, pad, mask) + model([h,e,x,q,mask]) (infer.py:32-35,73), for every system.
+ *   n_sys          number of systems
+ *   atom_offsets   int32[n_sys+1], atom_offsets[0] = 0; system s owns atoms [off[s], off[s+1])
+ *   xyz            float32[3*n_atoms], Angstrom, AoS
+ *   species        int32[n_atoms], index into the element table chosen by n_x
+ *   Q              float32[n_sys], net charge of each system; q0 = float32(Q)/n per atom (charge_gn.py:337)
+ *   npad           int32[n_sys] or NULL: the pad size N the reference's dense model would be built with
+ *                  (charge_gn.py:340; results depend on it).  NULL = no padding (N = n).
+ *   q_out          float32[n_atoms] predicted charges (real atoms only)
+ *   q_out_f64      optional double[n_atoms] (NULL to skip): the charges before rounding to float32
+ *   stats          optional */
+int epnn_infer_batch(epnn_ctx* ctx, int64_t n_sys, const int32_t* atom_offsets, const float* xyz,
+                     const int32_t* species, const float* Q, const int32_t* npad,
+                     float* q_out, double* q_out_f64, epnn_stats* stats);
+
+/* Same with DEVICE pointers for the bulk data (inputs already resident in HBM, outputs left in HBM).
+ * atom_offsets and npad stay HOST arrays: they drive launch geometry and are tiny (4 B per system).
+ * Work is enqueued on the ctx stream; the call returns after the stream has been synchronised. */
+int epnn_infer_batch_dev(epnn_ctx* ctx, int64_t n_sys, const int32_t* atom_offsets_host,
+                         const float* xyz_dev, const int32_t* species_dev, const float* Q_dev,
+                         const int32_t* npad_host, float* q_out_dev, double* q_out_f64_dev, epnn_stats* stats);
+
+/* Neighbour list only (for the bit-exactness check against the reference's is_near mask).
+ * Replaces: get_init_edges + the is_near predicate (charge_gn.py:122-163, 90-94).
+ *   which = 0: is_near set;  which = 1: the e != 0 set (i != j, D < 3.0).
+ * rowptr: int32[n_atoms+1]; col: int32[col_capacity], GLOBAL atom indices, ascending within a row;
+ * *nnz receives the number of entries (EPNN_E_CAPACITY if col_capacity is too small; *nnz is still set). */
+int epnn_neighbors(epnn_ctx* ctx, int64_t n_sys, const int32_t* atom_offsets, const float* xyz,
+                   int which, int32_t* rowptr, int32_t* col, int64_t col_capacity, int64_t* nnz);
+
+/* Radial descriptors of one system, dense: e float32[n*n*48] exactly as get_init_edges returns them
+ * (charge_gn.py:122-163).  Intended for tests and for the charge_gn.get_init_edges facade. */
+int epnn_init_edges(epnn_ctx* ctx, int32_t n, const float* xyz, float* e_out);
+
+/* Keras-shaped compatibility path: the model called on the dense padded tensors that
+ * gen_padded_init_state produces.  Replaces model([h,e,x,q,mask]) (charge_gn.py:369-391) literally:
+ * un-tiling by divide_no_nan, unmasked all-pairs GNN, EPN masked by mask*is_near(e).
+ *   h float32[B][N][N][48], e float32[B][N][N][48], x float32[B][N][N][n_x], q float32[B][N][N][1],
+ *   mask float32[B][N][N]; q_out float32[B][N] (the reference returns (B,N,1)). */
+int epnn_infer_dense(epnn_ctx* ctx, int32_t B, int32_t N, const float* h, const float* e, const float* x,
+                     const float* q, const float* mask, float* q_out);
+
+/* Final GNN hidden state of the last epnn_infer_batch call (needs option keep_hidden=1 and a
+ * single-chunk call): h_out float32[n_atoms*48].  Test hook: the shipped default checkpoint's GNN
+ * output is a dead constant, so charges alone cannot validate the GNN kernels (SURVEY.md trap 6). */
+int epnn_get_hidden(epnn_ctx* ctx, float* h_out, int64_t n_floats);
+
+/* Pinned host memory helpers so that callers can make the H2D/D2H copies asynchronous. */
+int epnn_host_alloc(void** ptr, size_t bytes);
+int epnn_host_free(void* ptr);
+
+/* The 48 Gaussian centres mu_k = linspace(0.1, 3.0, 48) the kernels use (charge_gn.py:123). */
+int epnn_rbf_centers(double* mu_out48);
+
+/* Library / build identification, e.g. "epnn_b200 0.1.0 sm_100a". */
+const char* epnn_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPNN_B200_H */

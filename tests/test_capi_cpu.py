@@ -1,0 +1,55 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/epnn_b200.h declares (CPU)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+from epnn_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "epnn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(epnn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    names = _declared()
+    assert set(names) == set(_capi.SIGNATURES), (names, sorted(_capi.SIGNATURES))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = _capi.load()
+    for n in _declared():
+        assert getattr(lib, n) is not None
+
+
+def test_version_and_rbf_centers():
+    lib = _capi.load()
+    assert b"sm_100a" in lib.epnn_version()
+    mu = np.zeros(48)
+    assert lib.epnn_rbf_centers(mu.ctypes.data_as(C.c_void_p)) == 0
+    assert np.array_equal(mu, np.linspace(0.1, 3.0, 48))          # bit-exact with charge_gn.py:123
+
+
+def test_create_rejects_bad_arguments_before_touching_cuda():
+    lib = _capi.load()
+    h = C.c_void_p()
+    w = np.zeros(10, np.float32)
+    assert lib.epnn_create(0, 5, 9, w.ctypes.data_as(C.c_void_p), 10, C.byref(h)) == -1
+    assert b"expected 74037" in lib.epnn_last_error(None)
+    assert lib.epnn_create(0, 5, 11, w.ctypes.data_as(C.c_void_p), 10, C.byref(h)) == -1
+    assert lib.epnn_create(0, 5, 9, None, 74037, C.byref(h)) == -1
+
+
+def test_product_never_imports_oracle():
+    """The product package must not route through the oracle or any CPU fallback."""
+    pkg = os.path.join(ROOT, "epnn_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
