@@ -1,0 +1,436 @@
+#!/usr/bin/env python
+"""bench.py -- atoms/s of EPNN charge inference (BASELINE.json metric) on N B200s of one node.
+
+A "step" is one pass of the hot path (neighbour list + descriptors -> T message-passing steps -> T
+electron-passing passes -> charges) over one batch of synthetic input:
+
+  workload "qm9"     (default; BASELINE.json configs[3]) : --molecules QM9-shaped molecules PER GPU, drawn from
+                     the 1338 QM9 molecules of data/mixed, randomly rotated + jittered (epnn_b200/synth.py),
+                     Q = 0, pad N = 29, decay_model_weights.  Molecules are independent, so N GPUs hold N
+                     disjoint shards of the same stream (molecule k depends only on (seed, k)) and there is
+                     no data-path collective: "scaling": "weak".
+  workload "protein" (BASELINE.json configs[2]/[4])      : one protein-like system of --atoms atoms (Galectin-3C
+                     tiled), exact all-pairs GNN; single GPU per replica.
+
+Printed JSON (rank 0, one line): the driver contract + "roofline" (dominant kernel, FP32-SIMT bound, against
+the FMA peak measured in the same run; the HBM-side kernels against MEASURED_PEAKS.json) + "cpu_baseline"
+(the numpy oracle's reference formulation on the box's host cores, bounded sample).
+
+`--impl reference` times that CPU formulation as its own arm (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+METRIC = "atoms/sec EPNN charge inference"
+UNIT = "atoms/s"
+FLOP_PAIR = 2 * 32 * 32 + 3 * 32           # per ordered (i,j) pair per GNN step: 2144
+FLOP_PAIR_E = 2 * 48 * 32                  # extra for pairs with e != 0: 3072
+FLOP_EPN_PAIR = 2 * (48 * 32 + 2 * (32 * 32 + 32)) + 2 * 64   # per unordered near pair per pass: 7424
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="qm9", choices=["qm9", "protein"])
+    ap.add_argument("--molecules", type=int, default=1_000_000, help="QM9-shaped molecules per GPU per step")
+    ap.add_argument("--atoms", type=int, default=2220, help="atoms of the protein-like system (workload protein)")
+    ap.add_argument("--npad", type=int, default=29, help="pad size N of the reference's dense model (qm9 workload)")
+    ap.add_argument("--checkpoint", default="decay_model_weights")
+    ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
+    ap.add_argument("--chunk-atoms", type=int, default=0, help="override the library's internal batch size")
+    ap.add_argument("--ref-molecules", type=int, default=2048, help="molecules per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ workloads
+def make_workload(args, w, rank):
+    from epnn_b200 import synth
+    if args.workload == "qm9":
+        offs, xyz, sp, Q = synth.qm9_shaped(args.molecules, w.n_x, seed=args.seed, first=rank * args.molecules)
+        npad = np.full(args.molecules, args.npad, np.int32)
+        desc = {"workload": f"synthetic QM9-shaped molecules (<=29 atoms), {args.molecules} per GPU per step, pad N={args.npad}",
+                "molecules_per_gpu": args.molecules}
+    else:
+        offs, xyz, sp, Q = synth.protein_like(args.atoms, w.n_x, seed=1 + rank)
+        npad = np.array([args.atoms], np.int32)
+        desc = {"workload": f"protein-like single system, {args.atoms} atoms (Galectin-3C tiled), pad N=n, exact all-pairs GNN",
+                "atoms_per_gpu": args.atoms}
+    return offs, np.ascontiguousarray(xyz, np.float32), sp, Q, npad, desc
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.lines = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+_W = None
+
+
+def _ref_init(ckpt):
+    global _W
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    from epnn_b200.checkpoint import load_weights
+    _W = load_weights(os.path.join(GOLDEN, "checkpoints", ckpt))
+
+
+def _ref_work(job):
+    """The reference formulation (dense padded (N*N,K) pair inputs, three Dense layers per MLP, float32 like
+    Keras) for a slice of systems, including get_init_edges: oracle.forward_literal."""
+    from oracle import epnn_oracle as O
+    xyz, sp, Q, offs, npad = job
+    out = []
+    for s in range(len(Q)):
+        a0, a1 = offs[s], offs[s + 1]
+        out.append(O.forward_literal(_W, xyz[a0:a1], sp[a0:a1], Q[s], int(npad[s]), np.float32))
+    return np.concatenate(out) if out else np.zeros(0)
+
+
+def run_reference(args):
+    """`--impl reference`: rank 0 times the CPU port of the reference path on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from epnn_b200.checkpoint import load_weights
+    w = load_weights(os.path.join(GOLDEN, "checkpoints", args.checkpoint))
+    cores = os.cpu_count() or 1
+    sub = argparse.Namespace(**vars(args))
+    if args.workload == "qm9":
+        sub.molecules = args.ref_molecules
+        sample = f"{args.ref_molecules} molecules of the same synthetic stream per step (of {args.molecules} per GPU)"
+    else:
+        sub.atoms = min(args.atoms, 2220)
+        sample = f"one {sub.atoms}-atom system per step"
+    offs, xyz, sp, Q, npad, desc = make_workload(sub, w, 0)
+    n_sys = len(Q)
+    # one job per core (contiguous slices); a single big system cannot be split -> 1 process using BLAS threads
+    if n_sys >= cores:
+        bounds = np.linspace(0, n_sys, cores + 1).astype(int)
+        jobs = []
+        for c in range(cores):
+            s0, s1 = bounds[c], bounds[c + 1]
+            a0, a1 = offs[s0], offs[s1]
+            jobs.append((xyz[a0:a1], sp[a0:a1], Q[s0:s1], offs[s0:s1 + 1] - a0, npad[s0:s1]))
+        pool = mp.get_context("fork").Pool(cores, initializer=_ref_init, initargs=(args.checkpoint,))
+        step = lambda: pool.map(_ref_work, jobs)
+        used = cores
+    else:
+        pool = None
+        global _W
+        _W = w
+        jobs = [(xyz, sp, Q, offs, npad)]
+        step = lambda: [_ref_work(jobs[0])]
+        used = cores      # OpenBLAS default: all cores
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    if pool is not None:
+        pool.close()
+    atoms = int(offs[-1]) * args.steps
+    value = atoms / dt
+    _, _, _, _, _, full_desc = make_workload_desc_only(args)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": full_desc,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
+                             "what": "numpy float32 restatement of the reference formulation (oracle.forward_literal: "
+                                     "get_init_edges + dense padded pair tensors + 3 Dense layers per MLP); TensorFlow is "
+                                     "not installable in this image"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def make_workload_desc_only(args):
+    if args.workload == "qm9":
+        desc = {"workload": f"synthetic QM9-shaped molecules (<=29 atoms), {args.molecules} per GPU per step, pad N={args.npad}",
+                "molecules_per_gpu": args.molecules}
+    else:
+        desc = {"workload": f"protein-like single system, {args.atoms} atoms (Galectin-3C tiled), pad N=n, exact all-pairs GNN",
+                "atoms_per_gpu": args.atoms}
+    desc.update({"checkpoint": args.checkpoint, "parallelism": f"molecule-shards x{args.gpus}, no collective"})
+    return None, None, None, None, None, desc
+
+
+def cpu_baseline_subprocess(args):
+    """Run the reference arm in a fresh interpreter (no CUDA context to fork) and return its cpu_baseline."""
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1",
+           "--workload", args.workload, "--molecules", str(args.molecules), "--atoms", str(min(args.atoms, 2220)),
+           "--npad", str(args.npad), "--checkpoint", args.checkpoint, "--ref-molecules", str(args.ref_molecules),
+           "--seed", str(args.seed)]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: " + out.stderr[-300:]}
+    except Exception as ex:      # noqa: BLE001
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from epnn_b200.checkpoint import load_weights
+    from epnn_b200.engine import Engine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: epnn_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    # CPU baseline first (rank 0, N = 1 only), before this process owns a CUDA context
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline_subprocess(args)
+
+    w = load_weights(os.path.join(GOLDEN, "checkpoints", args.checkpoint))
+    offs, xyz, sp, Q, npad, desc = make_workload(args, w, rank)
+    n_atoms = int(offs[-1])
+    eng = Engine(w, device=local, precision=args.precision)
+    eng.set_option("timing", 1)
+    if args.chunk_atoms:
+        eng.set_option("chunk_atoms", args.chunk_atoms)
+    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(step_fn):
+        """W warm-up + K timed steps; CUDA events on the ctx stream; returns (ms, per-phase stats sum, clocks)."""
+        for _ in range(args.warmup):
+            step_fn()
+        barrier()
+        clk = ClockSampler(local)
+        if rank == 0:
+            clk.start()
+            time.sleep(0.25)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        acc = {}
+        barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_fn()
+            for k, v in eng.last_stats.items():
+                acc[k] = acc.get(k, 0) + v
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = clk.stop() if rank == 0 else None
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, acc, clocks
+
+    # ---- (1) device-resident: inputs already in HBM when the timed region starts
+    d_xyz = torch.from_numpy(xyz).to(dev)
+    d_sp = torch.from_numpy(sp).to(dev)
+    d_Q = torch.from_numpy(Q).to(dev)
+    d_out = torch.empty(n_atoms, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize(dev)
+
+    def step_dev():
+        eng.infer_batch_dev(offs, d_xyz.data_ptr(), d_sp.data_ptr(), d_Q.data_ptr(), npad, d_out.data_ptr())
+
+    ms_dev, acc, clocks = timed(step_dev)
+    q_dev = d_out.cpu().numpy()
+
+    # ---- (2) end to end through the public host API: pinned host buffers, H2D + D2H inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        h_xyz = eng.pinned_empty(xyz.shape, np.float32); h_xyz[...] = xyz
+        h_sp = eng.pinned_empty(sp.shape, np.int32); h_sp[...] = sp
+        h_Q = eng.pinned_empty(Q.shape, np.float32); h_Q[...] = Q
+        h_out = eng.pinned_empty((n_atoms,), np.float32)
+
+        def step_host():
+            eng.infer_batch(offs, h_xyz, h_sp, h_Q, npad, out=h_out)
+
+        ms_e2e, _, _ = timed(step_host)
+        if not np.array_equal(h_out, q_dev):
+            raise SystemExit("host-API and device-API results differ")
+        h2d = xyz.nbytes + sp.nbytes + Q.nbytes + offs.nbytes + npad.nbytes
+        e2e = {"value": world * n_atoms * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_out.nbytes), "ms_per_step": ms_e2e / args.steps}
+
+    # ---- sanity on the result of the timed path (cheap, outside the timed region)
+    sums = np.add.reduceat(q_dev.astype(np.float64), offs[:-1])
+    max_dQ = float(np.abs(sums - Q.astype(np.float64)).max())
+
+    # ---- totals over ranks
+    tot_atoms = n_atoms
+    launches = int(acc["n_launches"])
+    if world > 1:
+        t = torch.tensor([n_atoms, launches], device=dev, dtype=torch.float64)
+        dist.all_reduce(t)
+        tot_atoms, launches = int(t[0].item()), int(t[1].item())
+
+    if rank == 0:
+        # roofline of the dominant kernel (gnn_pair_kernel): algorithmic FLOPs / CUDA-event time of its launches
+        n_sys_sizes = np.diff(offs).astype(np.float64)
+        ordered_pairs = float((n_sys_sizes ** 2).sum() + (n_sys_sizes * (npad > np.diff(offs))).sum())
+        nnz = 2.0 * acc["n_pairs_e"] / args.steps
+        gnn_flops_step = w.T * (FLOP_PAIR * ordered_pairs + FLOP_PAIR_E * nnz)
+        epn_flops_step = w.T * FLOP_EPN_PAIR * acc["n_pairs_near"] / args.steps
+        ms_gnn = acc["ms_gnn_pair"] / args.steps
+        ms_epn = acc["ms_epn_pair"] / args.steps
+        fp32_peak = eng.measure_fp32_peak(5)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        phases = {k: acc[k] / args.steps for k in acc if k.startswith("ms_")}
+        dominant = max(("ms_gnn_pair", "ms_epn_pair", "ms_neighbor", "ms_gnn_atom", "ms_epn_atom"), key=lambda k: phases[k])
+        n_chunks = acc["n_chunks"] / args.steps
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                tj = json.load(open(tpath))
+                if tj.get("workload") == args.workload:
+                    traffic = tj["gnn_pair_dram_bytes_per_atom_per_launch"] * n_atoms / n_chunks
+            except Exception:   # noqa: BLE001
+                traffic = None
+        achieved = gnn_flops_step / (ms_gnn * 1e-3) * 1e-12
+        roofline = {
+            "kernel": "gnn_pair_kernel (message-passing pair MLP, FP32 SIMT)", "bound": "fp32",
+            "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
+            "peak_source": "FP32 FMA micro-benchmark measured in this run (epnn_measure_fp32_peak); MEASURED_PEAKS.json "
+                           "holds no SIMT peak. north_star: pair MLP defaults to FP32 SIMT, tensor pipe unused",
+            "traffic": traffic,
+            "launches_per_step": w.T * n_chunks, "avg_launch_ms": ms_gnn / (w.T * n_chunks),
+            "algorithmic_flops_per_launch": gnn_flops_step / (w.T * n_chunks),
+            "share_of_step": ms_gnn / phases["ms_total"],
+            "dominant_phase": dominant,
+            "epn_pair": {"achieved": epn_flops_step / (ms_epn * 1e-3) * 1e-12, "unit": "TFLOP/s",
+                         "frac": epn_flops_step / (ms_epn * 1e-3) * 1e-12 / fp32_peak if fp32_peak else None},
+            "hbm_side": {
+                "bound": "hbm", "peak": hbm_peak, "unit": "GB/s",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)",
+                "neighbor_build": {"achieved": (20.0 * n_atoms + 4.0 * nnz) / (phases["ms_neighbor"] * 1e-3) * 1e-9},
+                "charge_reduction": {"achieved": w.T * (4.0 * nnz + 8.0 * n_atoms) / (phases["ms_epn_atom"] * 1e-3) * 1e-9},
+            },
+        }
+        for k in ("neighbor_build", "charge_reduction"):
+            roofline["hbm_side"][k]["frac"] = roofline["hbm_side"][k]["achieved"] / hbm_peak
+        desc.update({"checkpoint": args.checkpoint, "parallelism": f"molecule-shards x{world}, no collective",
+                     "l2": "inputs larger than L2 (no flush needed)" if n_atoms * 16 > 126e6 else "inputs smaller than L2",
+                     "atoms_per_gpu_per_step": n_atoms, "T": w.T, "precision": args.precision})
+        line = {"metric": METRIC, "value": tot_atoms * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic",
+                "config": desc, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "cpu_baseline": cpu_base, "phases_ms_per_step": phases,
+                "checks": {"max_abs_sum_q_minus_Q": max_dQ}}
+        print(json.dumps(line), flush=True)
+    eng.free_pinned()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        import socket
+        s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -48,6 +48,8 @@ SIGNATURES = {
     "epnn_get_hidden": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "epnn_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "epnn_host_free": (C.c_int, [C.c_void_p]),
+    "epnn_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "epnn_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "epnn_rbf_centers": (C.c_int, [C.c_void_p]),
     "epnn_version": (C.c_char_p, []),
 }

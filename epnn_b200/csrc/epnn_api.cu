@@ -665,3 +665,47 @@ extern "C" int epnn_infer_dense(epnn_ctx* c, int32_t B, int32_t N, const float* 
     (void)B; (void)N; (void)h; (void)e; (void)x; (void)q; (void)mask; (void)q_out;
     return fail(c, EPNN_E_UNSUPPORTED, "epnn_infer_dense is not implemented yet");
 }
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int epnn_get_stream(epnn_ctx* c, void** stream_out) {
+    if (!c || !stream_out) return EPNN_E_INVALID;
+    *stream_out = (void*)c->stream;
+    return EPNN_OK;
+}
+
+// FP32 FMA micro-benchmark: 8 independent accumulator chains per thread, ITER x 8 FMAs, nothing else in the loop.
+#define FMA_ITERS 4096
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 16
+    for (int i = 0; i < FMA_ITERS; ++i) {
+        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456f) out[0] = s;            // never true in practice; keeps the chains alive
+}
+
+extern "C" int epnn_measure_fp32_peak(epnn_ctx* c, int repeats, double* tflops_out) {
+    if (!c || !tflops_out || repeats < 1) return EPNN_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    void* p; int rc;
+    if ((rc = ensure(c, B_MISC, 64, &p)) != EPNN_OK) return rc;
+    const int blocks = c->sm_count * 32, threads = 256;
+    cudaEvent_t e0, e1;
+    CU(c, cudaEventCreate(&e0)); CU(c, cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int r = 0; r < repeats + 1; ++r) {            // first launch is the warm-up
+        cudaEventRecord(e0, c->stream);
+        fma_peak_kernel<<<blocks, threads, 0, c->stream>>>((float*)p + 8, 0.999f, 0.001f);
+        cudaEventRecord(e1, c->stream);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); CU(c, e); }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * FMA_ITERS * (double)blocks * threads / (ms * 1e-3) * 1e-12;
+        if (r > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops_out = best;
+    return EPNN_OK;
+}

@@ -68,6 +68,52 @@ __device__ __forceinline__ void tile_gemm(const R* __restrict__ at, const R* __r
     }
 }
 
+// FP32 specialisation on Blackwell's packed FFMA2 (PTX fma.rn.f32x2, sm_100+): one instruction does two
+// IEEE fma.rn -- bit-identical to two scalar FFMAs -- so the k-loop needs half the issue slots, and the
+// 3-distinct-register scalar FFMA's register-bank limit (measured: 35 of 67 TFLOP/s for acc += a*w, tools/ubench.cu)
+// goes away.  The pair operand is the weight pair (w[c], w[c+1]); the activation is the scalar that ptxas
+// folds into FFMA2's broadcast ".F32" operand form (no MOV is emitted for the duplicated pair).
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void fma2(f32x2_t& d, f32x2_t wpair, float a) {
+    const f32x2_t aa = pack2(a, a);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(wpair), "l"(aa));
+}
+template <int K, int WLD>
+__device__ __forceinline__ void tile_gemm_f32x2(const float* __restrict__ at, const float* __restrict__ W, int wcol,
+                                                float (&acc)[8][4], int pg) {
+    const float* arow = at + pg * 8 * K;
+    f32x2_t c[8][2];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) { c[s][0] = pack2(acc[s][0], acc[s][1]); c[s][1] = pack2(acc[s][2], acc[s][3]); }
+#pragma unroll 2
+    for (int kc = 0; kc < K / 4; ++kc) {
+        f32x2_t w[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const ulonglong2 t = *reinterpret_cast<const ulonglong2*>(W + (kc * 4 + k) * WLD + wcol);
+            w[k][0] = t.x; w[k][1] = t.y;
+        }
+        const int kcs = (kc ^ pg) * 4;
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+            const float4 a = *reinterpret_cast<const float4*>(arow + s * K + kcs);
+            fma2(c[s][0], w[0][0], a.x); fma2(c[s][1], w[0][1], a.x);
+            fma2(c[s][0], w[1][0], a.y); fma2(c[s][1], w[1][1], a.y);
+            fma2(c[s][0], w[2][0], a.z); fma2(c[s][1], w[2][1], a.z);
+            fma2(c[s][0], w[3][0], a.w); fma2(c[s][1], w[3][1], a.w);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < 8; ++s) { unpack2(c[s][0], acc[s][0], acc[s][1]); unpack2(c[s][1], acc[s][2], acc[s][3]); }
+}
+template <> __device__ __forceinline__ void tile_gemm<float, ED, HID>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<ED, HID>(at, W, wcol, acc, pg); }
+template <> __device__ __forceinline__ void tile_gemm<float, HID, HID>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<HID, HID>(at, W, wcol, acc, pg); }
+template <> __device__ __forceinline__ void tile_gemm<float, UPD_IN, HID>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<UPD_IN, HID>(at, W, wcol, acc, pg); }
+template <> __device__ __forceinline__ void tile_gemm<float, HID, HD>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<HID, HD>(at, W, wcol, acc, pg); }
+template <> __device__ __forceinline__ void tile_gemm<float, HD, 64>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<HD, 64>(at, W, wcol, acc, pg); }
+
 template <typename R> __device__ __forceinline__ void zero_acc(R (&acc)[8][4]) {
 #pragma unroll
     for (int s = 0; s < 8; ++s) { acc[s][0] = acc[s][1] = acc[s][2] = acc[s][3] = R(0); }

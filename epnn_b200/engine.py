@@ -54,6 +54,38 @@ class Engine:
         except Exception:
             pass
 
+    @property
+    def stream(self) -> int:
+        """The ctx's cudaStream_t as an integer handle (for torch.cuda.ExternalStream / caller-side events)."""
+        p = C.c_void_p()
+        self._check(self.lib.epnn_get_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def measure_fp32_peak(self, repeats: int = 5) -> float:
+        """Measured FP32 FMA peak of this GPU in TFLOP/s (epnn_measure_fp32_peak)."""
+        out = C.c_double(0.0)
+        self._check(self.lib.epnn_measure_fp32_peak(self._h, repeats, C.byref(out)))
+        return out.value
+
+    def pinned_empty(self, shape, dtype):
+        """numpy array backed by page-locked host memory (epnn_host_alloc); freed by ``free_pinned``."""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        rc = self.lib.epnn_host_alloc(C.byref(p), max(n, 1))
+        if rc != 0:
+            raise _capi.EpnnError(rc, "epnn_host_alloc failed")
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        a = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        return a
+
+    def free_pinned(self):
+        for p in getattr(self, "_pinned", []):
+            self.lib.epnn_host_free(p)
+        self._pinned = []
+
     # ------------------------------------------------------------------ hot path
     def infer_batch(self, offsets, xyz, species, Q, npad=None, want_f64: bool = False, out=None):
         """Charges for a packed batch (see epnn_infer_batch in include/epnn_b200.h).  Host numpy arrays."""

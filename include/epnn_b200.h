@@ -134,6 +134,15 @@ int epnn_get_hidden(epnn_ctx* ctx, float* h_out, int64_t n_floats);
 int epnn_host_alloc(void** ptr, size_t bytes);
 int epnn_host_free(void* ptr);
 
+/* The CUDA stream (cudaStream_t, returned as void*) every kernel and copy of this ctx is enqueued on, so
+ * that a caller can record its own CUDA events around a sequence of calls (bench.py does). */
+int epnn_get_stream(epnn_ctx* ctx, void** stream_out);
+
+/* FP32 FMA micro-benchmark on the ctx device: the measured SIMT peak (TFLOP/s, 2 flops per FMA, best of
+ * `repeats` launches timed with CUDA events) that the pair-MLP kernels' roofline fraction is quoted against
+ * (MEASURED_PEAKS.json only holds HBM and tensor peaks). */
+int epnn_measure_fp32_peak(epnn_ctx* ctx, int repeats, double* tflops_out);
+
 /* The 48 Gaussian centres mu_k = linspace(0.1, 3.0, 48) the kernels use (charge_gn.py:123). */
 int epnn_rbf_centers(double* mu_out48);
 
