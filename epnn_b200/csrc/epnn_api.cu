@@ -34,7 +34,8 @@ struct epnn_ctx {
     float* wf = nullptr;         // packed weights, float
     double* wd = nullptr;        // packed weights, double
     std::vector<DevBuf> bufs;    // grow-only workspaces, indexed by enum below
-    int* d_flags = nullptr;      // [0] error bits, [1..4] totals (nnz, P, n_rg_small, n_rg_large)
+    std::vector<int2> h_bundles; // host staging of the bundle table of the current chunk
+    int* d_flags = nullptr;      // [0] error bits, [1..4] totals (nnz, P, n_far, n_rg_large)
     int* h_flags = nullptr;      // pinned mirror
     int64_t hidden_atoms = 0;    // atoms covered by the retained hidden state
     int hidden_precision = 32;
@@ -45,7 +46,7 @@ static thread_local std::string g_create_err;
 
 enum {
     B_XYZ, B_SPECIES, B_OFF, B_Q, B_NPAD, B_ATOMSYS, B_DEG, B_DEGU, B_ROWPTR, B_USTART, B_COL, B_PID, B_PI, B_PJ, B_PD,
-    B_E, B_NEAR, B_RGS, B_RGL, B_H, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTS, B_CNTL, B_RGSOFF, B_RGLOFF,
+    B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_ATOMB0, B_BNAT, B_PERM, B_H, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
     B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_COUNT
 };
 
@@ -263,7 +264,7 @@ extern "C" int epnn_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSucce
 // Per-system prep: rebased offsets, default npad, validation, row-group counts.
 __global__ void sys_prep_kernel(int n_sys, const int* __restrict__ off_in, int base, int* __restrict__ off_out,
                                 const int* __restrict__ npad_in, int* __restrict__ npad_out,
-                                int* __restrict__ cnt_small, int* __restrict__ cnt_large, int* __restrict__ flags) {
+                                int* __restrict__ cnt_large, int* __restrict__ flags) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s > n_sys) return;
     const int o = off_in[s] - base;
@@ -273,18 +274,15 @@ __global__ void sys_prep_kernel(int n_sys, const int* __restrict__ off_in, int b
     int np = npad_in ? npad_in[s] : n;
     if (np < n || n <= 0) { atomicOr(flags, n <= 0 ? 2 : 1); np = n; }
     npad_out[s] = np;
-    const int g = (n + 3) >> 2;
-    cnt_small[s] = n <= SMALL_MAX ? g : 0;
-    cnt_large[s] = n <= SMALL_MAX ? 0 : g;
+    cnt_large[s] = n <= SMALL_MAX ? 0 : (n + 3) >> 2;      // 4-row groups of the large systems
 }
 
-__global__ void rg_fill_kernel(int n_sys, const int* __restrict__ off, const int* __restrict__ rgs_off,
-                               const int* __restrict__ rgl_off, int* __restrict__ rg_small, int* __restrict__ rg_large) {
+__global__ void rg_fill_kernel(int n_sys, const int* __restrict__ off, const int* __restrict__ rgl_off, int* __restrict__ rg_large) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_sys) return;
     const int a0 = off[s], a1 = off[s + 1];
-    const bool small = (a1 - a0) <= SMALL_MAX;
-    int* dst = small ? rg_small + rgs_off[s] : rg_large + rgl_off[s];
+    if (a1 - a0 <= SMALL_MAX) return;
+    int* dst = rg_large + rgl_off[s];
     int k = 0;
     for (int i = a0; i < a1; i += 4) dst[k++] = i;
 }
@@ -294,9 +292,9 @@ __global__ void species_check_kernel(int n, const int* __restrict__ species, int
     if (i < n && (species[i] < 0 || species[i] >= n_species)) atomicOr(flags, 4);
 }
 
-__global__ void collect_totals_kernel(const int* rowptr, const int* ustart, int n_atoms, const int* rgs_off,
+__global__ void collect_totals_kernel(const int* rowptr, const int* ustart, const int* far_off, int n_atoms,
                                       const int* rgl_off, int n_sys, int* flags) {
-    flags[1] = rowptr[n_atoms]; flags[2] = ustart[n_atoms]; flags[3] = rgs_off[n_sys]; flags[4] = rgl_off[n_sys];
+    flags[1] = rowptr[n_atoms]; flags[2] = ustart[n_atoms]; flags[3] = far_off[n_atoms]; flags[4] = rgl_off[n_sys];
 }
 
 struct Timer {
@@ -323,7 +321,7 @@ struct Timer {
 
 // One chunk, device-resident inputs: d_off_in = slice of the caller's GLOBAL offsets (n_sys+1), base = its first value.
 template <typename R>
-static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int* d_off_in, int base, const float* d_xyz,
+static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, const int* d_off_in, int base, const float* d_xyz,
                      const int* d_species, const float* d_Q, const int* d_npad_in, float* d_out32, double* d_out64,
                      epnn_stats* stats, Timer& tm, int* n_launch, bool neighbors_only, Workspace* ws_out) {
     cudaStream_t st = c->stream;
@@ -334,12 +332,10 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int* d_off_in, i
     void* p;
     int rc;
 #define ENS(which, bytes, field, type) do { if ((rc = ensure(c, which, (bytes), &p)) != EPNN_OK) return rc; field = (type)p; } while (0)
-    int *off_local, *npad_local, *cnt_s, *cnt_l, *rgs_off, *rgl_off, *scantmp;
+    int *off_local, *npad_local, *cnt_l, *rgl_off, *scantmp, *far_cnt, *atom_b0;
     ENS(B_OFF, sizeof(int) * ((size_t)n_sys + 1), off_local, int*);
     ENS(B_NPAD, sizeof(int) * ((size_t)n_sys + 1), npad_local, int*);
-    ENS(B_CNTS, sizeof(int) * ((size_t)n_sys + 1), cnt_s, int*);
     ENS(B_CNTL, sizeof(int) * ((size_t)n_sys + 1), cnt_l, int*);
-    ENS(B_RGSOFF, sizeof(int) * ((size_t)n_sys + 1), rgs_off, int*);
     ENS(B_RGLOFF, sizeof(int) * ((size_t)n_sys + 1), rgl_off, int*);
     const size_t nmax = (size_t)(n_atoms > n_sys ? n_atoms : n_sys);
     ENS(B_SCANTMP, sizeof(int) * (nmax / 1024 + 2), scantmp, int*);
@@ -348,29 +344,55 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int* d_off_in, i
     ENS(B_DEGU, sizeof(int) * (size_t)n_atoms, w.degU, int*);
     ENS(B_ROWPTR, sizeof(int) * ((size_t)n_atoms + 1), w.rowptr, int*);
     ENS(B_USTART, sizeof(int) * ((size_t)n_atoms + 1), w.ustart, int*);
+    ENS(B_FARCNT, sizeof(int) * ((size_t)n_atoms + 1), far_cnt, int*);
+    ENS(B_FAROFF, sizeof(int) * ((size_t)n_atoms + 1), w.far_off, int*);
+    ENS(B_ATOMB0, sizeof(int) * ((size_t)n_atoms + 1), atom_b0, int*);
+    ENS(B_BNAT, sizeof(int) * ((size_t)n_atoms + 1), w.bundle_nat, int*);
     ENS(B_QD, sizeof(double) * (size_t)n_atoms, w.q, double*);
     w.sys_off = off_local; w.npad = npad_local;
 
+    // ---- bundles: greedy runs of consecutive small systems with <= BUNDLE_ATOMS atoms (host: the offsets are host data)
+    {
+        std::vector<int2>& hb = c->h_bundles;
+        hb.clear();
+        int cur0 = -1, cur_n = 0;
+        for (int s = 0; s < n_sys; ++s) {
+            const int a0 = h_off[s] - base, n = h_off[s + 1] - h_off[s];
+            if (n > SMALL_MAX) {
+                if (cur_n) { hb.push_back(make_int2(cur0, cur_n)); cur_n = 0; }
+                continue;
+            }
+            if (cur_n && cur_n + n > BUNDLE_ATOMS) { hb.push_back(make_int2(cur0, cur_n)); cur_n = 0; }
+            if (!cur_n) cur0 = a0;
+            cur_n += n;
+        }
+        if (cur_n) hb.push_back(make_int2(cur0, cur_n));
+        w.n_bundles = (int)hb.size();
+        ENS(B_BUNDLE, sizeof(int2) * (hb.size() + 1), w.bundle, int2*);
+        if (!hb.empty()) CU(c, cudaMemcpyAsync(w.bundle, hb.data(), sizeof(int2) * hb.size(), cudaMemcpyHostToDevice, st));
+    }
+
     CU(c, cudaMemsetAsync(c->d_flags, 0, 8 * sizeof(int), st));
-    sys_prep_kernel<<<div_up(n_sys + 1, 256), 256, 0, st>>>(n_sys, d_off_in, base, off_local, d_npad_in, npad_local, cnt_s, cnt_l, c->d_flags);
+    sys_prep_kernel<<<div_up(n_sys + 1, 256), 256, 0, st>>>(n_sys, d_off_in, base, off_local, d_npad_in, npad_local, cnt_l, c->d_flags);
     species_check_kernel<<<div_up(n_atoms, 256), 256, 0, st>>>(n_atoms, d_species, c->n_species, c->d_flags);
     *n_launch += 2;
     CU(c, cudaGetLastError());
-    CU(c, launch_scan_i32(cnt_s, rgs_off, n_sys, scantmp, st, n_launch));
     CU(c, launch_scan_i32(cnt_l, rgl_off, n_sys, scantmp, st, n_launch));
     CU(c, launch_prep(w, st, n_launch));
     CU(c, launch_nbr_count(w, st, n_launch));
     CU(c, launch_scan_i32(w.deg, w.rowptr, n_atoms, scantmp, st, n_launch));
     CU(c, launch_scan_i32(w.degU, w.ustart, n_atoms, scantmp, st, n_launch));
-    collect_totals_kernel<<<1, 1, 0, st>>>(w.rowptr, w.ustart, n_atoms, rgs_off, rgl_off, n_sys, c->d_flags);
+    CU(c, launch_far_count(w, far_cnt, atom_b0, st, n_launch));
+    CU(c, launch_scan_i32(far_cnt, w.far_off, n_atoms, scantmp, st, n_launch));
+    collect_totals_kernel<<<1, 1, 0, st>>>(w.rowptr, w.ustart, w.far_off, n_atoms, rgl_off, n_sys, c->d_flags);
     ++*n_launch;
     CU(c, cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));
     if (c->h_flags[0] & 1) return fail(c, EPNN_E_INVALID, "npad smaller than the number of atoms for at least one system");
     if (c->h_flags[0] & 2) return fail(c, EPNN_E_INVALID, "a system with zero (or negative) atoms was passed");
     if (c->h_flags[0] & 4) return fail(c, EPNN_E_INVALID, "species index outside the element table (n_x=%d has %d species)", c->n_x, c->n_species);
-    w.nnz = c->h_flags[1]; w.P = c->h_flags[2]; w.n_rg_small = c->h_flags[3]; w.n_rg_large = c->h_flags[4];
-    if (w.nnz < 0 || w.P < 0) return fail(c, EPNN_E_UNSUPPORTED, "neighbour list of one chunk exceeds 2^31 entries; lower chunk_atoms");
+    w.nnz = c->h_flags[1]; w.P = c->h_flags[2]; w.n_far = c->h_flags[3]; w.n_rg_large = c->h_flags[4];
+    if (w.nnz < 0 || w.P < 0 || w.n_far < 0) return fail(c, EPNN_E_UNSUPPORTED, "pair lists of one chunk exceed 2^31 entries; lower chunk_atoms");
     w.nsplit = 1;
     if (w.n_rg_large > 0) {
         int ns = div_up((int64_t)c->sm_count * 64, w.n_rg_large);
@@ -384,16 +406,18 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int* d_off_in, i
     ENS(B_PD, sizeof(double) * (size_t)(w.P + 1), w.pair_D, double*);
     ENS(B_E, sizeof(float) * ED * (size_t)(w.P + 1), w.e, float*);
     ENS(B_NEAR, (size_t)(w.P + 16), w.near, unsigned char*);
-    ENS(B_RGS, sizeof(int) * (size_t)(w.n_rg_small + 1), w.rg_small, int*);
+    ENS(B_PERM, (size_t)(w.P + 16), w.perm_j, unsigned char*);
+    ENS(B_FARLIST, sizeof(unsigned short) * (size_t)(w.n_far + 2), w.far_list, unsigned short*);
     ENS(B_RGL, sizeof(int) * (size_t)(w.n_rg_large + 1), w.rg_large, int*);
-    rg_fill_kernel<<<div_up(n_sys, 256), 256, 0, st>>>(n_sys, off_local, rgs_off, rgl_off, w.rg_small, w.rg_large);
+    rg_fill_kernel<<<div_up(n_sys, 256), 256, 0, st>>>(n_sys, off_local, rgl_off, w.rg_large);
     ++*n_launch;
     CU(c, cudaGetLastError());
     CU(c, launch_nbr_fill(w, st, n_launch));
+    CU(c, launch_far_fill(w, atom_b0, st, n_launch));
     tm.mark(2);
     if (stats) {
         stats->n_pairs_e += w.P;
-        stats->n_row_groups += w.n_rg_small + w.n_rg_large;
+        stats->n_row_groups += w.n_bundles + w.n_rg_large;
     }
     if (ws_out) *ws_out = w;
     if (neighbors_only) return EPNN_OK;
@@ -415,6 +439,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int* d_off_in, i
     CU(c, launch_atom<R>(w, ATOM_PROJECT, nullptr, nullptr, &msg[0], 1, nullptr, nullptr, st, n_launch));
     tm.mark(4);
     for (int t = 0; t < c->T; ++t) {
+        CU(c, launch_gnn_bundle<R>(w, msg[t], st, n_launch));
         CU(c, launch_gnn_pair<R>(w, msg[t], st, n_launch));
         tm.mark(3);
         const StepW<R>* next = t + 1 < c->T ? &msg[t + 1] : &pas[0];
@@ -423,6 +448,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int* d_off_in, i
     }
     // ---- EPN layer: T electron-passing passes (charge_gn.py:98-118)
     for (int t = 0; t < c->T; ++t) {
+        CU(c, launch_epn_bundle<R>(w, pas[t], st, n_launch));
         CU(c, launch_epn_pair<R>(w, pas[t], st, n_launch));
         tm.mark(5);
         if (t + 1 < c->T)
@@ -518,9 +544,9 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
         tm.mark(1);
         Workspace w;
         if (c->precision == 64)
-            rc = run_chunk<double>(c, ns, na, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
+            rc = run_chunk<double>(c, ns, na, off + s0, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
         else
-            rc = run_chunk<float>(c, ns, na, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
+            rc = run_chunk<float>(c, ns, na, off + s0, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
         if (rc != EPNN_OK) return rc;
         if (stats && w.P > 0) {
             count_near_kernel<<<div_up(w.P, 256), 256, 0, st>>>(w.P, w.near, d_near_count);
@@ -594,7 +620,7 @@ extern "C" int epnn_neighbors(epnn_ctx* c, int64_t n_sys, const int32_t* off, co
         CU(c, cudaMemsetAsync(bs, 0, sizeof(int) * (size_t)na, st));
         CU(c, cudaMemsetAsync(bq, 0, sizeof(float) * (size_t)ns, st));
         Workspace w;
-        rc = run_chunk<float>(c, ns, na, d_off, a0, bx, bs, bq, nullptr, nullptr, nullptr, nullptr, tm, &n_launch, true, &w);
+        rc = run_chunk<float>(c, ns, na, off + s0, d_off, a0, bx, bs, bq, nullptr, nullptr, nullptr, nullptr, tm, &n_launch, true, &w);
         if (rc != EPNN_OK) return rc;
         h_rowptr.resize((size_t)na + 1); h_col.resize((size_t)w.nnz + 1); h_pid.resize((size_t)w.nnz + 1); h_near.resize((size_t)w.P + 1);
         CU(c, cudaMemcpyAsync(h_rowptr.data(), w.rowptr, sizeof(int) * ((size_t)na + 1), cudaMemcpyDeviceToHost, st));

@@ -16,6 +16,7 @@
 template <typename R> struct EpnArgs {
     int64_t P;
     const int* pair_i; const int* pair_j; const unsigned char* near; const float* e;
+    const int* atom_sys; const int* sys_off;
     const R* u; const R* v;
     const R* Cw; const R* W2; const R* b2; const R* w3;
     R* delta;
@@ -46,9 +47,16 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) epn_pair_kern
 
     for (int64_t tile = (int64_t)blockIdx.x * NW + warp; tile < n_tiles; tile += (int64_t)gridDim.x * NW) {
         const int64_t p = tile * 32 + lane;
-        const bool valid = p < a.P;
-        slot_i[lane] = valid ? a.pair_i[p] : -1;
-        slot_j[lane] = valid ? a.pair_j[p] : -1;
+        bool valid = p < a.P;
+        int pi = -1, pj = -1;
+        if (valid) {                                  // pairs of small systems belong to the bundle kernel
+            pi = a.pair_i[p]; pj = a.pair_j[p];
+            const int sys = a.atom_sys[pi];
+            valid = a.sys_off[sys + 1] - a.sys_off[sys] > SMALL_MAX;
+        }
+        if (!__any_sync(0xffffffffu, valid)) continue;
+        slot_i[lane] = valid ? pi : -1;
+        slot_j[lane] = valid ? pj : -1;
         const R nearf = valid ? (R)a.near[p] : R(0);
         const int64_t rows_left = a.P - tile * 32;
         const float4* esrc = reinterpret_cast<const float4*>(a.e + tile * 32 * ED);
@@ -141,10 +149,10 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) epn_pair_kern
 
 template <typename R>
 cudaError_t launch_epn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* nl) {
-    if (w.P == 0) return cudaSuccess;
+    if (w.P == 0 || w.n_rg_large == 0) return cudaSuccess;
     constexpr int NW = 8;
     EpnArgs<R> ea;
-    ea.P = w.P; ea.pair_i = w.pair_i; ea.pair_j = w.pair_j; ea.near = w.near; ea.e = w.e;
+    ea.P = w.P; ea.pair_i = w.pair_i; ea.pair_j = w.pair_j; ea.near = w.near; ea.e = w.e; ea.atom_sys = w.atom_sys; ea.sys_off = w.sys_off;
     ea.u = (const R*)w.u; ea.v = (const R*)w.v; ea.Cw = sw.Cw; ea.W2 = sw.W2; ea.b2 = sw.b2; ea.w3 = sw.W3;
     ea.delta = (R*)w.delta;
     const size_t smem = sizeof(R) * (ED * HID + HID * HID + 2 * HID + (size_t)NW * (32 * ED + 32 * HID)) + sizeof(int) * NW * 64;

@@ -8,13 +8,13 @@
 // with u = A^T a, v = B^T a + b1 from the per-atom kernel and C^T e_ij only for pairs with e != 0.
 // The linear last layer (W3, b3) is applied per atom afterwards (epnn_atom.cu).
 //
-// Work unit = one warp on a "row group" of 4 consecutive atoms i of one system.  A tile is
-// 4 rows x 8 j-slots = 32 pair slots; thread (pg, og) owns row pg and hidden columns og*4..og*4+3,
+// This file is the LARGE-system variant (n > SMALL_MAX, e.g. the 2220-atom protein); small systems take the
+// bundle kernel (epnn_bundle.cu).  Work unit = one warp on a "row group" of 4 consecutive atoms i of one system.
+// A tile is 4 rows x 8 j-slots = 32 pair slots; thread (pg, og) owns row pg and hidden columns og*4..og*4+3,
 // so the sum over j stays in registers (FP64 accumulators) and is written once: no atomics, fixed order.
 //   near phase : 8 CSR neighbours per row at a time; C^T e via tile_gemm<48>, then tile_gemm<32>
-//   far phase  : SMALL systems (n <= 64): the complement of the row's neighbour bitmask (incl. self) and
-//                the weighted pad slot, 8 at a time;  LARGE systems: 8 consecutive j with e != 0 members
-//                masked out, the j range optionally split across warps (partial sums, fixed order).
+//   far phase  : 8 consecutive j at a time with the e != 0 members masked out; the j range is split across
+//                warps when there are few row groups (partial-sum planes, added in fixed order per atom).
 #include "epnn_internal.cuh"
 
 template <typename R> struct GnnArgs {
@@ -26,12 +26,6 @@ template <typename R> struct GnnArgs {
     const R* Cw; const R* W2; const R* b2; const R* b1;
     R* S;
 };
-
-__device__ __forceinline__ int kth_set_bit64(unsigned long long m, int k) {   // k-th (0-based) set bit; k < popc(m)
-    const unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
-    const int pl = __popc(lo);
-    return k < pl ? (int)__fns(lo, 0, k + 1) : 32 + (int)__fns(hi, 0, k - pl + 1);
-}
 
 template <typename R, bool LARGE, int NW>
 __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kernel(const GnnArgs<R> a) {
@@ -122,51 +116,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kern
         }
 
         // ---------------------------------------------------------------- far phase
-        if (!LARGE) {
-            unsigned long long emask = 0ull;
-            for (int k = rp0; k < rp1; ++k) emask |= 1ull << (a.col[k] - a0);
-            const unsigned long long all = n >= 64 ? ~0ull : ((1ull << n) - 1ull);
-            const unsigned long long farm = rowok ? (~emask & all) : 0ull;     // includes the self pair
-            const int nfar = __popcll(farm);
-            const bool has_pad = rowok && padn > 0;
-            int maxslots = nfar + (has_pad ? 1 : 0);
-            maxslots = max(maxslots, __shfl_xor_sync(0xffffffffu, maxslots, 8));
-            maxslots = max(maxslots, __shfl_xor_sync(0xffffffffu, maxslots, 16));
-            const R padw = (R)padn;
-            for (int b0 = 0; b0 < maxslots; b0 += 8) {
-                {
-                    const int k = b0 + og;
-                    int j = -2;
-                    if (k < nfar) j = a0 + kth_set_bit64(farm, k);
-                    else if (k == nfar && has_pad) j = -1;
-                    slot_j[lane] = j;
-                }
-                __syncwarp();
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const int jj = slot_j[pg * 8 + s];
-                    Vec4<R> z = vzero<R>();
-                    if (jj >= -1) {
-                        const Vec4<R> vj = jj >= 0 ? ldv(a.v + (int64_t)jj * HID + og * 4) : b1v;
-                        z.x = relu(ur.x + vj.x); z.y = relu(ur.y + vj.y); z.z = relu(ur.z + vj.z); z.w = relu(ur.w + vj.w);
-                    }
-                    stv(at2 + tile_off(pg * 8 + s, og, HID), z);
-                }
-                __syncwarp();
-                zero_acc(acc);
-                tile_gemm<R, HID, HID>(at2, sW2, og * 4, acc, pg);
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const int jj = slot_j[pg * 8 + s];
-                    if (jj >= -1) {
-                        const R wgt = jj >= 0 ? R(1) : padw;
-                        rs0 += (double)(wgt * relu(acc[s][0] + b2v.x)); rs1 += (double)(wgt * relu(acc[s][1] + b2v.y));
-                        rs2 += (double)(wgt * relu(acc[s][2] + b2v.z)); rs3 += (double)(wgt * relu(acc[s][3] + b2v.w));
-                    }
-                }
-                __syncwarp();
-            }
-        } else {
+        {
             int clen = (n + a.nsplit - 1) / a.nsplit;
             clen = (clen + 7) & ~7;
             const int jlo = min(a1, a0 + split * clen), jhi = min(a1, jlo + clen);
@@ -248,13 +198,7 @@ cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t
     ga.u = (const R*)w.u; ga.v = (const R*)w.v; ga.Cw = sw.Cw; ga.W2 = sw.W2; ga.b2 = sw.b2; ga.b1 = sw.b1;
     ga.S = (R*)w.S;
     cudaError_t e = cudaSuccess;
-    if (w.n_rg_small > 0) {
-        ga.rg_atom = w.rg_small; ga.n_units = w.n_rg_small; ga.nsplit = 1;
-        e = launch_one<R, false, 8>(ga, w.sm_count, st);
-        ++*nl;
-        if (e != cudaSuccess) return e;
-    }
-    if (w.n_rg_large > 0) {
+    if (w.n_rg_large > 0) {      // small systems (n <= SMALL_MAX) are handled by the bundle kernel (epnn_bundle.cu)
         ga.rg_atom = w.rg_large; ga.n_units = w.n_rg_large * w.nsplit; ga.nsplit = w.nsplit;
         e = launch_one<R, true, 8>(ga, w.sm_count, st);
         ++*nl;

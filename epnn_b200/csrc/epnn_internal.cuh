@@ -12,7 +12,8 @@
 #define HD 48           // h_dim
 #define ED 48           // e_dim
 #define UPD_IN 80       // [h | M]
-#define SMALL_MAX 64    // systems with n <= SMALL_MAX take the bitmask ("small") GNN path
+#define SMALL_MAX 48    // systems with n <= SMALL_MAX are packed into warp-private "bundles" (epnn_bundle.cu)
+#define BUNDLE_ATOMS SMALL_MAX   // max atoms of one bundle (whole systems only)
 #define MAX_SPECIES 16
 
 // ------------------------------------------------------------------------------------------------
@@ -150,8 +151,10 @@ struct Workspace {
     int* atom_sys;
     int* deg; int* degU; int* rowptr; int* ustart; int* col; int* pid;
     int* pair_i; int* pair_j; double* pair_D; float* e; unsigned char* near;
-    int* rg_small; int n_rg_small;     // first atom of every 4-row group of systems with n <= SMALL_MAX
-    int* rg_large; int n_rg_large; int nsplit;
+    int2* bundle; int n_bundles;       // (first atom, atom count) of every bundle of small systems (n <= SMALL_MAX)
+    int* bundle_nat; unsigned char* perm_j;   // atoms of the bundle (at its first atom); rank of a pair's j inside its tile
+    int* far_off; unsigned short* far_list; int64_t n_far;   // per-bundle list of the GNN's e == 0 ("far") ordered pairs
+    int* rg_large; int n_rg_large; int nsplit;    // 4-row groups of the large systems
     void* h; void* S; void* u; void* v; void* delta;   // precision-dependent (float or double)
     double* q;
 };
@@ -165,6 +168,10 @@ cudaError_t launch_nbr_fill(const Workspace& w, cudaStream_t st, int* n_launch);
 cudaError_t launch_edges_dense(int n, const float* xyz, float* e, cudaStream_t st);
 cudaError_t upload_rbf_centers(const double* mu);
 
+cudaError_t launch_far_count(const Workspace& w, int* far_cnt, int* atom_b0, cudaStream_t st, int* n_launch);
+cudaError_t launch_far_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* n_launch);
+template <typename R> cudaError_t launch_gnn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
+template <typename R> cudaError_t launch_epn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_epn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 // mode bits for the per-atom kernel
