@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
     R* eb = uv + BUNDLE_ATOMS * 64 + (EPN ? 0 : BUNDLE_ATOMS * HID + BUNDLE_ATOMS);   // [32][48] e tile, then [32][32] z tile
     R* wgt = eb + 32 * ED;                           // [32]
     int* sl_i = reinterpret_cast<int*>(sx + HID + NW * L::PW) + warp * L::PI;
-    int* sl_j = sl_i + 32;                           // local atom index of the pair's j (near) / code of j (far)
+    int* sl_c = sl_i + 32;                           // packed slot code: local i | local j << 8 (0xFF = pad pseudo-atom), -1 = empty
     int* sl_p = sl_i + 64;                           // near: position of the slot when the tile is sorted by j
     int* sl_t = sl_i + 96;                           // near: j targets in that sorted order
 
@@ -141,15 +141,14 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
         const int p0 = a.ustart[atom0], p1 = a.ustart[atom0 + nat];
         const int ntile = (p1 - p0 + 31) >> 5;
         // ---- software prefetch (registers) of tile 0: indices + e rows
-        int n_i = -1, n_j = -1, n_p = lane;
-        R n_near = R(0);
+        int n_i = 0, n_j = 0;                        // raw (global) indices of the prefetched tile; rebased when consumed
+        unsigned char n_x = 0;                       // near flag (EPN) / j-order position (GNN)
         float4 er[ED / 4];
         auto fetch_tile = [&](int tb) {
             const int rows = min(32, p1 - tb);
-            n_i = -1; n_j = -1; n_p = lane; n_near = R(0);
             if (lane < rows) {
-                n_i = a.pair_i[tb + lane] - atom0; n_j = a.pair_j[tb + lane] - atom0;
-                if (EPN) n_near = (R)a.near[tb + lane]; else n_p = a.perm_j[tb + lane];
+                n_i = a.pair_i[tb + lane]; n_j = a.pair_j[tb + lane];
+                n_x = EPN ? a.near[tb + lane] : a.perm_j[tb + lane];
             }
             const float4* esrc = reinterpret_cast<const float4*>(a.e + (int64_t)tb * ED);
 #pragma unroll
@@ -187,9 +186,13 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
         for (int t = 0; t < ntile; ++t) {
             const int tb = p0 + t * 32;
             const bool ok = lane < min(32, p1 - tb);
-            const R nearf = n_near;
-            sl_i[lane] = n_i; sl_j[lane] = n_j;
-            if (!EPN) { sl_p[lane] = n_p; sl_t[n_p] = n_j; }
+            const R nearf = ok ? (R)n_x : R(0);
+            {
+                const int li = ok ? n_i - atom0 : -1, lj = ok ? n_j - atom0 : -1;
+                const int lp = ok ? (int)n_x : lane;
+                sl_c[lane] = ok ? (li | (lj << 8)) : -1;
+                if (!EPN) { sl_i[lane] = li; sl_p[lane] = lp; sl_t[lp] = lj; }
+            }
 #pragma unroll
             for (int m = 0; m < ED / 4; ++m) {                          // prefetched e rows -> swizzled tile
                 const int f = lane + 32 * m;
@@ -205,15 +208,22 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
 
             R part[8];
             R acc[8][4];
-#pragma unroll
+            int code[8];                                               // this thread's 8 slots: i | j << 8, or -1
+            {
+                const int4 c0 = *reinterpret_cast<const int4*>(sl_c + pg * 8);
+                const int4 c1 = *reinterpret_cast<const int4*>(sl_c + pg * 8 + 4);
+                code[0] = c0.x; code[1] = c0.y; code[2] = c0.z; code[3] = c0.w;
+                code[4] = c1.x; code[5] = c1.y; code[6] = c1.z; code[7] = c1.w;
+            }
+#pragma unroll 1
             for (int dir = 0; dir < 2; ++dir) {
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     const int slot = pg * 8 + s;
-                    int ii = sl_i[slot], jj = sl_j[slot];
+                    int ii = code[s] & 0xFF, jj = (code[s] >> 8) & 0xFF;
                     if (dir) { const int tmp = ii; ii = jj; jj = tmp; }
                     Vec4<R> z = vzero<R>();
-                    if (ii >= 0) {
+                    if (code[s] >= 0) {
                         const Vec4<R> ui = ldv(uv + ii * 64 + og * 4);
                         const Vec4<R> vj = ldv(uv + jj * 64 + HID + og * 4);
                         z.x = relu(ce[s][0] + ui.x + vj.x); z.y = relu(ce[s][1] + ui.y + vj.y);
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                         f = fma(relu(acc[s][1] + b2v.y), xv.y, f);
                         f = fma(relu(acc[s][2] + b2v.z), xv.z, f);
                         f = fma(relu(acc[s][3] + b2v.w), xv.w, f);
-                        part[s] = dir ? part[s] - f : f;
+                        part[s] = dir ? part[s] - f : f;      // (dir is a run-time value now: the dir loop is not unrolled)
                     }
                 } else {
                     Vec4<R> val[8];
@@ -295,7 +305,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                         li = n_code >> 8; lj = n_code & 0xFF;
                         if (lj == 0xFF) wv = padw[li];
                     }
-                    sl_i[lane] = li; sl_j[lane] = lj; wgt[lane] = wv;
+                    sl_c[lane] = li < 0 ? -1 : (li | (lj << 8)); wgt[lane] = wv;
                 }
                 {
                     const int k = f0 + (t + 1) * 32 + lane;
@@ -303,13 +313,19 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                 }
                 __syncwarp();
                 int tg[8];
+                {
+                    const int4 c0 = *reinterpret_cast<const int4*>(sl_c + pg * 8);
+                    const int4 c1 = *reinterpret_cast<const int4*>(sl_c + pg * 8 + 4);
+                    tg[0] = c0.x; tg[1] = c0.y; tg[2] = c0.z; tg[3] = c0.w; tg[4] = c1.x; tg[5] = c1.y; tg[6] = c1.z; tg[7] = c1.w;
+                }
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     const int slot = pg * 8 + s;
-                    const int ii = sl_i[slot], jj = sl_j[slot];
-                    tg[s] = ii;
+                    const int ii = tg[s] & 0xFF, jj = (tg[s] >> 8) & 0xFF;
+                    const bool live = tg[s] >= 0;
+                    tg[s] = live ? ii : -1;
                     Vec4<R> z = vzero<R>();
-                    if (ii >= 0) {
+                    if (live) {
                         const Vec4<R> ui = ldv(uv + ii * 64 + og * 4);
                         const Vec4<R> vj = jj == 0xFF ? xv : ldv(uv + jj * 64 + HID + og * 4);
                         z.x = relu(ui.x + vj.x); z.y = relu(ui.y + vj.y); z.z = relu(ui.z + vj.z); z.w = relu(ui.w + vj.w);
