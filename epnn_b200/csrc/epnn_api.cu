@@ -19,7 +19,7 @@ struct DevBuf {
 };
 
 struct PackedOffsets {           // element offsets into the packed device weight buffer (same for float/double)
-    struct Step { size_t Ah64, Aq64, Ax64, Cw, b1, W2, b2, W3, b3; };
+    struct Step { size_t Ah64, Aq64, Ax64, Wx64, Cw, b1, W2, b2, W3, b3; };
     std::vector<Step> msg, pas;
     size_t U1, c1, U2, c2, U3, c3;
     size_t total;
@@ -35,6 +35,7 @@ struct epnn_ctx {
     double* wd = nullptr;        // packed weights, double
     std::vector<DevBuf> bufs;    // grow-only workspaces, indexed by enum below
     std::vector<int2> h_bundles; // host staging of the bundle table of the current chunk
+    std::vector<int> h_large;    // host staging: big systems of the chunk + their cell bases
     int* d_flags = nullptr;      // [0] error bits, [1..4] totals (nnz, P, n_far, n_rg_large)
     int* h_flags = nullptr;      // pinned mirror
     int64_t hidden_atoms = 0;    // atoms covered by the retained hidden state
@@ -46,7 +47,7 @@ static thread_local std::string g_create_err;
 
 enum {
     B_XYZ, B_SPECIES, B_OFF, B_Q, B_NPAD, B_ATOMSYS, B_DEG, B_DEGU, B_ROWPTR, B_USTART, B_COL, B_PID, B_PI, B_PJ, B_PD,
-    B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_ATOMB0, B_BNAT, B_PERM, B_H, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
+    B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_ATOMB0, B_BNAT, B_PERM, B_LARGESYS, B_GRID, B_CELLCNT, B_CELLSTART, B_CELLATOMS, B_DTMP, B_H, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
     B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_COUNT
 };
 
@@ -109,6 +110,11 @@ static void pack_step(std::vector<double>& P, const PackedOffsets::Step& o, cons
         P[o.Aq64 + 32 + c] = W1[(F + n_x + 48) * 32 + c];
         P[o.b1 + c] = b1[c];
     }
+    for (int f = 0; f < n_x; ++f)                 // raw x-rows (dense compatibility path: arbitrary x features)
+        for (int c = 0; c < 32; ++c) {
+            P[o.Wx64 + f * 64 + c] = W1[f * 32 + c];
+            P[o.Wx64 + f * 64 + 32 + c] = W1[(F + f) * 32 + c];
+        }
     for (int s = 0; s < n_species; ++s)
         for (int c = 0; c < 32; ++c) {
             P[o.Ax64 + s * 64 + c] = Z[s] * (double)W1[c] + (double)W1[(1 + s) * 32 + c];
@@ -121,6 +127,12 @@ template <typename R> static StepW<R> step_view(const R* base, const PackedOffse
     s.Ah64 = base + o.Ah64; s.Aq64 = base + o.Aq64; s.Ax64 = base + o.Ax64; s.Cw = base + o.Cw; s.b1 = base + o.b1;
     s.W2 = base + o.W2; s.b2 = base + o.b2; s.W3 = base + o.W3; s.b3 = base + o.b3;
     return s;
+}
+template <typename R> static DenseW<R> dense_view(const R* base, const PackedOffsets::Step& o) {
+    DenseW<R> d;
+    d.Wx64 = base + o.Wx64; d.Ah64 = base + o.Ah64; d.Aq64 = base + o.Aq64; d.Cw = base + o.Cw; d.b1 = base + o.b1;
+    d.W2 = base + o.W2; d.b2 = base + o.b2; d.W3 = base + o.W3; d.b3 = base + o.b3;
+    return d;
 }
 template <typename R> static UpdW<R> upd_view(const R* base, const PackedOffsets& po) {
     UpdW<R> u;
@@ -187,7 +199,8 @@ extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_
     size_t cur = 0;
     auto step_offsets = [&](bool is_pass) {
         PackedOffsets::Step o;
-        o.Ah64 = take(cur, 48 * 64); o.Aq64 = take(cur, 64); o.Ax64 = take(cur, MAX_SPECIES * 64); o.Cw = take(cur, 48 * 32);
+        o.Ah64 = take(cur, 48 * 64); o.Aq64 = take(cur, 64); o.Ax64 = take(cur, MAX_SPECIES * 64); o.Wx64 = take(cur, 16 * 64);
+        o.Cw = take(cur, 48 * 32);
         o.b1 = take(cur, 32); o.W2 = take(cur, 32 * 32); o.b2 = take(cur, 32);
         o.W3 = take(cur, is_pass ? 32 : 32 * 32); o.b3 = take(cur, is_pass ? 1 : 32);
         return o;
@@ -372,6 +385,36 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
         if (!hb.empty()) CU(c, cudaMemcpyAsync(w.bundle, hb.data(), sizeof(int2) * hb.size(), cudaMemcpyHostToDevice, st));
     }
 
+    // ---- cell lists for the big systems of the chunk (host knows the sizes; budgets give the cell bases without a sync)
+    CellWork cw;
+    memset(&cw, 0, sizeof(cw));
+    {
+        std::vector<int>& hl = c->h_large;
+        hl.clear();
+        std::vector<int> base;
+        long long cells = 0, big_atoms = 0;
+        for (int s = 0; s < n_sys; ++s) {
+            const int n = h_off[s + 1] - h_off[s];
+            if (n > CELL_MIN) { hl.push_back(s); base.push_back((int)cells); cells += 4ll * n + 64; big_atoms += n; }
+        }
+        if (cells + 1 >= (1ll << 31)) return fail(c, EPNN_E_UNSUPPORTED, "cell grid exceeds 2^31 cells; lower chunk_atoms");
+        cw.n_large = (int)hl.size(); cw.n_cells = (int)cells;
+        if (cw.n_large) {
+            hl.insert(hl.end(), base.begin(), base.end());
+            int* dl;
+            ENS(B_LARGESYS, sizeof(int) * hl.size(), dl, int*);
+            CU(c, cudaMemcpyAsync(dl, hl.data(), sizeof(int) * hl.size(), cudaMemcpyHostToDevice, st));
+            cw.large_sys = dl; cw.large_base = dl + cw.n_large;
+            ENS(B_GRID, sizeof(CellGrid) * ((size_t)n_sys + 1), cw.grid, CellGrid*);
+            ENS(B_CELLCNT, sizeof(int) * ((size_t)cells + 2), cw.cell_cnt, int*);
+            ENS(B_CELLSTART, sizeof(int) * ((size_t)cells + 2), cw.cell_start, int*);
+            ENS(B_CELLATOMS, sizeof(int) * ((size_t)big_atoms + 1), cw.cell_atoms, int*);
+            int* st2;
+            ENS(B_SCANTMP, sizeof(int) * (((size_t)cells > nmax ? (size_t)cells : nmax) / 1024 + 2), st2, int*);
+            scantmp = st2;
+        }
+    }
+
     CU(c, cudaMemsetAsync(c->d_flags, 0, 8 * sizeof(int), st));
     sys_prep_kernel<<<div_up(n_sys + 1, 256), 256, 0, st>>>(n_sys, d_off_in, base, off_local, d_npad_in, npad_local, cnt_l, c->d_flags);
     species_check_kernel<<<div_up(n_atoms, 256), 256, 0, st>>>(n_atoms, d_species, c->n_species, c->d_flags);
@@ -379,7 +422,8 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     CU(c, cudaGetLastError());
     CU(c, launch_scan_i32(cnt_l, rgl_off, n_sys, scantmp, st, n_launch));
     CU(c, launch_prep(w, st, n_launch));
-    CU(c, launch_nbr_count(w, st, n_launch));
+    CU(c, launch_cell_build(w, cw, scantmp, st, n_launch));
+    CU(c, launch_nbr_count(w, cw, st, n_launch));
     CU(c, launch_scan_i32(w.deg, w.rowptr, n_atoms, scantmp, st, n_launch));
     CU(c, launch_scan_i32(w.degU, w.ustart, n_atoms, scantmp, st, n_launch));
     CU(c, launch_far_count(w, far_cnt, atom_b0, st, n_launch));
@@ -412,7 +456,8 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     rg_fill_kernel<<<div_up(n_sys, 256), 256, 0, st>>>(n_sys, off_local, rgl_off, w.rg_large);
     ++*n_launch;
     CU(c, cudaGetLastError());
-    CU(c, launch_nbr_fill(w, st, n_launch));
+    if (cw.n_large) ENS(B_DTMP, sizeof(double) * (size_t)(w.nnz + 1), cw.Dtmp, double*);
+    CU(c, launch_nbr_fill(w, cw, st, n_launch));
     CU(c, launch_far_fill(w, atom_b0, st, n_launch));
     tm.mark(2);
     if (stats) {
@@ -685,11 +730,52 @@ extern "C" int epnn_get_hidden(epnn_ctx* c, float* h_out, int64_t n_floats) {
     return EPNN_OK;
 }
 
-// Implemented in epnn_dense.cu once the compat kernels land; until then fail loudly (never silently fall back).
+template <typename R>
+static int dense_impl(epnn_ctx* c, int B, int N, const float* h, const float* e, const float* x, const float* q,
+                      const float* mask, float* q_out) {
+    cudaStream_t st = c->stream;
+    const size_t rows = (size_t)B * N, pairs = rows * N;
+    const int F = c->n_x + HD + 1;
+    void* p; int rc;
+    float *dh, *de, *dx, *dq, *dm, *dout;
+    R *da, *dnm, *duv, *dmsg;
+#define ENS(which, bytes, var, type) do { if ((rc = ensure(c, which, (bytes), &p)) != EPNN_OK) return rc; var = (type)p; } while (0)
+    ENS(B_H, sizeof(float) * pairs * HD, dh, float*);
+    ENS(B_E, sizeof(float) * pairs * ED, de, float*);
+    ENS(B_XYZ, sizeof(float) * pairs * c->n_x, dx, float*);
+    ENS(B_Q, sizeof(float) * pairs, dq, float*);
+    ENS(B_DELTA, sizeof(float) * pairs, dm, float*);
+    ENS(B_OUT32, sizeof(float) * rows, dout, float*);
+    ENS(B_S, sizeof(R) * rows * F, da, R*);
+    ENS(B_QD, sizeof(R) * rows, dnm, R*);
+    ENS(B_U, sizeof(R) * rows * 64, duv, R*);
+    ENS(B_V, sizeof(R) * rows * HID, dmsg, R*);
+#undef ENS
+    CU(c, cudaMemcpyAsync(dh, h, sizeof(float) * pairs * HD, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(de, e, sizeof(float) * pairs * ED, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(dx, x, sizeof(float) * pairs * c->n_x, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(dq, q, sizeof(float) * pairs, cudaMemcpyHostToDevice, st));
+    CU(c, cudaMemcpyAsync(dm, mask, sizeof(float) * pairs, cudaMemcpyHostToDevice, st));
+    const R* wb = sizeof(R) == 4 ? (const R*)c->wf : (const R*)c->wd;
+    std::vector<DenseW<R>> msg(c->T), pas(c->T);
+    for (int t = 0; t < c->T; ++t) { msg[t] = dense_view<R>(wb, c->po.msg[t]); pas[t] = dense_view<R>(wb, c->po.pas[t]); }
+    const UpdW<R> upd = upd_view<R>(wb, c->po);
+    CU(c, launch_dense_forward<R>(B, N, c->n_x, c->T, dh, de, dx, dq, dm, msg.data(), upd, pas.data(), da, dnm, duv, dmsg, dout, st));
+    CU(c, cudaMemcpyAsync(q_out, dout, sizeof(float) * rows, cudaMemcpyDeviceToHost, st));
+    CU(c, cudaStreamSynchronize(st));
+    c->hidden_atoms = 0;
+    return EPNN_OK;
+}
+
 extern "C" int epnn_infer_dense(epnn_ctx* c, int32_t B, int32_t N, const float* h, const float* e, const float* x,
                                 const float* q, const float* mask, float* q_out) {
-    (void)B; (void)N; (void)h; (void)e; (void)x; (void)q; (void)mask; (void)q_out;
-    return fail(c, EPNN_E_UNSUPPORTED, "epnn_infer_dense is not implemented yet");
+    if (!c) return EPNN_E_INVALID;
+    if (B < 0 || N < 0) return fail(c, EPNN_E_INVALID, "epnn_infer_dense: negative shape");
+    if (B == 0 || N == 0) return EPNN_OK;
+    if (!h || !e || !x || !q || !mask || !q_out) return fail(c, EPNN_E_INVALID, "epnn_infer_dense: NULL pointer");
+    CU(c, cudaSetDevice(c->device));
+    return c->precision == 64 ? dense_impl<double>(c, B, N, h, e, x, q, mask, q_out)
+                              : dense_impl<float>(c, B, N, h, e, x, q, mask, q_out);
 }
 
 // ------------------------------------------------------------------------------------------------

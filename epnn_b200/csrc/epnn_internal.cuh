@@ -15,6 +15,7 @@
 #define SMALL_MAX 48    // systems with n <= SMALL_MAX are packed into warp-private "bundles" (epnn_bundle.cu)
 #define BUNDLE_ATOMS SMALL_MAX   // max atoms of one bundle (whole systems only)
 #define MAX_SPECIES 16
+#define CELL_MIN 512     // systems with more atoms than this build their neighbour list through a cell list
 
 // ------------------------------------------------------------------------------------------------
 // Vector of 4 reals: one LDS.128 / LDG.128 for float, two for double.
@@ -140,6 +141,20 @@ template <typename R> struct UpdW {       // shared update MLP 80 -> 32 -> 32 ->
     const R* U1; const R* c1; const R* U2; const R* c2; const R* U3; const R* c3;
 };
 
+template <typename R> struct DenseW {      // raw (un-split) views of one MLP step
+    const R* Wx64;   // [n_x][64]  x-rows of the first layer: cols 0..31 a_i block, 32..63 a_j block
+    const R* Ah64;   // [48][64]
+    const R* Aq64;   // [64]
+    const R* Cw;     // [48][32]
+    const R* b1;     // [32]
+    const R* W2; const R* b2; const R* W3; const R* b3;
+};
+
+template <typename R>
+cudaError_t launch_dense_forward(int B, int N, int n_x, int T, const float* h, const float* e, const float* x, const float* q,
+                                 const float* mask, const DenseW<R>* msgw, const UpdW<R>& upd, const DenseW<R>* pasw,
+                                 R* a, R* node_mask, R* uv, R* msg, float* q_out, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------------
 // Per-chunk device workspace (pointers into grow-only buffers owned by the ctx).
 struct Workspace {
@@ -159,12 +174,22 @@ struct Workspace {
     double* q;
 };
 
+// Cell-list state of the big systems of one chunk (epnn_neighbor.cu)
+struct CellGrid { float ox, oy, oz, inv_h; int nx, ny, nz, base; };
+struct CellWork {
+    int n_large; int n_cells;                 // big systems in the chunk; total cell budget (host-side prefix of 4 n + 64)
+    const int* large_sys; const int* large_base;   // [n_large] system index, first cell
+    CellGrid* grid;                           // [n_sys] (entries of big systems only)
+    int* cell_cnt; int* cell_start; int* cell_atoms; double* Dtmp;
+};
+
 // ------------------------------------------------------------------------------------------------
 // Launchers (defined in the .cu files; every one enqueues on `st` and returns cudaGetLastError()).
 cudaError_t launch_prep(const Workspace& w, cudaStream_t st, int* n_launch);
-cudaError_t launch_nbr_count(const Workspace& w, cudaStream_t st, int* n_launch);
+cudaError_t launch_cell_build(const Workspace& w, const CellWork& cw, int* scantmp, cudaStream_t st, int* n_launch);
+cudaError_t launch_nbr_count(const Workspace& w, const CellWork& cw, cudaStream_t st, int* n_launch);
 cudaError_t launch_scan_i32(const int* in, int* out, int n, int* tmp, cudaStream_t st, int* n_launch);
-cudaError_t launch_nbr_fill(const Workspace& w, cudaStream_t st, int* n_launch);
+cudaError_t launch_nbr_fill(const Workspace& w, const CellWork& cw, cudaStream_t st, int* n_launch);
 cudaError_t launch_edges_dense(int n, const float* xyz, float* e, cudaStream_t st);
 cudaError_t upload_rbf_centers(const double* mu);
 

@@ -69,13 +69,95 @@ cudaError_t launch_prep(const Workspace& w, cudaStream_t st, int* nl) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Brute-force (within a system) neighbour search: one thread per atom row, two passes (count, fill).
-// Columns come out ascending because j is scanned ascending.
+// Cell lists for big systems (n > CELL_MIN atoms).  Every such system gets its own uniform grid with cell edge
+// h >= 3.01 A (> the 3.0 A cutoff with a margin far above float32 rounding of the cell coordinate), enlarged if the
+// bounding box would need more cells than the host-side budget (4 n + 64).  Atoms are binned with integer atomics
+// (only the ORDER inside a cell depends on scheduling; rows are sorted afterwards, so the lists do not).
+__global__ void cell_setup_kernel(int n_large, const int* __restrict__ large_sys, const int* __restrict__ large_base,
+                                  const int* __restrict__ sys_off, const float* __restrict__ xyz, CellGrid* __restrict__ grid) {
+    __shared__ float red[6][8];
+    const int s = large_sys[blockIdx.x];
+    const int a0 = sys_off[s], a1 = sys_off[s + 1];
+    float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int i = a0 + threadIdx.x; i < a1; i += blockDim.x)
+        for (int d = 0; d < 3; ++d) { const float v = xyz[3 * i + d]; lo[d] = fminf(lo[d], v); hi[d] = fmaxf(hi[d], v); }
+    for (int d = 0; d < 3; ++d) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+        if ((threadIdx.x & 31) == 0) { red[d][threadIdx.x >> 5] = lo[d]; red[3 + d][threadIdx.x >> 5] = hi[d]; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int d = 0; d < 3; ++d)
+            for (int w = 0; w < nw; ++w) { lo[d] = fminf(lo[d], red[d][w]); hi[d] = fmaxf(hi[d], red[3 + d][w]); }
+        const long long budget = 4ll * (a1 - a0) + 64;
+        float h = 3.01f;
+        int nx, ny, nz;
+        for (;;) {
+            nx = (int)floorf((hi[0] - lo[0]) / h) + 1; ny = (int)floorf((hi[1] - lo[1]) / h) + 1; nz = (int)floorf((hi[2] - lo[2]) / h) + 1;
+            if ((long long)nx * ny * nz <= budget) break;
+            h *= 1.26f;                              // ~2x fewer cells per round
+        }
+        CellGrid g;
+        g.ox = lo[0]; g.oy = lo[1]; g.oz = lo[2]; g.inv_h = 1.0f / h;
+        g.nx = nx; g.ny = ny; g.nz = nz; g.base = large_base[blockIdx.x];
+        grid[s] = g;
+    }
+}
+
+__device__ __forceinline__ void cell_of(const CellGrid& g, float x, float y, float z, int& cx, int& cy, int& cz) {
+    cx = min(g.nx - 1, max(0, (int)floorf((x - g.ox) * g.inv_h)));
+    cy = min(g.ny - 1, max(0, (int)floorf((y - g.oy) * g.inv_h)));
+    cz = min(g.nz - 1, max(0, (int)floorf((z - g.oz) * g.inv_h)));
+}
+
+// pass 0: histogram (cell_cnt) ; pass 1: scatter into cell order (cell_atoms) using cell_start + a cursor
+template <int PASS>
+__global__ void cell_bin_kernel(int n_atoms, const int* __restrict__ atom_sys, const int* __restrict__ sys_off,
+                                const float* __restrict__ xyz, const CellGrid* __restrict__ grid, int* __restrict__ cell_cnt,
+                                const int* __restrict__ cell_start, int* __restrict__ cell_atoms) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_atoms) return;
+    const int s = atom_sys[i];
+    if (sys_off[s + 1] - sys_off[s] <= CELL_MIN) return;
+    const CellGrid g = grid[s];
+    int cx, cy, cz;
+    cell_of(g, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], cx, cy, cz);
+    const int c = g.base + (cz * g.ny + cy) * g.nx + cx;
+    const int k = atomicAdd(cell_cnt + c, 1);
+    if (PASS == 1) cell_atoms[cell_start[c] + k] = i;
+}
+
+cudaError_t launch_cell_build(const Workspace& w, const CellWork& cw, int* scantmp, cudaStream_t st, int* nl) {
+    if (cw.n_large == 0) return cudaSuccess;
+    cell_setup_kernel<<<cw.n_large, 256, 0, st>>>(cw.n_large, cw.large_sys, cw.large_base, w.sys_off, w.xyz, cw.grid);
+    cudaError_t e = cudaMemsetAsync(cw.cell_cnt, 0, sizeof(int) * (size_t)cw.n_cells, st);
+    if (e != cudaSuccess) return e;
+    cell_bin_kernel<0><<<div_up(w.n_atoms, 256), 256, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, cw.grid, cw.cell_cnt, nullptr, nullptr);
+    *nl += 2;
+    e = launch_scan_i32(cw.cell_cnt, cw.cell_start, cw.n_cells, scantmp, st, nl);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(cw.cell_cnt, 0, sizeof(int) * (size_t)cw.n_cells, st);
+    if (e != cudaSuccess) return e;
+    cell_bin_kernel<1><<<div_up(w.n_atoms, 256), 256, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, cw.grid, cw.cell_cnt, cw.cell_start, cw.cell_atoms);
+    ++*nl;
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Neighbour search: one thread per atom row, two passes (count, fill).  Systems with n <= CELL_MIN scan their own
+// atoms (columns come out ascending because j is scanned ascending); bigger systems walk the 27 cells around the
+// atom and sort the row afterwards, so both paths emit identical, ascending, bit-exact lists.
 template <bool FILL>
 __global__ void nbr_kernel(int n_atoms, const int* __restrict__ atom_sys, const int* __restrict__ sys_off,
                            const float* __restrict__ xyz, int* __restrict__ deg, int* __restrict__ degU,
                            const int* __restrict__ rowptr, const int* __restrict__ ustart, int* __restrict__ col,
-                           int* __restrict__ pair_i, int* __restrict__ pair_j, double* __restrict__ pair_D) {
+                           int* __restrict__ pair_i, int* __restrict__ pair_j, double* __restrict__ pair_D,
+                           const CellGrid* __restrict__ grid, const int* __restrict__ cell_start,
+                           const int* __restrict__ cell_atoms, double* __restrict__ Dtmp) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_atoms) return;
     const int s = atom_sys[i];
@@ -84,27 +166,71 @@ __global__ void nbr_kernel(int n_atoms, const int* __restrict__ atom_sys, const 
     int c = 0, cu = 0;
     int wp = 0, wu = 0;
     if (FILL) { wp = rowptr[i]; wu = ustart[i]; }
-    for (int j = a0; j < a1; ++j) {
-        if (j == i) continue;
-        const float xj = xyz[3 * j], yj = xyz[3 * j + 1], zj = xyz[3 * j + 2];
-        if (far_reject(xi, yi, zi, xj, yj, zj)) continue;
-        const double D = dist64(xi, yi, zi, xj, yj, zj);
-        if (D < 3.0) {
-            if (FILL) {
-                col[wp + c] = j;
-                if (j > i) { pair_i[wu + cu] = i; pair_j[wu + cu] = j; pair_D[wu + cu] = D; }
+    if (a1 - a0 <= CELL_MIN) {
+        for (int j = a0; j < a1; ++j) {
+            if (j == i) continue;
+            const float xj = xyz[3 * j], yj = xyz[3 * j + 1], zj = xyz[3 * j + 2];
+            if (far_reject(xi, yi, zi, xj, yj, zj)) continue;
+            const double D = dist64(xi, yi, zi, xj, yj, zj);
+            if (D < 3.0) {
+                if (FILL) {
+                    col[wp + c] = j;
+                    if (j > i) { pair_i[wu + cu] = i; pair_j[wu + cu] = j; pair_D[wu + cu] = D; }
+                }
+                ++c;
+                cu += (j > i);
             }
-            ++c;
-            cu += (j > i);
+        }
+    } else {
+        const CellGrid g = grid[s];
+        int cx, cy, cz;
+        cell_of(g, xi, yi, zi, cx, cy, cz);
+        for (int dz = -1; dz <= 1; ++dz) {
+            const int z = cz + dz;
+            if (z < 0 || z >= g.nz) continue;
+            for (int dy = -1; dy <= 1; ++dy) {
+                const int y = cy + dy;
+                if (y < 0 || y >= g.ny) continue;
+                const int x0 = max(cx - 1, 0), x1 = min(cx + 1, g.nx - 1);
+                const int cb = g.base + (z * g.ny + y) * g.nx;
+                const int k0 = cell_start[cb + x0], k1 = cell_start[cb + x1 + 1];     // x-neighbours are contiguous cells
+                for (int k = k0; k < k1; ++k) {
+                    const int j = cell_atoms[k];
+                    if (j == i) continue;
+                    const float xj = xyz[3 * j], yj = xyz[3 * j + 1], zj = xyz[3 * j + 2];
+                    if (far_reject(xi, yi, zi, xj, yj, zj)) continue;
+                    const double D = dist64(xi, yi, zi, xj, yj, zj);
+                    if (D < 3.0) {
+                        if (FILL) { col[wp + c] = j; Dtmp[wp + c] = D; }
+                        ++c;
+                        cu += (j > i);
+                    }
+                }
+            }
+        }
+        if (FILL) {
+            for (int p = 1; p < c; ++p) {                       // insertion sort of the row by column index
+                const int jv = col[wp + p];
+                const double dv = Dtmp[wp + p];
+                int q = p - 1;
+                while (q >= 0 && col[wp + q] > jv) { col[wp + q + 1] = col[wp + q]; Dtmp[wp + q + 1] = Dtmp[wp + q]; --q; }
+                col[wp + q + 1] = jv; Dtmp[wp + q + 1] = dv;
+            }
+            int k = 0;
+            for (int p = 0; p < c; ++p) {
+                const int j = col[wp + p];
+                if (j > i) { pair_i[wu + k] = i; pair_j[wu + k] = j; pair_D[wu + k] = Dtmp[wp + p]; ++k; }
+            }
         }
     }
     if (!FILL) { deg[i] = c; degU[i] = cu; }
 }
 
-cudaError_t launch_nbr_count(const Workspace& w, cudaStream_t st, int* nl) {
+cudaError_t launch_nbr_count(const Workspace& w, const CellWork& cw, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0) return cudaSuccess;
     nbr_kernel<false><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, w.deg, w.degU,
-                                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+                                                              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                              cw.grid, cw.cell_start, cw.cell_atoms, nullptr);
     ++*nl;
     return cudaGetLastError();
 }
@@ -156,10 +282,11 @@ __global__ void edge_desc_kernel(int64_t P, const double* __restrict__ pair_D, f
     if (p < P && k == 0) near[p] = (unsigned char)flag[lp];
 }
 
-cudaError_t launch_nbr_fill(const Workspace& w, cudaStream_t st, int* nl) {
+cudaError_t launch_nbr_fill(const Workspace& w, const CellWork& cw, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0) return cudaSuccess;
     nbr_kernel<true><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, nullptr, nullptr,
-                                                             w.rowptr, w.ustart, w.col, w.pair_i, w.pair_j, w.pair_D);
+                                                             w.rowptr, w.ustart, w.col, w.pair_i, w.pair_j, w.pair_D,
+                                                             cw.grid, cw.cell_start, cw.cell_atoms, cw.Dtmp);
     ++*nl;
     nbr_rev_kernel<<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.rowptr, w.ustart, w.degU, w.col, w.pid);
     ++*nl;

@@ -279,3 +279,57 @@ def test_error_behaviour(engines, mixed):
         eng.infer_batch(np.array([0, 0], np.int32), np.zeros((0, 3), np.float32), np.zeros(0, np.int32), np.zeros(1, np.float32))
     q = eng.infer_batch(offs, xyz, sp, Q, 41)                      # ctx still usable after errors
     assert np.isfinite(q).all()
+
+
+# ------------------------------------------------------------------------------------------------ big systems (cell list)
+def test_cell_list_neighbors_big_system(engines):
+    """~30k-atom protein-like system (Galectin-3C tiled): the cell-list build must give the same sorted CSR as an
+    exact float64 evaluation of the reference predicate on the candidate pairs found by a KD-tree."""
+    from scipy.spatial import cKDTree
+    from epnn_b200 import synth
+    offs, xyz, sp, Q = synth.protein_like(30000, 9, seed=3)
+    eng = engines("decay_model_weights")
+    x64 = xyz.astype(np.float64)
+    cand = cKDTree(x64).query_pairs(3.05, output_type="ndarray")
+    d = np.abs(x64[cand[:, 1]] - x64[cand[:, 0]])
+    sq = d * d
+    D = np.sqrt((sq[:, 0] + sq[:, 1]) + sq[:, 2])
+    C = (np.cos(np.pi * D / 3.0) + 1.0) / 2.0
+    C[D >= 3.0] = 0
+    C[D <= 0.0] = 1.0
+    mu = np.linspace(0.1, 3.0, 48)
+    near = np.zeros(len(D), bool)
+    for k0 in range(0, len(D), 200000):
+        sl = slice(k0, k0 + 200000)
+        e = (C[sl, None] * np.exp(-2.0 * (D[sl, None] - mu[None]) ** 2)).astype(np.float32)
+        near[sl] = e.max(1) > np.float32(1e-5)
+    for which, sel in ((1, D < 3.0), (0, near)):
+        ij = cand[sel]
+        rows = np.concatenate([ij[:, 0], ij[:, 1]])
+        cols = np.concatenate([ij[:, 1], ij[:, 0]])
+        order = np.lexsort((cols, rows))
+        exp_col = cols[order].astype(np.int32)
+        exp_rp = np.zeros(len(xyz) + 1, np.int64)
+        np.add.at(exp_rp, rows + 1, 1)
+        exp_rp = np.cumsum(exp_rp).astype(np.int32)
+        rowptr, col = eng.neighbors(offs, xyz, which=which)
+        assert np.array_equal(rowptr, exp_rp) and np.array_equal(col, exp_col), which
+    assert exp_rp[-1] / len(xyz) > 8                       # a protein-like density (about 11 near neighbours per atom)
+
+
+def test_big_system_charges_and_chunk_of_mixed_sizes(engines, weights, protein, mixed):
+    """One call holding a cell-list system (2220 atoms), a brute-force large system and small bundles."""
+    w = weights["decay_model_weights"]
+    eng = engines("decay_model_weights", 64)
+    offs, xyz, sp, Q = mixed.batch([5, 6, 7], 9)
+    pz = O.species_from_Z(protein["Z"], 9)
+    n, m = len(pz), 300
+    offs2 = np.concatenate([offs, [offs[-1] + n, offs[-1] + n + m]]).astype(np.int32)
+    xyz2 = np.concatenate([xyz, protein["xyz"], protein["xyz"][500:500 + m]]).astype(np.float32)
+    sp2 = np.concatenate([sp, pz, pz[500:500 + m]]).astype(np.int32)
+    Q2 = np.concatenate([Q, [2.0, -1.0]]).astype(np.float32)
+    npad = np.array([41, 41, 41, n, m + 7], np.int32)
+    q, q64 = eng.infer_batch(offs2, xyz2, sp2, Q2, npad, want_f64=True)
+    ref = O.predict_batch(w, offs2, xyz2, sp2, Q2, npad)
+    assert np.abs(q64 - ref).max() < 1e-8
+    assert np.abs(q[offs[-1]:offs[-1] + n] - protein["preds"]).max() < TOL
