@@ -30,6 +30,8 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
+
 # name -> (restype, argtypes); mirrors include/epnn_b200.h one to one
 SIGNATURES = {
     "epnn_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
@@ -48,6 +50,7 @@ SIGNATURES = {
     "epnn_get_hidden": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "epnn_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "epnn_host_free": (C.c_int, [C.c_void_p]),
+    "epnn_set_shard": (C.c_int, [C.c_void_p, C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p]),
     "epnn_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "epnn_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "epnn_rbf_centers": (C.c_int, [C.c_void_p]),

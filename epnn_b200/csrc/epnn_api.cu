@@ -29,6 +29,9 @@ struct epnn_ctx {
     int device = 0, T = 0, n_x = 0, n_species = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
     int precision = 32, timing = 0, keep_hidden = 0;
+    int shard_rank = 0, shard_world = 1;
+    epnn_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
     int64_t chunk_atoms = 4 * 1024 * 1024;
     PackedOffsets po;
     float* wf = nullptr;         // packed weights, float
@@ -341,6 +344,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     Workspace w;
     memset(&w, 0, sizeof(w));
     w.n_atoms = n_atoms; w.n_sys = n_sys; w.sm_count = c->sm_count;
+    w.shard_rank = c->shard_rank; w.shard_world = c->shard_world;
     w.xyz = d_xyz; w.species = d_species; w.Qsys = d_Q;
     void* p;
     int rc;
@@ -480,12 +484,18 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     std::vector<StepW<R>> msg(c->T), pas(c->T);
     for (int t = 0; t < c->T; ++t) { msg[t] = step_view<R>(wb, c->po.msg[t]); pas[t] = step_view<R>(wb, c->po.pas[t]); }
 
+    // Sharding only concerns the large-system pair kernels; a chunk without large systems runs replicated.
+    const bool sharded = c->shard_world > 1 && w.n_rg_large > 0;
+    if (!sharded) { w.shard_rank = 0; w.shard_world = 1; }
     // ---- GNN layer: T message-passing steps (charge_gn.py:60-74)
     CU(c, launch_atom<R>(w, ATOM_PROJECT, nullptr, nullptr, &msg[0], 1, nullptr, nullptr, st, n_launch));
     tm.mark(4);
     for (int t = 0; t < c->T; ++t) {
-        CU(c, launch_gnn_bundle<R>(w, msg[t], st, n_launch));
+        if (sharded) CU(c, cudaMemsetAsync(w.S, 0, sizeof(R) * HID * (size_t)n_atoms * w.nsplit, st));
+        if (!sharded || c->shard_rank == 0) CU(c, launch_gnn_bundle<R>(w, msg[t], st, n_launch));
         CU(c, launch_gnn_pair<R>(w, msg[t], st, n_launch));
+        if (sharded && c->allreduce(c->allreduce_user, w.S, (size_t)HID * n_atoms * w.nsplit, sizeof(R) == 8, (void*)st) != 0)
+            return fail(c, EPNN_E_CUDA, "allreduce callback failed (GNN step %d)", t);
         tm.mark(3);
         const StepW<R>* next = t + 1 < c->T ? &msg[t + 1] : &pas[0];
         CU(c, launch_atom<R>(w, ATOM_UPDATE | ATOM_PROJECT, &msg[t], &upd, next, 0, nullptr, nullptr, st, n_launch));
@@ -493,8 +503,11 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     }
     // ---- EPN layer: T electron-passing passes (charge_gn.py:98-118)
     for (int t = 0; t < c->T; ++t) {
-        CU(c, launch_epn_bundle<R>(w, pas[t], st, n_launch));
+        if (sharded) CU(c, cudaMemsetAsync(w.delta, 0, sizeof(R) * (size_t)(w.P + 1), st));
+        if (!sharded || c->shard_rank == 0) CU(c, launch_epn_bundle<R>(w, pas[t], st, n_launch));
         CU(c, launch_epn_pair<R>(w, pas[t], st, n_launch));
+        if (sharded && w.P > 0 && c->allreduce(c->allreduce_user, w.delta, (size_t)w.P, sizeof(R) == 8, (void*)st) != 0)
+            return fail(c, EPNN_E_CUDA, "allreduce callback failed (EPN pass %d)", t);
         tm.mark(5);
         if (t + 1 < c->T)
             CU(c, launch_atom<R>(w, ATOM_QUPDATE | ATOM_PROJECT, nullptr, nullptr, &pas[t + 1], 0, nullptr, nullptr, st, n_launch));
@@ -779,6 +792,14 @@ extern "C" int epnn_infer_dense(epnn_ctx* c, int32_t B, int32_t N, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------
+extern "C" int epnn_set_shard(epnn_ctx* c, int rank, int world, epnn_allreduce_fn fn, void* user) {
+    if (!c) return EPNN_E_INVALID;
+    if (world < 1 || rank < 0 || rank >= world) return fail(c, EPNN_E_INVALID, "epnn_set_shard: rank %d not in [0,%d)", rank, world);
+    if (world > 1 && !fn) return fail(c, EPNN_E_INVALID, "epnn_set_shard: an allreduce callback is required for world > 1");
+    c->shard_rank = rank; c->shard_world = world; c->allreduce = fn; c->allreduce_user = user;
+    return EPNN_OK;
+}
+
 extern "C" int epnn_get_stream(epnn_ctx* c, void** stream_out) {
     if (!c || !stream_out) return EPNN_E_INVALID;
     *stream_out = (void*)c->stream;

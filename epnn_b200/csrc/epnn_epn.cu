@@ -14,7 +14,7 @@
 #include "epnn_internal.cuh"
 
 template <typename R> struct EpnArgs {
-    int64_t P;
+    int64_t P; int64_t tile_begin, tile_end;
     const int* pair_i; const int* pair_j; const unsigned char* near; const float* e;
     const int* atom_sys; const int* sys_off;
     const R* u; const R* v;
@@ -43,9 +43,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) epn_pair_kern
     const int pg = lane >> 3, og = lane & 7;
     const Vec4<R> b2v = ldv(sb2 + og * 4);
     const Vec4<R> w3v = ldv(sw3 + og * 4);
-    const int64_t n_tiles = (a.P + 31) / 32;
-
-    for (int64_t tile = (int64_t)blockIdx.x * NW + warp; tile < n_tiles; tile += (int64_t)gridDim.x * NW) {
+    for (int64_t tile = a.tile_begin + (int64_t)blockIdx.x * NW + warp; tile < a.tile_end; tile += (int64_t)gridDim.x * NW) {
         const int64_t p = tile * 32 + lane;
         bool valid = p < a.P;
         int pi = -1, pj = -1;
@@ -159,7 +157,10 @@ cudaError_t launch_epn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t
     cudaError_t e = cudaFuncSetAttribute(epn_pair_kernel<R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int per_sm = sizeof(R) == 4 ? 2 : 1;
-    int64_t grid = ((w.P + 31) / 32 + NW - 1) / NW;
+    const int64_t n_tiles = (w.P + 31) / 32;
+    ea.tile_begin = n_tiles * w.shard_rank / w.shard_world; ea.tile_end = n_tiles * (w.shard_rank + 1) / w.shard_world;
+    int64_t grid = (ea.tile_end - ea.tile_begin + NW - 1) / NW;
+    if (grid < 1) return cudaSuccess;
     if (grid > (int64_t)w.sm_count * per_sm) grid = (int64_t)w.sm_count * per_sm;
     epn_pair_kernel<R, NW><<<(int)grid, NW * 32, smem, st>>>(ea);
     ++*nl;

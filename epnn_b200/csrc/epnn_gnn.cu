@@ -18,7 +18,7 @@
 #include "epnn_internal.cuh"
 
 template <typename R> struct GnnArgs {
-    const int* rg_atom; int n_units; int nsplit; int n_atoms;
+    const int* rg_atom; int unit_begin; int n_units; int nsplit; int n_atoms;
     const int* atom_sys; const int* sys_off; const int* npad;
     const int* rowptr; const int* col; const int* pid;
     const float* e;
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kern
     const Vec4<R> b2v = ldv(sb2 + og * 4);
     const Vec4<R> b1v = ldv(sb1 + og * 4);
 
-    for (int unit = blockIdx.x * NW + warp; unit < a.n_units; unit += gridDim.x * NW) {
+    for (int unit = a.unit_begin + blockIdx.x * NW + warp; unit < a.n_units; unit += gridDim.x * NW) {
         const int rg = LARGE ? unit / a.nsplit : unit;
         const int split = LARGE ? unit - rg * a.nsplit : 0;
         const int i0 = a.rg_atom[rg];
@@ -184,7 +184,8 @@ static cudaError_t launch_one(const GnnArgs<R>& ga, int sm_count, cudaStream_t s
     cudaError_t e = cudaFuncSetAttribute(gnn_pair_kernel<R, LARGE, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int per_sm = sizeof(R) == 4 ? 2 : 1;
-    int grid = div_up(ga.n_units, NW);
+    int grid = div_up(ga.n_units - ga.unit_begin, NW);
+    if (grid < 1) return cudaSuccess;
     if (grid > sm_count * per_sm) grid = sm_count * per_sm;      // persistent: warps stride over the units
     gnn_pair_kernel<R, LARGE, NW><<<grid, NW * 32, smem, st>>>(ga);
     return cudaGetLastError();
@@ -199,7 +200,9 @@ cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t
     ga.S = (R*)w.S;
     cudaError_t e = cudaSuccess;
     if (w.n_rg_large > 0) {      // small systems (n <= SMALL_MAX) are handled by the bundle kernel (epnn_bundle.cu)
-        ga.rg_atom = w.rg_large; ga.n_units = w.n_rg_large * w.nsplit; ga.nsplit = w.nsplit;
+        const int64_t total = (int64_t)w.n_rg_large * w.nsplit;      // this rank's contiguous slice of the work units
+        ga.rg_atom = w.rg_large; ga.nsplit = w.nsplit;
+        ga.unit_begin = (int)(total * w.shard_rank / w.shard_world); ga.n_units = (int)(total * (w.shard_rank + 1) / w.shard_world);
         e = launch_one<R, true, 8>(ga, w.sm_count, st);
         ++*nl;
     }

@@ -170,6 +170,7 @@ struct Workspace {
     int* bundle_nat; unsigned char* perm_j;   // atoms of the bundle (at its first atom); rank of a pair's j inside its tile
     int* far_off; unsigned short* far_list; int64_t n_far;   // per-bundle list of the GNN's e == 0 ("far") ordered pairs
     int* rg_large; int n_rg_large; int nsplit;    // 4-row groups of the large systems
+    int shard_rank, shard_world;                  // this rank's slice of the large-system pair kernels (world 1 = everything)
     void* h; void* S; void* u; void* v; void* delta;   // precision-dependent (float or double)
     double* q;
 };

@@ -61,6 +61,16 @@ class Engine:
         self._check(self.lib.epnn_get_stream(self._h, C.byref(p)))
         return p.value or 0
 
+    def set_shard(self, rank: int, world: int, group=None):
+        """Split the large-system pair kernels over ``world`` ranks (epnn_set_shard); the per-step exchange is a
+        ``torch.distributed.all_reduce`` on this ctx's stream.  ``world == 1`` switches sharding off."""
+        if world > 1:
+            from .shard import make_allreduce
+            self._shard_cb, self.shard_state = make_allreduce(group, self.device, self.stream)
+        else:
+            self._shard_cb, self.shard_state = _capi.ALLREDUCE_FN(0), None
+        self._check(self.lib.epnn_set_shard(self._h, rank, world, self._shard_cb, None))
+
     def measure_fp32_peak(self, repeats: int = 5) -> float:
         """Measured FP32 FMA peak of this GPU in TFLOP/s (epnn_measure_fp32_peak)."""
         out = C.c_double(0.0)

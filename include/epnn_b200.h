@@ -134,6 +134,19 @@ int epnn_get_hidden(epnn_ctx* ctx, float* h_out, int64_t n_floats);
 int epnn_host_alloc(void** ptr, size_t bytes);
 int epnn_host_free(void* ptr);
 
+/* Multi-GPU sharding of LARGE systems (n > 48 atoms; BASELINE config 5: one big system on several GPUs).
+ * Every rank is given the SAME epnn_infer_batch call.  Everything that is O(atoms) -- neighbour lists, per-atom
+ * kernels, the charge reduction -- is replicated; the two kernels that carry the work are split by contiguous
+ * ranges (message-passing: rows of the exact all-pairs sum; electron passing: tiles of the near-pair list), the
+ * rest of their output buffers is zero-filled, and after each of the T steps / T passes the library calls
+ * `allreduce` once (sum over ranks, in place, on the ctx stream) on the partial-sum buffer S, respectively on the
+ * per-pair transfers delta.  Each element is non-zero on one rank only, so the sum is exact and the result is
+ * bit-identical to a single-GPU run whatever order the collective adds in.  The callback is the NVLink exchange
+ * step (torch.distributed / NCCL in this repo's host code); rank 0 also runs the small-system bundles.
+ *   allreduce(user, dev_ptr, count, is_double, stream) -> 0 on success.   world == 1 switches sharding off. */
+typedef int (*epnn_allreduce_fn)(void* user, void* dev_ptr, size_t count, int is_double, void* stream);
+int epnn_set_shard(epnn_ctx* ctx, int rank, int world, epnn_allreduce_fn allreduce, void* user);
+
 /* The CUDA stream (cudaStream_t, returned as void*) every kernel and copy of this ctx is enqueued on, so
  * that a caller can record its own CUDA events around a sequence of calls (bench.py does). */
 int epnn_get_stream(epnn_ctx* ctx, void** stream_out);

@@ -1,0 +1,68 @@
+"""Two real GPUs (skipped on a 1-GPU box): the sharded large-system path (epnn_set_shard + NCCL all-reduce per
+step / pass) must reproduce the single-GPU charges BIT FOR BIT, including a batch that mixes small systems in."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _inputs():
+    from epnn_b200 import synth
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = np.load(os.path.join(root, "tests", "golden", "protein.npz"))
+    sp = synth.species_from_Z(d["Z"], 9)
+    offs_s, xyz_s, sp_s, Q_s = synth.qm9_shaped(5, 9, seed=2)
+    n = len(sp)
+    offs = np.concatenate([offs_s, [offs_s[-1] + n, offs_s[-1] + n + 700]]).astype(np.int32)
+    xyz = np.concatenate([xyz_s, d["xyz"], d["xyz"][100:800]]).astype(np.float32)
+    spc = np.concatenate([sp_s, sp, sp[100:800]]).astype(np.int32)
+    Q = np.concatenate([Q_s, [2.0, -1.0]]).astype(np.float32)
+    npad = np.concatenate([np.full(5, 29), [n, 720]]).astype(np.int32)
+    return offs, xyz, spc, Q, npad
+
+
+def _worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from epnn_b200.checkpoint import load_weights
+        from epnn_b200.engine import Engine
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        offs, xyz, sp, Q, npad = _inputs()
+        for name in ("decay_model_weights", "model2_weights"):
+            w = load_weights(os.path.join(root, "tests", "golden", "checkpoints", name))
+            eng = Engine(w, device=rank)
+            single = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
+            eng.set_shard(rank, world)
+            sharded = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
+            assert eng.shard_state["error"] is None and eng.shard_state["calls"] == 2 * w.T
+            assert np.array_equal(single, sharded), (name, np.abs(single - sharded).max())
+            eng.set_shard(0, 1)
+            again = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1]
+            assert np.array_equal(single, again)
+            eng.close()
+        open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_sharded_large_system_is_bit_identical(tmp_path):
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
