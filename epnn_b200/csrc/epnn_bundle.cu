@@ -226,8 +226,8 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                     if (code[s] >= 0) {
                         const Vec4<R> ui = ldv(uv + ii * 64 + og * 4);
                         const Vec4<R> vj = ldv(uv + jj * 64 + HID + og * 4);
-                        z.x = relu(ce[s][0] + ui.x + vj.x); z.y = relu(ce[s][1] + ui.y + vj.y);
-                        z.z = relu(ce[s][2] + ui.z + vj.z); z.w = relu(ce[s][3] + ui.w + vj.w);
+                        Vec4<R> cv; cv.x = ce[s][0]; cv.y = ce[s][1]; cv.z = ce[s][2]; cv.w = ce[s][3];
+                        z = vrelu(vadd(vadd(cv, ui), vj));
                     }
                     stv(zt + tile_off(slot, og, HID), z);
                 }
@@ -249,8 +249,8 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                     int tg[8];
 #pragma unroll
                     for (int s = 0; s < 8; ++s) {
-                        val[s].x = relu(acc[s][0] + b2v.x); val[s].y = relu(acc[s][1] + b2v.y);
-                        val[s].z = relu(acc[s][2] + b2v.z); val[s].w = relu(acc[s][3] + b2v.w);
+                        Vec4<R> av; av.x = acc[s][0]; av.y = acc[s][1]; av.z = acc[s][2]; av.w = acc[s][3];
+                        val[s] = vrelu(vadd(av, b2v));
                     }
                     if (dir == 0) {                                    // targets i: the pair list is sorted by i already
 #pragma unroll
@@ -298,6 +298,8 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
             R acc[8][4];
             int n_code = (f0 + lane < f1) ? (int)a.far_list[f0 + lane] : -1;
             for (int t = 0; t < nft; ++t) {
+                int my_code;
+                R my_w;
                 {
                     int li = -1, lj = 0;
                     R wv = R(1);
@@ -305,18 +307,18 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                         li = n_code >> 8; lj = n_code & 0xFF;
                         if (lj == 0xFF) wv = padw[li];
                     }
-                    sl_c[lane] = li < 0 ? -1 : (li | (lj << 8)); wgt[lane] = wv;
+                    my_code = li < 0 ? -1 : (li | (lj << 8)); my_w = wv;
                 }
                 {
                     const int k = f0 + (t + 1) * 32 + lane;
                     n_code = k < f1 ? (int)a.far_list[k] : -1;
                 }
-                __syncwarp();
                 int tg[8];
-                {
-                    const int4 c0 = *reinterpret_cast<const int4*>(sl_c + pg * 8);
-                    const int4 c1 = *reinterpret_cast<const int4*>(sl_c + pg * 8 + 4);
-                    tg[0] = c0.x; tg[1] = c0.y; tg[2] = c0.z; tg[3] = c0.w; tg[4] = c1.x; tg[5] = c1.y; tg[6] = c1.z; tg[7] = c1.w;
+                R wcode[8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {                           // this thread's 8 slots, straight from the owner lanes
+                    tg[s] = __shfl_sync(0xffffffffu, my_code, pg * 8 + s);
+                    wcode[s] = __shfl_sync(0xffffffffu, my_w, pg * 8 + s);
                 }
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
@@ -328,7 +330,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                     if (live) {
                         const Vec4<R> ui = ldv(uv + ii * 64 + og * 4);
                         const Vec4<R> vj = jj == 0xFF ? xv : ldv(uv + jj * 64 + HID + og * 4);
-                        z.x = relu(ui.x + vj.x); z.y = relu(ui.y + vj.y); z.z = relu(ui.z + vj.z); z.w = relu(ui.w + vj.w);
+                        z = vrelu(vadd(ui, vj));
                     }
                     stv(zt + tile_off(slot, og, HID), z);
                 }
@@ -338,9 +340,8 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                 Vec4<R> val[8];
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
-                    const R wv = wgt[pg * 8 + s];
-                    val[s].x = wv * relu(acc[s][0] + b2v.x); val[s].y = wv * relu(acc[s][1] + b2v.y);
-                    val[s].z = wv * relu(acc[s][2] + b2v.z); val[s].w = wv * relu(acc[s][3] + b2v.w);
+                    Vec4<R> av; av.x = acc[s][0]; av.y = acc[s][1]; av.z = acc[s][2]; av.w = acc[s][3];
+                    val[s] = vscale(vrelu(vadd(av, b2v)), wcode[s]);
                 }
                 scatter_sorted<R>(val, tg, S, pg, og);
                 __syncwarp();

@@ -23,6 +23,33 @@ template <typename R> struct alignas(4 * sizeof(R)) Vec4 { R x, y, z, w; };
 
 template <typename R> __device__ __forceinline__ Vec4<R> vzero() { Vec4<R> v; v.x = v.y = v.z = v.w = R(0); return v; }
 template <typename R> __device__ __forceinline__ Vec4<R> vadd(Vec4<R> a, Vec4<R> b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; return a; }
+// FP32: two packed adds (Blackwell add.rn.f32x2, bit-identical to four scalar FADDs, half the FMA-pipe slots)
+template <> __device__ __forceinline__ Vec4<float> vadd<float>(Vec4<float> a, Vec4<float> b) {
+    unsigned long long a0, a1, b0, b1;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a0) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a1) : "f"(a.z), "f"(a.w));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(b0) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(b1) : "f"(b.z), "f"(b.w));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a0) : "l"(b0));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a1) : "l"(b1));
+    Vec4<float> r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a0));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.z), "=f"(r.w) : "l"(a1));
+    return r;
+}
+template <typename R> __device__ __forceinline__ Vec4<R> vscale(Vec4<R> a, R s) { a.x *= s; a.y *= s; a.z *= s; a.w *= s; return a; }
+template <> __device__ __forceinline__ Vec4<float> vscale<float>(Vec4<float> a, float s) {
+    unsigned long long a0, a1, ss;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a0) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(a1) : "f"(a.z), "f"(a.w));
+    asm("mov.b64 %0, {%1,%1};" : "=l"(ss) : "f"(s));
+    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a0) : "l"(ss));
+    asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a1) : "l"(ss));
+    Vec4<float> r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(a0));
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.z), "=f"(r.w) : "l"(a1));
+    return r;
+}
 template <typename R> __device__ __forceinline__ Vec4<R> vrelu(Vec4<R> a) {
     a.x = a.x > R(0) ? a.x : R(0); a.y = a.y > R(0) ? a.y : R(0);
     a.z = a.z > R(0) ? a.z : R(0); a.w = a.w > R(0) ? a.w : R(0); return a;
