@@ -383,13 +383,16 @@ def run_b200(args):
         if os.path.exists(tpath):
             try:
                 tj = json.load(open(tpath))
-                if tj.get("workload") == args.workload:
+                if tj.get("workload") == args.workload and not sharded_system:
+                    # ncu --set full capture of one launch (profiles/), scaled per atom to this run's launch size
                     traffic = tj["gnn_pair_dram_bytes_per_atom_per_launch"] * n_atoms / n_chunks
             except Exception:   # noqa: BLE001
                 traffic = None
         achieved = gnn_flops_step / (ms_gnn * 1e-3) * 1e-12
+        if sharded_system:
+            achieved /= world                # every rank ran 1/world of the launch's work: quote the per-GPU rate
         roofline = {
-            "kernel": "gnn_pair_kernel (message-passing pair MLP, FP32 SIMT)", "bound": "fp32",
+            "kernel": "bundle_kernel<float,8,GNN> / gnn_pair_kernel (message-passing pair MLP, FP32 SIMT, FFMA2)", "bound": "fp32",
             "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
             "peak_source": "FP32 FMA micro-benchmark measured in this run (epnn_measure_fp32_peak); MEASURED_PEAKS.json "
                            "holds no SIMT peak. north_star: pair MLP defaults to FP32 SIMT, tensor pipe unused",

@@ -46,7 +46,7 @@ typedef struct epnn_stats {
     int64_t n_atoms;
     int64_t n_pairs_e;        /* unordered pairs with 0 <= D < 3.0 A, i != j  (e_ij != 0 set) */
     int64_t n_pairs_near;     /* unordered pairs in the reference's is_near set (charge_gn.py:90-94) */
-    int64_t n_row_groups;     /* GNN work units (4 atom rows each) */
+    int64_t n_row_groups;     /* GNN work units: bundles of small systems + 4-row groups of large systems */
     int64_t n_chunks;         /* internal batches the call was split into */
     int64_t n_launches;       /* kernels launched by this call */
     float ms_total;           /* first H2D copy -> last D2H copy */
