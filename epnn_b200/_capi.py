@@ -63,10 +63,11 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(LIB_PATH):
-        raise ImportError(f"{LIB_PATH} not found: run `python __graft_entry__.py` (nvcc, sm_100a) first. "
+    path = os.environ.get("EPNN_B200_LIB", LIB_PATH)      # development hook: try an alternative build of the same ABI
+    if not os.path.exists(path):
+        raise ImportError(f"{path} not found: run `python __graft_entry__.py` (nvcc, sm_100a) first. "
                           "epnn_b200 has no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res

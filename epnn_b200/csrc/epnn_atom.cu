@@ -24,6 +24,9 @@ template <typename R> struct AtomArgs {
     float* q_out; double* q_out64;
 };
 
+#ifndef ATOM_NW
+#define ATOM_NW 12
+#endif
 #define ATOM_W_UPD (HID * HID + HID + UPD_IN * HID + HID + HID * HID + HID + HID * HD + HD)   // 6288
 #define ATOM_W_PROJ (HD * 64 + 64 + MAX_SPECIES * 64)                                       // 4160
 #define ATOM_TILE (32 * UPD_IN + 32 * HID)                                                  // 3584 per warp
@@ -233,7 +236,7 @@ template <typename R>
 cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd, const StepW<R>* next,
                         int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0) return cudaSuccess;
-    constexpr int NW = sizeof(R) == 4 ? 8 : 4;
+    constexpr int NW = sizeof(R) == 4 ? ATOM_NW : 4;
     AtomArgs<R> aa;
     memset(&aa, 0, sizeof(aa));
     aa.n_atoms = w.n_atoms; aa.mode = mode; aa.nsplit = w.nsplit; aa.h_is_zero = h_is_zero;

@@ -23,6 +23,10 @@
 // and the index lists come from global memory inside the tile loop.
 #include "epnn_internal.cuh"
 
+#ifndef EPN_NW
+#define EPN_NW 8
+#endif
+
 template <typename R> struct BundleArgs {
     int n_bundles; const int2* bundle;
     const int* ustart; const int* pair_i; const int* pair_j; const unsigned char* near; const float* e;
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
 template <typename R, bool EPN>
 static cudaError_t launch_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* nl) {
     if (w.n_bundles == 0) return cudaSuccess;
-    constexpr int NW = sizeof(R) == 4 ? 8 : 4;
+    constexpr int NW = sizeof(R) == 4 ? (EPN ? EPN_NW : 8) : 4;   // the EPN variant has no S accumulators: more warps fit
     BundleArgs<R> ba;
     ba.n_bundles = w.n_bundles; ba.bundle = w.bundle;
     ba.ustart = w.ustart; ba.pair_i = w.pair_i; ba.pair_j = w.pair_j; ba.near = w.near; ba.e = w.e;

@@ -333,3 +333,34 @@ def test_big_system_charges_and_chunk_of_mixed_sizes(engines, weights, protein, 
     ref = O.predict_batch(w, offs2, xyz2, sp2, Q2, npad)
     assert np.abs(q64 - ref).max() < 1e-8
     assert np.abs(q[offs[-1]:offs[-1] + n] - protein["preds"]).max() < TOL
+
+
+def test_bundle_boundaries_and_routing(engines, weights, protein):
+    """Sizes around the bundle capacity (48) and the small/large routing threshold, many 1-atom systems, systems
+    that exactly fill a bundle, pad sizes equal to / far above n -- all in one batch, FP64 kernels vs the oracle."""
+    w = weights["model2_weights"]
+    eng = engines("model2_weights", 64)
+    sizes = [1, 1, 1, 47, 1, 48, 49, 50, 24, 24, 24, 25, 23, 1, 48, 2, 46, 3]
+    pz = O.species_from_Z(protein["Z"], 9)
+    offs = [0]
+    xyz, sp, Q, npad = [], [], [], []
+    start = 0
+    for k, n in enumerate(sizes):
+        xyz.append(protein["xyz"][start:start + n])
+        sp.append(pz[start:start + n])
+        start += n + 5
+        offs.append(offs[-1] + n)
+        Q.append([0.0, 1.0, -1.0][k % 3])
+        npad.append(n if k % 2 else n + (k % 5) * 9)
+    offs = np.array(offs, np.int32)
+    xyz = np.concatenate(xyz).astype(np.float32)
+    sp = np.concatenate(sp).astype(np.int32)
+    Q = np.array(Q, np.float32)
+    npad = np.array(npad, np.int32)
+    q, q64 = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)
+    ref = O.predict_batch(w, offs, xyz, sp, Q, npad)
+    assert np.abs(q64 - ref).max() < 1e-8 * max(1.0, np.abs(ref).max())
+    assert eng.last_stats["n_row_groups"] > 0
+    # the FP32 default path on the same batch
+    q32 = engines("model2_weights").infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1]
+    assert np.abs(q32 - ref).max() < 5e-5 * max(1.0, np.abs(ref).max())
