@@ -96,8 +96,9 @@ def protein_like(n_atoms: int, n_x: int = 9, seed: int = 1):
     x0 = xyz.astype(np.float64) - cen
     r = np.linalg.norm(x0, axis=1).max()
     spacing = 2 * r / np.sqrt(3) + 1.5          # rotated copies overlap mildly at the faces; reject clashes below
+    from scipy.spatial import cKDTree
     out = []
-    placed = []
+    placed = []          # (centre, lazily built KD-tree holder, coordinates)
     c = 0
     for ix in range(side):
         for iy in range(side):
@@ -108,15 +109,17 @@ def protein_like(n_atoms: int, n_x: int = 9, seed: int = 1):
                     R = _random_rotations(rng, 1)[0]
                     x = x0 @ R.T + np.array([ix, iy, iz]) * spacing
                     ok = True
+                    cx = x.mean(0)
                     for prev in placed[-side * side - side - 1:]:
-                        if np.linalg.norm(prev.mean(0) - x.mean(0)) < 2 * r:
-                            from scipy.spatial import cKDTree
-                            if cKDTree(prev).query(x, k=1, distance_upper_bound=0.96)[0].min() < 0.96:
+                        if np.linalg.norm(prev[0] - cx) < 2 * r:
+                            if prev[1][0] is None:
+                                prev[1][0] = cKDTree(prev[2])
+                            if prev[1][0].query(x, k=1, distance_upper_bound=0.96)[0].min() < 0.96:
                                 ok = False
                                 break
                     if ok:
                         break
-                placed.append(x)
+                placed.append((x.mean(0), [None], x))
                 out.append(x)
                 c += 1
     x = np.concatenate(out)[:n_atoms].astype(np.float32)
