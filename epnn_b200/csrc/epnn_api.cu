@@ -29,6 +29,8 @@ struct epnn_ctx {
     int device = 0, T = 0, n_x = 0, n_species = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
     int precision = 32, timing = 0, keep_hidden = 0;
+    int far_tensor = 0;          // option "gnn_far_tensor"
+    float* w2split = nullptr;    // [T][2][32][32]: hi / lo parts of W2^T of every message MLP (tensor-core far kernel)
     int shard_rank = 0, shard_world = 1;
     epnn_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
@@ -231,6 +233,20 @@ extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_
         r += (size_t)K * 32 + 32;
         copy(po.pas[t].W2, 32 * 32); copy(po.pas[t].b2, 32); copy(po.pas[t].W3, 32); copy(po.pas[t].b3, 1);
     }
+    {   // 3xTF32 split of W2^T for the tensor-core far kernel: hi = W with the low 13 mantissa bits cleared, lo = W - hi
+        std::vector<float> ws((size_t)T * 2 * 32 * 32);
+        for (int t = 0; t < T; ++t)
+            for (int n = 0; n < 32; ++n)
+                for (int k = 0; k < 32; ++k) {
+                    const float wv = (float)P[po.msg[t].W2 + (size_t)k * 32 + n];
+                    uint32_t bits; memcpy(&bits, &wv, 4); bits &= 0xFFFFE000u;
+                    float hi; memcpy(&hi, &bits, 4);
+                    ws[((size_t)t * 2 + 0) * 1024 + n * 32 + k] = hi;
+                    ws[((size_t)t * 2 + 1) * 1024 + n * 32 + k] = wv - hi;
+                }
+        CUC(cudaMalloc(&c->w2split, ws.size() * sizeof(float)));
+        CUC(cudaMemcpy(c->w2split, ws.data(), ws.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     std::vector<float> Pf(po.total);
     for (size_t i = 0; i < po.total; ++i) Pf[i] = (float)P[i];
     CUC(cudaMalloc(&c->wf, po.total * sizeof(float)));
@@ -249,6 +265,7 @@ extern "C" void epnn_destroy(epnn_ctx* c) {
     for (DevBuf& b : c->bufs) if (b.p) cudaFree(b.p);
     if (c->wf) cudaFree(c->wf);
     if (c->wd) cudaFree(c->wd);
+    if (c->w2split) cudaFree(c->w2split);
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -263,6 +280,7 @@ extern "C" int epnn_set_option(epnn_ctx* c, const char* key, double value) {
         c->precision = (int)value;
     } else if (k == "timing") c->timing = value != 0;
     else if (k == "keep_hidden") c->keep_hidden = value != 0;
+    else if (k == "gnn_far_tensor") c->far_tensor = value != 0;
     else if (k == "chunk_atoms") {
         if (value < 64) return fail(c, EPNN_E_INVALID, "chunk_atoms must be >= 64");
         c->chunk_atoms = (int64_t)value;
@@ -442,9 +460,17 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     w.nnz = c->h_flags[1]; w.P = c->h_flags[2]; w.n_far = c->h_flags[3]; w.n_rg_large = c->h_flags[4];
     if (w.nnz < 0 || w.P < 0 || w.n_far < 0) return fail(c, EPNN_E_UNSUPPORTED, "pair lists of one chunk exceed 2^31 entries; lower chunk_atoms");
     w.nsplit = 1;
+    w.far_tc = 0;
     if (w.n_rg_large > 0) {
-        int ns = div_up((int64_t)c->sm_count * 64, w.n_rg_large);
-        w.nsplit = ns < 1 ? 1 : (ns > 32 ? 32 : ns);
+        if (c->far_tensor && sizeof(R) == 4) {       // tensor-core far kernel: CTA units = row group x column range
+            int ns = div_up((int64_t)c->sm_count * 8, w.n_rg_large);
+            ns = ns < 1 ? 1 : (ns > 15 ? 15 : ns);
+            w.far_tc = 1;
+            w.nsplit = ns + 1;                       // + the SIMT kernel's plane (near pairs, pad pair)
+        } else {
+            int ns = div_up((int64_t)c->sm_count * 64, w.n_rg_large);
+            w.nsplit = ns < 1 ? 1 : (ns > 32 ? 32 : ns);
+        }
     }
 
     ENS(B_COL, sizeof(int) * (size_t)(w.nnz + 1), w.col, int*);
@@ -493,6 +519,9 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     for (int t = 0; t < c->T; ++t) {
         if (sharded) CU(c, cudaMemsetAsync(w.S, 0, sizeof(R) * HID * (size_t)n_atoms * w.nsplit, st));
         if (!sharded || c->shard_rank == 0) CU(c, launch_gnn_bundle<R>(w, msg[t], st, n_launch));
+        if (w.far_tc)
+            CU(c, launch_gnn_far_tc(w, c->w2split + (size_t)t * 2048, c->w2split + (size_t)t * 2048 + 1024, (const float*)msg[t].b2,
+                                    w.nsplit - 1, st, n_launch));
         CU(c, launch_gnn_pair<R>(w, msg[t], st, n_launch));
         if (sharded && c->allreduce(c->allreduce_user, w.S, (size_t)HID * n_atoms * w.nsplit, sizeof(R) == 8, (void*)st) != 0)
             return fail(c, EPNN_E_CUDA, "allreduce callback failed (GNN step %d)", t);

@@ -18,7 +18,7 @@
 #include "epnn_internal.cuh"
 
 template <typename R> struct GnnArgs {
-    const int* rg_atom; int unit_begin; int n_units; int nsplit; int n_atoms;
+    const int* rg_atom; int unit_begin; int n_units; int nsplit; int n_atoms; int skip_far; int plane;
     const int* atom_sys; const int* sys_off; const int* npad;
     const int* rowptr; const int* col; const int* pid;
     const float* e;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kern
         }
 
         // ---------------------------------------------------------------- far phase
-        {
+        if (!a.skip_far) {
             int clen = (n + a.nsplit - 1) / a.nsplit;
             clen = (clen + 7) & ~7;
             const int jlo = min(a1, a0 + split * clen), jhi = min(a1, jlo + clen);
@@ -150,6 +150,8 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kern
                 }
                 __syncwarp();
             }
+        }
+        {
             if (split == 0 && padn > 0) {           // weighted pad pseudo-pair, one slot per row
                 Vec4<R> z = vzero<R>();
                 if (rowok) { z.x = relu(ur.x + b1v.x); z.y = relu(ur.y + b1v.y); z.z = relu(ur.z + b1v.z); z.w = relu(ur.w + b1v.w); }
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kern
 
         if (rowok) {
             Vec4<R> out; out.x = (R)rs0; out.y = (R)rs1; out.z = (R)rs2; out.w = (R)rs3;
-            stv(a.S + ((int64_t)split * a.n_atoms + i) * HID + og * 4, out);
+            stv(a.S + ((int64_t)(a.plane + split) * a.n_atoms + i) * HID + og * 4, out);
         }
     }
 }
@@ -200,8 +202,11 @@ cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t
     ga.S = (R*)w.S;
     cudaError_t e = cudaSuccess;
     if (w.n_rg_large > 0) {      // small systems (n <= SMALL_MAX) are handled by the bundle kernel (epnn_bundle.cu)
-        const int64_t total = (int64_t)w.n_rg_large * w.nsplit;      // this rank's contiguous slice of the work units
-        ga.rg_atom = w.rg_large; ga.nsplit = w.nsplit;
+        // tensor-core mode: this kernel does the near pairs + pad pair only (one unit per row group, last plane)
+        const int ns = w.far_tc ? 1 : w.nsplit;
+        ga.skip_far = w.far_tc; ga.plane = w.far_tc ? w.nsplit - 1 : 0;
+        const int64_t total = (int64_t)w.n_rg_large * ns;      // this rank's contiguous slice of the work units
+        ga.rg_atom = w.rg_large; ga.nsplit = ns;
         ga.unit_begin = (int)(total * w.shard_rank / w.shard_world); ga.n_units = (int)(total * (w.shard_rank + 1) / w.shard_world);
         e = launch_one<R, true, 8>(ga, w.sm_count, st);
         ++*nl;

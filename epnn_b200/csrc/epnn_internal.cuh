@@ -197,6 +197,8 @@ struct Workspace {
     int* bundle_nat; unsigned char* perm_j;   // atoms of the bundle (at its first atom); rank of a pair's j inside its tile
     int* far_off; unsigned short* far_list; int64_t n_far;   // per-bundle list of the GNN's e == 0 ("far") ordered pairs
     int* rg_large; int n_rg_large; int nsplit;    // 4-row groups of the large systems
+    int far_tc;                                   // 1: the far part of the big-system message sum runs on the tensor cores;
+                                                  //    planes [0, nsplit-1) of S are theirs, the SIMT kernel (near only) owns the last
     int shard_rank, shard_world;                  // this rank's slice of the large-system pair kernels (world 1 = everything)
     void* h; void* S; void* u; void* v; void* delta;   // precision-dependent (float or double)
     double* q;
@@ -225,6 +227,8 @@ cudaError_t launch_far_count(const Workspace& w, int* far_cnt, int* atom_b0, cud
 cudaError_t launch_far_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_gnn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_epn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
+cudaError_t launch_gnn_far_tc(const Workspace& w, const float* Whi, const float* Wlo, const float* b2, int nsplit_tc,
+                              cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_epn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 // mode bits for the per-atom kernel
