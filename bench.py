@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--chunk-atoms", type=int, default=0, help="override the library's internal batch size")
     ap.add_argument("--ref-molecules", type=int, default=2048, help="molecules per step of the CPU reference arm")
+    ap.add_argument("--gnn-far-tensor", type=int, default=0, choices=[0, 1],
+                    help="big systems: far part of the message sum on tcgen05 tensor cores (3xTF32) instead of FP32 SIMT")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
@@ -276,6 +278,8 @@ def run_b200(args):
     eng.set_option("timing", 1)
     if args.chunk_atoms:
         eng.set_option("chunk_atoms", args.chunk_atoms)
+    if args.gnn_far_tensor:
+        eng.set_option("gnn_far_tensor", 1)
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
     sharded_system = args.workload == "protein" and world > 1
     if sharded_system:                       # one big system: pair kernels split over the ranks, all-reduce per step / pass
@@ -416,7 +420,8 @@ def run_b200(args):
                if sharded_system else f"molecule-shards x{world}, no collective")
         desc.update({"checkpoint": args.checkpoint, "parallelism": par,
                      "l2": "inputs larger than L2 (no flush needed)" if n_atoms * 16 > 126e6 else "inputs smaller than L2",
-                     "atoms_per_gpu_per_step": n_atoms, "T": w.T, "precision": args.precision})
+                     "atoms_per_gpu_per_step": n_atoms, "T": w.T, "precision": args.precision,
+                     "gnn_far_tensor": args.gnn_far_tensor})
         line = {"metric": METRIC, "value": tot_atoms * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
                 "scaling": "strong" if sharded_system else "weak", "vs_baseline": None,

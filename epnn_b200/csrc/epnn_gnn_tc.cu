@@ -18,6 +18,8 @@
 //
 // The near (e != 0) pairs and the pad pseudo-pair stay on the FP32 SIMT kernel (epnn_gnn.cu, skip_far mode), written to
 // their own partial-sum plane; the per-atom kernel adds the planes in a fixed order.
+#include <type_traits>
+
 #include "epnn_internal.cuh"
 
 #define TC_THREADS 128
@@ -140,10 +142,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
             if (i0 + tid < a1) { p = a.rowptr[i0 + tid]; const int e = a.rowptr[i0 + tid + 1]; while (p < e && a.col[p] < jlo) ++p; }
             sPtr[tid] = p;
         }
-        float rs[TC_ROWS] = {0.f, 0.f, 0.f, 0.f};                 // lane c: column c, this warp's pairs, rows 0..3
-        int pend_row = -1, pend_stage = 0, pend_j0 = 0, pend_par = 0, iter = 0;
+        float rsum[TC_ROWS][32];                                  // this thread's pairs only: row r, column c (registers)
+#pragma unroll
+        for (int r = 0; r < TC_ROWS; ++r)
+#pragma unroll
+            for (int c = 0; c < 32; ++c) rsum[r][c] = 0.f;
+        bool pending = false;
+        int pend_j0 = 0, pend_par = 0;
 
-        auto epilogue = [&](int r, int stage, int j0, int par) {
+        // epilogue of (row r, stage r & 1): r is a compile-time constant at every call site (the row loop is unrolled)
+        auto epilogue = [&](auto rc, int j0, int par) {
+            constexpr int r = decltype(rc)::value;
+            constexpr int stage = r & 1;
             mbar_wait(smem_u32(&sBar[stage]), (stage ? uses1 : uses0) & 1u);
             if (stage) ++uses1; else ++uses0;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -151,19 +161,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
             tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)stage * 32u, d);
             const int j = j0 + tid;
             const bool valid = j < jhi && i0 + r < a1 && !((sMask[(par * TC_ROWS + r) * 4 + warp] >> lane) & 1u);
+            if (valid) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) d[c] = valid ? relu(d[c] + sb2[c]) : 0.f;
-            // transpose-reduce: after the five steps lane c holds the sum over the 32 lanes of d[c]
-#pragma unroll
-            for (int h = 16; h >= 1; h >>= 1) {
-#pragma unroll
-                for (int q = 0; q < h; ++q) {
-                    const float send = (lane & h) ? d[q] : d[q + h];
-                    const float keep = (lane & h) ? d[q + h] : d[q];
-                    d[q] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 bb = *reinterpret_cast<const float4*>(sb2 + c4 * 4);
+                    rsum[r][c4 * 4 + 0] += fmaxf(d[c4 * 4 + 0] + bb.x, 0.f); rsum[r][c4 * 4 + 1] += fmaxf(d[c4 * 4 + 1] + bb.y, 0.f);
+                    rsum[r][c4 * 4 + 2] += fmaxf(d[c4 * 4 + 2] + bb.z, 0.f); rsum[r][c4 * 4 + 3] += fmaxf(d[c4 * 4 + 3] + bb.w, 0.f);
                 }
             }
-            rs[r] += d[0];
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         };
 
@@ -196,8 +201,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
                 if (lane == 0) sPtr[warp] = p;
             }
             __syncthreads();
-            for (int r = 0; r < TC_ROWS; ++r, ++iter) {
-                const int stage = iter & 1;
+            auto row_step = [&](auto rc) {
+                constexpr int r = decltype(rc)::value;
+                constexpr int stage = r & 1;
                 // ---- produce row t of A (hi and lo) for pair (i0 + r, j0 + t)
                 float* Ahi = sA + stage * 4096;
                 float* Alo = sA + (2 + stage) * 4096;
@@ -231,14 +237,31 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                                  :: "r"(smem_u32(&sBar[stage])) : "memory");
                 }
-                if (pend_row >= 0) epilogue(pend_row, pend_stage, pend_j0, pend_par);      // overlaps the MMAs just issued
-                pend_row = r; pend_stage = stage; pend_j0 = j0; pend_par = tile_par;
-            }
+                // the previous row's epilogue overlaps the MMAs just issued (row 0's predecessor is row 3 of the previous tile)
+                if (r > 0) epilogue(std::integral_constant<int, (r + 3) & 3>{}, j0, tile_par);
+                else if (pending) epilogue(std::integral_constant<int, 3>{}, pend_j0, pend_par);
+            };
+            row_step(std::integral_constant<int, 0>{});
+            row_step(std::integral_constant<int, 1>{});
+            row_step(std::integral_constant<int, 2>{});
+            row_step(std::integral_constant<int, 3>{});
+            pending = true; pend_j0 = j0; pend_par = tile_par;
         }
-        if (pend_row >= 0) epilogue(pend_row, pend_stage, pend_j0, pend_par);
-        // ---- combine the four warps in a fixed order and write this unit's plane of partial sums
+        if (pending) epilogue(std::integral_constant<int, 3>{}, pend_j0, pend_par);
+        // ---- per row: transpose-reduce over the lanes (lane c ends with column c), then the four warps in a fixed order
 #pragma unroll
-        for (int r = 0; r < TC_ROWS; ++r) sRed[(warp * TC_ROWS + r) * HID + lane] = rs[r];
+        for (int r = 0; r < TC_ROWS; ++r) {
+#pragma unroll
+            for (int h = 16; h >= 1; h >>= 1) {
+#pragma unroll
+                for (int q = 0; q < h; ++q) {
+                    const float send = (lane & h) ? rsum[r][q] : rsum[r][q + h];
+                    const float keep = (lane & h) ? rsum[r][q + h] : rsum[r][q];
+                    rsum[r][q] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+                }
+            }
+            sRed[(warp * TC_ROWS + r) * HID + lane] = rsum[r][0];
+        }
         __syncthreads();
         if (tid < TC_ROWS * HID) {
             const int r = tid >> 5, c = tid & 31;
