@@ -50,6 +50,33 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// A operand from tensor memory (lanes = pairs, 8 consecutive 32-bit columns per K step), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+                 :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                    "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+                    "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+                    "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&d)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int c = 0; c < 16; ++c) d[c] = __uint_as_float(r[c]);
+}
+
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -85,9 +112,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&d)[32]) {
 __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcArgs a) {
     extern __shared__ unsigned char tc_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_raw) + 1023) & ~(uintptr_t)1023);
-    float* sA = reinterpret_cast<float*>(base + TC_OFF_A);        // [hi0 | hi1 | lo0 | lo1], 4096 floats each
     float* sB = reinterpret_cast<float*>(base + TC_OFF_B);        // [hi | lo], 1024 floats each
-    float* sV = reinterpret_cast<float*>(base + TC_OFF_V);        // [128][32] swizzled
     float* sU = reinterpret_cast<float*>(base + TC_OFF_MISC);     // [4][32]
     float* sb2 = sU + TC_ROWS * HID;                              // [32]
     float* sRed = sb2 + HID;                                      // [4 warps][4 rows][32]
@@ -112,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(sTmem)), "r"(64u) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(sTmem)), "r"(256u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -120,7 +145,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *sTmem;
-    const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB);
+    const uint32_t bBase = smem_u32(sB);
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's 32 TMEM lanes
     uint32_t uses0 = 0, uses1 = 0;            // completed phases of the two barriers (uniform across the CTA)
 
     for (int unit = a.unit_begin + blockIdx.x; unit < a.unit_end; unit += gridDim.x) {
@@ -142,6 +168,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
             if (i0 + tid < a1) { p = a.rowptr[i0 + tid]; const int e = a.rowptr[i0 + tid + 1]; while (p < e && a.col[p] < jlo) ++p; }
             sPtr[tid] = p;
         }
+        __syncthreads();                                          // u rows and CSR cursors visible to every warp
         float rsum[TC_ROWS][32];                                  // this thread's pairs only: row r, column c (registers)
 #pragma unroll
         for (int r = 0; r < TC_ROWS; ++r)
@@ -157,16 +184,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
             mbar_wait(smem_u32(&sBar[stage]), (stage ? uses1 : uses0) & 1u);
             if (stage) ++uses1; else ++uses0;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float d[32];
-            tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)stage * 32u, d);
             const int j = j0 + tid;
             const bool valid = j < jhi && i0 + r < a1 && !((sMask[(par * TC_ROWS + r) * 4 + warp] >> lane) & 1u);
-            if (valid) {
 #pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 bb = *reinterpret_cast<const float4*>(sb2 + c4 * 4);
-                    rsum[r][c4 * 4 + 0] += fmaxf(d[c4 * 4 + 0] + bb.x, 0.f); rsum[r][c4 * 4 + 1] += fmaxf(d[c4 * 4 + 1] + bb.y, 0.f);
-                    rsum[r][c4 * 4 + 2] += fmaxf(d[c4 * 4 + 2] + bb.z, 0.f); rsum[r][c4 * 4 + 3] += fmaxf(d[c4 * 4 + 3] + bb.w, 0.f);
+            for (int half = 0; half < 2; ++half) {
+                float d[16];
+                tmem_ld16(lane_base + (uint32_t)stage * 96u + half * 16u, d);
+                if (valid) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(sb2 + half * 16 + c4 * 4);
+                        rsum[r][half * 16 + c4 * 4 + 0] += fmaxf(d[c4 * 4 + 0] + bb.x, 0.f); rsum[r][half * 16 + c4 * 4 + 1] += fmaxf(d[c4 * 4 + 1] + bb.y, 0.f);
+                        rsum[r][half * 16 + c4 * 4 + 2] += fmaxf(d[c4 * 4 + 2] + bb.z, 0.f); rsum[r][half * 16 + c4 * 4 + 3] += fmaxf(d[c4 * 4 + 3] + bb.w, 0.f);
+                    }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -174,14 +204,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
 
         int tile_par = 0;
         for (int j0 = jlo; j0 < jhi; j0 += TC_TILE, tile_par ^= 1) {
-            __syncthreads();                                      // producers of the previous tile are done with sV
-            // ---- v tile: 128 rows x 128 B, coalesced, stored with the 16-byte chunks XOR-swizzled by (row & 7)
+            // ---- this thread's v row (pair column j0 + t) straight into registers: 128 B per thread, L2-resident
+            float vr[32];
+            {
+                const float4* src = reinterpret_cast<const float4*>(a.v + (int64_t)(j0 + tid) * HID);
+                const bool in = j0 + tid < jhi;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const int row = (tid >> 3) + 16 * m, ch = tid & 7;
-                float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j0 + row < jhi) val = __ldg(reinterpret_cast<const float4*>(a.v + (int64_t)(j0 + row) * HID) + ch);
-                *reinterpret_cast<float4*>(sV + row * 32 + ((ch ^ (row & 7)) << 2)) = val;
+                for (int c = 0; c < 8; ++c) {
+                    const float4 t4 = in ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    vr[c * 4] = t4.x; vr[c * 4 + 1] = t4.y; vr[c * 4 + 2] = t4.z; vr[c * 4 + 3] = t4.w;
+                }
             }
             // ---- near masks of this tile (warp r <-> row r): bit (j - j0) set for CSR neighbours j in [j0, j0 + 128)
             if (lane < 4) sMask[(tile_par * TC_ROWS + warp) * 4 + lane] = 0u;
@@ -200,40 +232,40 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
                 __syncwarp();
                 if (lane == 0) sPtr[warp] = p;
             }
-            __syncthreads();
             auto row_step = [&](auto rc) {
                 constexpr int r = decltype(rc)::value;
                 constexpr int stage = r & 1;
-                // ---- produce row t of A (hi and lo) for pair (i0 + r, j0 + t)
-                float* Ahi = sA + stage * 4096;
-                float* Alo = sA + (2 + stage) * 4096;
+                // ---- produce row t of A (hi and lo) for pair (i0 + r, j0 + t): registers -> tensor memory (lane = pair)
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int off = tid * 32 + ((c ^ (tid & 7)) << 2);
-                    const float4 vv = *reinterpret_cast<const float4*>(sV + off);
-                    const float4 uu = *reinterpret_cast<const float4*>(sU + r * HID + c * 4);
-                    float4 z, hi, lo;
-                    z.x = fmaxf(uu.x + vv.x, 0.f); z.y = fmaxf(uu.y + vv.y, 0.f); z.z = fmaxf(uu.z + vv.z, 0.f); z.w = fmaxf(uu.w + vv.w, 0.f);
-                    hi.x = __uint_as_float(__float_as_uint(z.x) & 0xFFFFE000u); hi.y = __uint_as_float(__float_as_uint(z.y) & 0xFFFFE000u);
-                    hi.z = __uint_as_float(__float_as_uint(z.z) & 0xFFFFE000u); hi.w = __uint_as_float(__float_as_uint(z.w) & 0xFFFFE000u);
-                    lo.x = z.x - hi.x; lo.y = z.y - hi.y; lo.z = z.z - hi.z; lo.w = z.w - hi.w;
-                    *reinterpret_cast<float4*>(Ahi + off) = hi;
-                    *reinterpret_cast<float4*>(Alo + off) = lo;
+                for (int half = 0; half < 2; ++half) {
+                    float hi[16], lo[16];
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 uu = *reinterpret_cast<const float4*>(sU + r * HID + half * 16 + c4 * 4);
+                        const float uq[4] = {uu.x, uu.y, uu.z, uu.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const float z = fmaxf(uq[q] + vr[half * 16 + c4 * 4 + q], 0.f);
+                            const float h = __uint_as_float(__float_as_uint(z) & 0xFFFFE000u);
+                            hi[c4 * 4 + q] = h; lo[c4 * 4 + q] = z - h;
+                        }
+                    }
+                    tmem_st16(lane_base + (uint32_t)stage * 96u + 32u + half * 16u, hi);
+                    tmem_st16(lane_base + (uint32_t)stage * 96u + 64u + half * 16u, lo);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();
                 if (tid == 0) {
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t d = tmem + (uint32_t)stage * 32u;
-                    const uint64_t ahi = umma_desc_k128(aBase + stage * 16384u), alo = umma_desc_k128(aBase + (2 + stage) * 16384u);
+                    const uint32_t d = tmem + (uint32_t)stage * 96u, ahi = d + 32u, alo = d + 64u;
                     const uint64_t bhi = umma_desc_k128(bBase), blo = umma_desc_k128(bBase + 4096u);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_tf32(d, ahi + 2 * ks, bhi + 2 * ks, idesc, ks > 0);
+                    for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(d, ahi + 8 * ks, bhi + 2 * ks, idesc, ks > 0);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_tf32(d, alo + 2 * ks, bhi + 2 * ks, idesc, 1u);
+                    for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(d, alo + 8 * ks, bhi + 2 * ks, idesc, 1u);
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) umma_tf32(d, ahi + 2 * ks, blo + 2 * ks, idesc, 1u);
+                    for (int ks = 0; ks < 4; ++ks) umma_tf32_ts(d, ahi + 8 * ks, blo + 2 * ks, idesc, 1u);
                     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                                  :: "r"(smem_u32(&sBar[stage])) : "memory");
                 }
@@ -275,7 +307,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
     // ---- teardown
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(64u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(256u) : "memory");
 }
 
 cudaError_t launch_gnn_far_tc(const Workspace& w, const float* Whi, const float* Wlo, const float* b2, int nsplit_tc,
