@@ -176,6 +176,25 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
             for (int c = 0; c < 32; ++c) rsum[r][c] = 0.f;
         bool pending = false;
         int pend_j0 = 0, pend_par = 0;
+        // next CSR neighbour column of row (i0 + warp) not yet consumed by a tile (INT_MAX: none left): lets almost
+        // every tile skip the mask build without touching global memory
+        int row_end = 0, cur_p = 0, next_col = 0x7fffffff;
+        if (i0 + warp < a1) {
+            row_end = a.rowptr[i0 + warp + 1];
+            cur_p = sPtr[warp];
+            if (cur_p < row_end) next_col = a.col[cur_p];
+        }
+        float vr[32];                                             // this thread's v row of the current tile
+        auto load_v = [&](int j0) {
+            const float4* src = reinterpret_cast<const float4*>(a.v + (int64_t)(j0 + tid) * HID);
+            const bool in = j0 + tid < jhi;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 t4 = in ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+                vr[c * 4] = t4.x; vr[c * 4 + 1] = t4.y; vr[c * 4 + 2] = t4.z; vr[c * 4 + 3] = t4.w;
+            }
+        };
+        if (jlo < jhi) load_v(jlo);
 
         // epilogue of (row r, stage r & 1): r is a compile-time constant at every call site (the row loop is unrolled)
         auto epilogue = [&](auto rc, int j0, int par) {
@@ -204,33 +223,20 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
 
         int tile_par = 0;
         for (int j0 = jlo; j0 < jhi; j0 += TC_TILE, tile_par ^= 1) {
-            // ---- this thread's v row (pair column j0 + t) straight into registers: 128 B per thread, L2-resident
-            float vr[32];
-            {
-                const float4* src = reinterpret_cast<const float4*>(a.v + (int64_t)(j0 + tid) * HID);
-                const bool in = j0 + tid < jhi;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 t4 = in ? __ldg(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    vr[c * 4] = t4.x; vr[c * 4 + 1] = t4.y; vr[c * 4 + 2] = t4.z; vr[c * 4 + 3] = t4.w;
-                }
-            }
             // ---- near masks of this tile (warp r <-> row r): bit (j - j0) set for CSR neighbours j in [j0, j0 + 128)
             if (lane < 4) sMask[(tile_par * TC_ROWS + warp) * 4 + lane] = 0u;
             __syncwarp();
-            if (i0 + warp < a1) {
-                const int e = a.rowptr[i0 + warp + 1];
-                int p = sPtr[warp];
+            if (next_col < j0 + TC_TILE) {                        // rare: this tile holds near neighbours of the row
                 for (;;) {
-                    const int c = p + lane < e ? a.col[p + lane] : 0x7fffffff;
+                    const int c = cur_p + lane < row_end ? a.col[cur_p + lane] : 0x7fffffff;
                     const bool in = c < j0 + TC_TILE;
                     if (in) atomicOr(&sMask[(tile_par * TC_ROWS + warp) * 4 + ((c - j0) >> 5)], 1u << ((c - j0) & 31));
                     const int cnt = __popc(__ballot_sync(0xffffffffu, in));
-                    p += cnt;
+                    cur_p += cnt;
                     if (cnt < 32) break;
                 }
+                next_col = cur_p < row_end ? a.col[cur_p] : 0x7fffffff;
                 __syncwarp();
-                if (lane == 0) sPtr[warp] = p;
             }
             auto row_step = [&](auto rc) {
                 constexpr int r = decltype(rc)::value;
@@ -253,6 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
                     tmem_st16(lane_base + (uint32_t)stage * 96u + 32u + half * 16u, hi);
                     tmem_st16(lane_base + (uint32_t)stage * 96u + 64u + half * 16u, lo);
                 }
+                if (r == TC_ROWS - 1 && j0 + TC_TILE < jhi) load_v(j0 + TC_TILE);   // vr is dead now: next tile's row flies during the epilogues
                 asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncthreads();
