@@ -55,6 +55,12 @@ def _worker(rank, world, port, tmp):
             eng.set_shard(0, 1)
             again = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1]
             assert np.array_equal(single, again)
+            # the optional tensor-core far kernel shards the same way and stays bit-identical to its own 1-GPU run
+            eng.set_option("gnn_far_tensor", 1)
+            tc1 = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
+            eng.set_shard(rank, world)
+            tc2 = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
+            assert np.array_equal(tc1, tc2), (name, "tensor", np.abs(tc1 - tc2).max())
             eng.close()
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
