@@ -364,3 +364,41 @@ def test_bundle_boundaries_and_routing(engines, weights, protein):
     # the FP32 default path on the same batch
     q32 = engines("model2_weights").infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1]
     assert np.abs(q32 - ref).max() < 5e-5 * max(1.0, np.abs(ref).max())
+
+
+def test_synthetic_qm9_stream_properties(engines, weights):
+    """The bench workload (BASELINE config 4) at a size the oracle cannot cover in full: 20 000 QM9-shaped molecules
+    in several chunks.  Size-independent properties: charge conservation per molecule, a random sample against the
+    oracle, and independence of a molecule's charges from where it sits in the batch (bundles, tiles and chunks differ)."""
+    from epnn_b200 import synth
+    w = weights["model2_weights"]                      # live GNN: exercises every kernel
+    n_mol = 20000
+    offs, xyz, sp, Q = synth.qm9_shaped(n_mol, 9, seed=7)
+    Q = Q.copy()
+    Q[::3] = 1.0
+    Q[1::3] = -1.0
+    npad = np.full(n_mol, 29, np.int32)
+    eng = engines("model2_weights")
+    eng.set_option("chunk_atoms", 100000)
+    try:
+        q, q64 = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)
+        assert eng.last_stats["n_chunks"] >= 3
+        sums = np.add.reduceat(q64, offs[:-1])
+        assert np.abs(sums - Q.astype(np.float64)).max() < 1e-6
+        rng = np.random.default_rng(0)
+        pick = rng.choice(n_mol, 40, replace=False)
+        for k in pick:
+            a0, a1 = offs[k], offs[k + 1]
+            ref = O.forward_factorised(w, xyz[a0:a1], sp[a0:a1], Q[k], 29)
+            assert np.abs(q64[a0:a1] - ref).max() < 5e-5, k
+        # the same molecules in reverse order: other bundles, other tiles, other chunks
+        order = np.arange(n_mol)[::-1]
+        sizes = np.diff(offs)
+        offs_r = np.concatenate([[0], np.cumsum(sizes[order])]).astype(np.int32)
+        idx = np.concatenate([np.arange(offs[k], offs[k + 1]) for k in order])
+        q_r = eng.infer_batch(offs_r, xyz[idx], sp[idx], Q[order], npad, want_f64=True)[1]
+        back = np.empty_like(q_r)
+        back[idx] = q_r
+        assert np.abs(back - q64).max() < 2e-5
+    finally:
+        eng.set_option("chunk_atoms", 4 * 1024 * 1024)
