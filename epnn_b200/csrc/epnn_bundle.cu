@@ -18,9 +18,9 @@
 //     delta_p = 0.5 (w3 . m_ij - w3 . m_ji) * is_near_p, written per unordered pair (the +/- scatter into q is the
 //     per-atom kernel's fixed-order CSR reduction).
 //
-// The scatter into S is a warp-private, fixed-order pass (lane = hidden column, slots in tile order): no atomics,
-// bitwise reproducible.  Only the e rows (192 B per pair, streamed once per launch, next tile prefetched into L2)
-// and the index lists come from global memory inside the tile loop.
+// The scatter into S is a warp-private, fixed-order segmented sum over the sorted targets (scatter_sorted): no atomics,
+// bitwise reproducible.  Only the e rows (192 B per pair, streamed once per launch) and the index lists come from
+// global memory inside the tile loop, and both are prefetched one tile ahead into registers.
 #include "epnn_internal.cuh"
 
 #ifndef EPN_NW
@@ -104,7 +104,7 @@ __device__ __forceinline__ void scatter_sorted(Vec4<R> (&val)[8], const int (&tg
 
 template <typename R, bool EPN> struct BundleSmem {
     static constexpr int W_ELEMS = ED * HID + HID * HID + 2 * HID;                                  // shared weights
-    static constexpr int PW = BUNDLE_ATOMS * 64 + (EPN ? 0 : BUNDLE_ATOMS * HID + BUNDLE_ATOMS) + 32 * ED + 32;   // per warp
+    static constexpr int PW = BUNDLE_ATOMS * 64 + (EPN ? 0 : BUNDLE_ATOMS * HID + BUNDLE_ATOMS) + 32 * ED;   // per warp
     static constexpr int PI = 128;                                                                  // ints per warp
     static size_t bytes(int nw) { return sizeof(R) * (W_ELEMS + (size_t)nw * PW) + sizeof(int) * nw * PI; }
 };
@@ -122,7 +122,6 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
     R* S = uv + BUNDLE_ATOMS * 64;                   // [BUNDLE_ATOMS][32]      (GNN only)
     R* padw = S + BUNDLE_ATOMS * HID;                // [BUNDLE_ATOMS]          (GNN only)
     R* eb = uv + BUNDLE_ATOMS * 64 + (EPN ? 0 : BUNDLE_ATOMS * HID + BUNDLE_ATOMS);   // [32][48] e tile, then [32][32] z tile
-    R* wgt = eb + 32 * ED;                           // [32]
     int* sl_i = reinterpret_cast<int*>(sx + HID + NW * L::PW) + warp * L::PI;
     int* sl_c = sl_i + 32;                           // packed slot code: local i | local j << 8 (0xFF = pad pseudo-atom), -1 = empty
     int* sl_p = sl_i + 64;                           // near: position of the slot when the tile is sorted by j
