@@ -363,6 +363,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     memset(&w, 0, sizeof(w));
     w.n_atoms = n_atoms; w.n_sys = n_sys; w.sm_count = c->sm_count;
     w.shard_rank = c->shard_rank; w.shard_world = c->shard_world;
+    w.work_counter = c->d_flags + 7;
     w.xyz = d_xyz; w.species = d_species; w.Qsys = d_Q;
     void* p;
     int rc;

@@ -28,7 +28,7 @@
 #endif
 
 template <typename R> struct BundleArgs {
-    int n_bundles; const int2* bundle;
+    int n_bundles; const int2* bundle; int* work_counter;      // dynamic bundle queue (zeroed before the launch)
     const int* ustart; const int* pair_i; const int* pair_j; const unsigned char* near; const float* e;
     const unsigned char* perm_j;                              // per pair: rank of its j among the pairs of its tile
     const int* far_off; const unsigned short* far_list;
@@ -135,10 +135,19 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
     const int pg = lane >> 3, og = lane & 7;
     const Vec4<R> b2v = ldv(sb2 + og * 4);
     const Vec4<R> xv = ldv(sx + og * 4);             // b1 columns (GNN) / w3 columns (EPN)
-    const int stride = gridDim.x * NW;
     R* zt = eb;
 
-    for (int b = blockIdx.x * NW + warp; b < a.n_bundles; b += stride) {
+    // Bundles differ in cost (7 .. 48 atoms), so the warps pull them from a queue instead of striding; every warp holds
+    // the index of its NEXT bundle already, to prefetch that bundle's u / v rows.  Which warp handles a bundle has no
+    // influence on the result (each bundle is self-contained and its arithmetic order is fixed).
+    auto grab = [&]() {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(a.work_counter, 1);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    int b = grab();
+    int b_next = grab();
+    for (; b < a.n_bundles; b = b_next, b_next = grab()) {
         const int2 bd = a.bundle[b];
         const int atom0 = bd.x, nat = bd.y;
         const int p0 = a.ustart[atom0], p1 = a.ustart[atom0 + nat];
@@ -162,8 +171,8 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
             }
         };
         if (ntile > 0) fetch_tile(p0);
-        if (b + stride < a.n_bundles) {              // next bundle's u / v rows -> L2
-            const int2 nd = a.bundle[b + stride];
+        if (b_next < a.n_bundles) {                  // next bundle's u / v rows -> L2
+            const int2 nd = a.bundle[b_next];
             const int nbytes = nd.y * HID * (int)sizeof(R);
             for (int o = lane * 128; o < nbytes; o += 32 * 128) {
                 prefetch_l2(reinterpret_cast<const char*>(a.u + (int64_t)nd.x * HID) + o);
@@ -361,7 +370,9 @@ static cudaError_t launch_bundle(const Workspace& w, const StepW<R>& sw, cudaStr
     if (w.n_bundles == 0) return cudaSuccess;
     constexpr int NW = sizeof(R) == 4 ? (EPN ? EPN_NW : 8) : 4;   // the EPN variant has no S accumulators: more warps fit
     BundleArgs<R> ba;
-    ba.n_bundles = w.n_bundles; ba.bundle = w.bundle;
+    ba.n_bundles = w.n_bundles; ba.bundle = w.bundle; ba.work_counter = w.work_counter;
+    cudaError_t e0 = cudaMemsetAsync(w.work_counter, 0, sizeof(int), st);
+    if (e0 != cudaSuccess) return e0;
     ba.ustart = w.ustart; ba.pair_i = w.pair_i; ba.pair_j = w.pair_j; ba.near = w.near; ba.e = w.e;
     ba.perm_j = w.perm_j;
     ba.far_off = w.far_off; ba.far_list = w.far_list;

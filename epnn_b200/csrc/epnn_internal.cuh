@@ -193,6 +193,7 @@ struct Workspace {
     int* atom_sys;
     int* deg; int* degU; int* rowptr; int* ustart; int* col; int* pid;
     int* pair_i; int* pair_j; double* pair_D; float* e; unsigned char* near;
+    int* work_counter;                 // device int: dynamic work queue of the bundle kernels
     int2* bundle; int n_bundles;       // (first atom, atom count) of every bundle of small systems (n <= SMALL_MAX)
     int* bundle_nat; unsigned char* perm_j;   // atoms of the bundle (at its first atom); rank of a pair's j inside its tile
     int* far_off; unsigned short* far_list; int64_t n_far;   // per-bundle list of the GNN's e == 0 ("far") ordered pairs
