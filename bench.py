@@ -10,7 +10,9 @@ electron-passing passes -> charges) over one batch of synthetic input:
                      disjoint shards of the same stream (molecule k depends only on (seed, k)) and there is
                      no data-path collective: "scaling": "weak".
   workload "protein" (BASELINE.json configs[2]/[4])      : one protein-like system of --atoms atoms (Galectin-3C
-                     tiled), exact all-pairs GNN; single GPU per replica.
+                     tiled), exact all-pairs GNN.  With --gpus N the SAME system is sharded over the N ranks
+                     (epnn_set_shard: pair kernels split by ranges, one NCCL all-reduce per step / pass): "scaling":
+                     "strong".  --gnn-far-tensor 1 moves the O(n^2) far part to the tcgen05 tensor cores (3xTF32).
 
 Printed JSON (rank 0, one line): the driver contract + "roofline" (dominant kernel, FP32-SIMT bound, against
 the FMA peak measured in the same run; the HBM-side kernels against MEASURED_PEAKS.json) + "cpu_baseline"
