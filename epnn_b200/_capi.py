@@ -53,6 +53,17 @@ SIGNATURES = {
     "epnn_set_shard": (C.c_int, [C.c_void_p, C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p]),
     "epnn_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "epnn_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
+    "epnn_xyz_load": (C.c_int, [C.POINTER(C.c_char_p), C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "epnn_xyz_parse_text": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "epnn_xyz_n_systems": (C.c_int64, [C.c_void_p]),
+    "epnn_xyz_n_atoms": (C.c_int64, [C.c_void_p]),
+    "epnn_xyz_offsets": (C.c_void_p, [C.c_void_p]),
+    "epnn_xyz_coords": (C.c_void_p, [C.c_void_p]),
+    "epnn_xyz_species": (C.c_void_p, [C.c_void_p]),
+    "epnn_xyz_charges": (C.c_void_p, [C.c_void_p]),
+    "epnn_xyz_error": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "epnn_xyz_error_message": (C.c_char_p, [C.c_void_p]),
+    "epnn_xyz_free": (None, [C.c_void_p]),
     "epnn_rbf_centers": (C.c_int, [C.c_void_p]),
     "epnn_version": (C.c_char_p, []),
 }

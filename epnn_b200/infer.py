@@ -10,6 +10,7 @@ Defaults equal the literals of the reference script (``h_dim=48, e_dim=48, layer
 from __future__ import annotations
 
 import argparse
+import os
 import time
 
 import numpy as np
@@ -62,12 +63,14 @@ def main(argv=None):
         sizes = mask[:, 0].sum(axis=1).astype(int)
     else:
         timeA = time.time()
-        systems = xyzio.read_directory(args.path or ".")
-        if not systems:
+        # native multi-threaded ingest (epnn_xyz_load) straight into the packed arrays of the C-ABI
+        stems, offsets, xyz_all, species_all, Q_all = xyzio.read_directory_packed(args.path or ".", n_elems)
+        if not stems:
             raise SystemExit(f"no .xyz files under {args.path!r}")
-        names = np.array([s.name for s in systems])
+        names = np.array(stems)
+        sizes_all = np.diff(offsets)
         timeB = time.time()
-        N = args.npad or max(s.n for s in systems)
+        N = args.npad or int(sizes_all.max())
         model = charge_gn.make_model(layers, h_dim, T, n_elems, N, device=args.device, precision=args.precision)
         model.load_weights(args.weights)
         np.save("test_names.npy", names, allow_pickle=True)
@@ -75,18 +78,22 @@ def main(argv=None):
         timeC = timeD = time.time()
         for _ in range(args.repeats):
             timeC = time.time()
-            runs.append(model.predict_systems(systems, npad=N))
+            runs.append(model.predict_packed(offsets, xyz_all, species_all, Q_all, N))
             timeD = time.time()
             print(timeD - timeC)
-        preds = np.zeros((len(systems), args.repeats, N, 1), np.float32)
+        S = len(stems)
+        preds = np.zeros((S, args.repeats, N, 1), np.float32)
         for r, run in enumerate(runs):
-            for i, qv in enumerate(run):
-                preds[i, r, :len(qv), 0] = qv
-        sizes = np.array([s.n for s in systems])
-        y = np.zeros((len(systems), N, 1))
-        for i, s in enumerate(systems):
-            if s.labels is not None:
-                y[i, :s.n, 0] = s.labels[:s.n]
+            for i in range(S):
+                preds[i, r, :sizes_all[i], 0] = run[offsets[i]:offsets[i + 1]]
+        sizes = sizes_all
+        y = np.zeros((S, N, 1))
+        base = args.path or "."
+        for i, stem in enumerate(stems):                              # labels: <stem>.npy next to the xyz (charge_gn.py:311-316)
+            lab = os.path.join(base, stem + ".npy")
+            if os.path.exists(lab):
+                yv = np.array(np.load(lab), dtype=np.float32).reshape(-1)[:sizes[i]]
+                y[i, :len(yv), 0] = yv
 
     print(f"avg inference time: {(timeD - timeC) / max(1, args.repeats)}")
     print(f"avg feature time:{(timeB - timeA)}")

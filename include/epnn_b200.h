@@ -134,6 +134,26 @@ int epnn_infer_dense(epnn_ctx* ctx, int32_t B, int32_t N, const float* h, const 
  * output is a dead constant, so charges alone cannot validate the GNN kernels (SURVEY.md trap 6). */
 int epnn_get_hidden(epnn_ctx* ctx, float* h_out, int64_t n_floats);
 
+/* Host-side ingest of the reference's xyz dialect (no GPU involved): multi-threaded parse of a list of files into
+ * the packed arrays epnn_infer_batch takes.  Replaces the Python parsing loop of charge_gn.gen_padded_init_state
+ * (charge_gn.py:301-338): line 2 first token = Q (float32), atom lines "Elem x y z [ignored]", numbers parsed as
+ * float64 and rounded once to float32 like numpy; element symbols index the table chosen by n_x.  The file ORDER is
+ * the caller's (os.listdir order upstream, charge_gn.py:301).  On a malformed file / unknown element the call returns
+ * EPNN_E_INVALID and the batch only carries the error (kind 1 cannot open, 2 malformed, 3 unknown element -- the
+ * reference raises KeyError, charge_gn.py:326-327 -- plus the index of the first offending file and a message). */
+typedef struct epnn_xyz_batch epnn_xyz_batch;
+int epnn_xyz_load(const char* const* paths, int64_t n_files, int n_x, int threads, epnn_xyz_batch** out);
+int epnn_xyz_parse_text(const char* text, size_t len, int n_x, epnn_xyz_batch** out);
+int64_t epnn_xyz_n_systems(const epnn_xyz_batch* b);
+int64_t epnn_xyz_n_atoms(const epnn_xyz_batch* b);
+const int32_t* epnn_xyz_offsets(const epnn_xyz_batch* b);     /* int32[n_systems + 1] */
+const float* epnn_xyz_coords(const epnn_xyz_batch* b);        /* float32[3 * n_atoms] */
+const int32_t* epnn_xyz_species(const epnn_xyz_batch* b);     /* int32[n_atoms] */
+const float* epnn_xyz_charges(const epnn_xyz_batch* b);       /* float32[n_systems] */
+int epnn_xyz_error(const epnn_xyz_batch* b, int* kind, int* file_index);
+const char* epnn_xyz_error_message(const epnn_xyz_batch* b);
+void epnn_xyz_free(epnn_xyz_batch* b);
+
 /* Pinned host memory helpers so that callers can make the H2D/D2H copies asynchronous. */
 int epnn_host_alloc(void** ptr, size_t bytes);
 int epnn_host_free(void* ptr);
