@@ -65,6 +65,7 @@ SIGNATURES = {
     "epnn_xyz_error_message": (C.c_char_p, [C.c_void_p]),
     "epnn_xyz_free": (None, [C.c_void_p]),
     "epnn_rbf_centers": (C.c_int, [C.c_void_p]),
+    "epnn_rbf_basis": (C.c_int, [C.c_void_p]),
     "epnn_version": (C.c_char_p, []),
 }
 

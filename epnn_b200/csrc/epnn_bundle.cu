@@ -103,8 +103,9 @@ __device__ __forceinline__ void scatter_sorted(Vec4<R> (&val)[8], const int (&tg
 }
 
 template <typename R, bool EPN> struct BundleSmem {
-    static constexpr int W_ELEMS = ED * HID + HID * HID + 2 * HID;                                  // shared weights
-    static constexpr int PW = BUNDLE_ATOMS * 64 + (EPN ? 0 : BUNDLE_ATOMS * HID + BUNDLE_ATOMS) + 32 * ED;   // per warp
+    static constexpr int EK = EKof<R>::v;
+    static constexpr int W_ELEMS = EK * HID + HID * HID + 2 * HID;                                  // shared weights
+    static constexpr int PW = BUNDLE_ATOMS * 64 + (EPN ? 0 : BUNDLE_ATOMS * HID + BUNDLE_ATOMS) + 32 * (EK > HID ? EK : HID);   // per warp (tile buffer: e rows, then z rows)
     static constexpr int PI = 128;                                                                  // ints per warp
     static size_t bytes(int nw) { return sizeof(R) * (W_ELEMS + (size_t)nw * PW) + sizeof(int) * nw * PI; }
 };
@@ -113,8 +114,9 @@ template <typename R, int NW, bool EPN>
 __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> a) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
     using L = BundleSmem<R, EPN>;
-    R* sC = reinterpret_cast<R*>(smem_raw);          // [48][32]
-    R* sW2 = sC + ED * HID;                          // [32][32]
+    constexpr int EK = L::EK;
+    R* sC = reinterpret_cast<R*>(smem_raw);          // [EK][32]
+    R* sW2 = sC + EK * HID;                          // [32][32]
     R* sb2 = sW2 + HID * HID;                        // [32]
     R* sx = sb2 + HID;                               // [32]  b1 (GNN) / w3 (EPN)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -127,7 +129,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
     int* sl_p = sl_i + 64;                           // near: position of the slot when the tile is sorted by j
     int* sl_t = sl_i + 96;                           // near: j targets in that sorted order
 
-    for (int t = threadIdx.x; t < ED * HID; t += NW * 32) sC[t] = a.Cw[t];
+    for (int t = threadIdx.x; t < EK * HID; t += NW * 32) sC[t] = a.Cw[t];
     for (int t = threadIdx.x; t < HID * HID; t += NW * 32) sW2[t] = a.W2[t];
     if (threadIdx.x < HID) { sb2[threadIdx.x] = a.b2[threadIdx.x]; sx[threadIdx.x] = a.x32[threadIdx.x]; }
     __syncthreads();
@@ -155,19 +157,19 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
         // ---- software prefetch (registers) of tile 0: indices + e rows
         int n_i = 0, n_j = 0;                        // raw (global) indices of the prefetched tile; rebased when consumed
         unsigned char n_x = 0;                       // near flag (EPN) / j-order position (GNN)
-        float4 er[ED / 4];
+        float4 er[EK / 4];
         auto fetch_tile = [&](int tb) {
             const int rows = min(32, p1 - tb);
             if (lane < rows) {
                 n_i = a.pair_i[tb + lane]; n_j = a.pair_j[tb + lane];
                 n_x = EPN ? a.near[tb + lane] : a.perm_j[tb + lane];
             }
-            const float4* esrc = reinterpret_cast<const float4*>(a.e + (int64_t)tb * ED);
+            const float4* esrc = reinterpret_cast<const float4*>(a.e + (int64_t)tb * EK);
 #pragma unroll
-            for (int m = 0; m < ED / 4; ++m) {
+            for (int m = 0; m < EK / 4; ++m) {
                 const int f = lane + 32 * m;
                 er[m] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (f / (ED / 4) < rows) er[m] = __ldg(esrc + f);
+                if (f / (EK / 4) < rows) er[m] = __ldg(esrc + f);
             }
         };
         if (ntile > 0) fetch_tile(p0);
@@ -206,16 +208,16 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                 if (!EPN) { sl_i[lane] = li; sl_p[lane] = lp; sl_t[lp] = lj; }
             }
 #pragma unroll
-            for (int m = 0; m < ED / 4; ++m) {                          // prefetched e rows -> swizzled tile
+            for (int m = 0; m < EK / 4; ++m) {                          // prefetched e rows -> swizzled tile
                 const int f = lane + 32 * m;
-                const int sl = f / (ED / 4), ch = f - sl * (ED / 4);
-                stv(eb + tile_off(sl, ch, ED), cvt4<R>(er[m]));
+                const int sl = f / (EK / 4), ch = f - sl * (EK / 4);
+                stv(eb + tile_off(sl, ch, EK), cvt4<R>(er[m]));
             }
             if (t + 1 < ntile) fetch_tile(tb + 32);                     // next tile's loads fly during this tile's math
             __syncwarp();
             R ce[8][4];
             zero_acc(ce);
-            tile_gemm<R, ED, HID>(eb, sC, og * 4, ce, pg);
+            tile_gemm<R, EK, HID>(eb, sC, og * 4, ce, pg);
             __syncwarp();                                              // e tile consumed; eb becomes the z tile
 
             R part[8];

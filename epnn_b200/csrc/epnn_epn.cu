@@ -25,17 +25,18 @@ template <typename R> struct EpnArgs {
 template <typename R, int NW>
 __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) epn_pair_kernel(const EpnArgs<R> a) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
+    constexpr int EK = EKof<R>::v;
     R* sC = reinterpret_cast<R*>(smem_raw);          // [48][32]
-    R* sW2 = sC + ED * HID;                          // [32][32]
+    R* sW2 = sC + EK * HID;                          // [32][32]
     R* sb2 = sW2 + HID * HID;                        // [32]
     R* sw3 = sb2 + HID;                              // [32]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    R* at1 = sw3 + HID + warp * (32 * ED + 32 * HID);
-    R* at2 = at1 + 32 * ED;
-    int* slot_i = reinterpret_cast<int*>(sw3 + HID + NW * (32 * ED + 32 * HID)) + warp * 64;
+    R* at1 = sw3 + HID + warp * (32 * EK + 32 * HID);
+    R* at2 = at1 + 32 * EK;
+    int* slot_i = reinterpret_cast<int*>(sw3 + HID + NW * (32 * EK + 32 * HID)) + warp * 64;
     int* slot_j = slot_i + 32;
 
-    for (int t = threadIdx.x; t < ED * HID; t += NW * 32) sC[t] = a.Cw[t];
+    for (int t = threadIdx.x; t < EK * HID; t += NW * 32) sC[t] = a.Cw[t];
     for (int t = threadIdx.x; t < HID * HID; t += NW * 32) sW2[t] = a.W2[t];
     if (threadIdx.x < HID) { sb2[threadIdx.x] = a.b2[threadIdx.x]; sw3[threadIdx.x] = a.w3[threadIdx.x]; }
     __syncthreads();
@@ -57,18 +58,18 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) epn_pair_kern
         slot_j[lane] = valid ? pj : -1;
         const R nearf = valid ? (R)a.near[p] : R(0);
         const int64_t rows_left = a.P - tile * 32;
-        const float4* esrc = reinterpret_cast<const float4*>(a.e + tile * 32 * ED);
+        const float4* esrc = reinterpret_cast<const float4*>(a.e + tile * 32 * EK);
 #pragma unroll 4
-        for (int f = lane; f < 32 * (ED / 4); f += 32) {           // 32 rows x 192 B, contiguous in HBM
-            const int sl = f / (ED / 4), ch = f - sl * (ED / 4);
+        for (int f = lane; f < 32 * (EK / 4); f += 32) {           // 32 rows x 192 B, contiguous in HBM
+            const int sl = f / (EK / 4), ch = f - sl * (EK / 4);
             Vec4<R> ev = vzero<R>();
             if (sl < rows_left) ev = cvt4<R>(__ldg(esrc + f));
-            stv(at1 + tile_off(sl, ch, ED), ev);
+            stv(at1 + tile_off(sl, ch, EK), ev);
         }
         __syncwarp();
         R ce[8][4];
         zero_acc(ce);
-        tile_gemm<R, ED, HID>(at1, sC, og * 4, ce, pg);
+        tile_gemm<R, EK, HID>(at1, sC, og * 4, ce, pg);
 
         R part[8];
         R acc[8][4];
@@ -153,7 +154,8 @@ cudaError_t launch_epn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t
     ea.P = w.P; ea.pair_i = w.pair_i; ea.pair_j = w.pair_j; ea.near = w.near; ea.e = w.e; ea.atom_sys = w.atom_sys; ea.sys_off = w.sys_off;
     ea.u = (const R*)w.u; ea.v = (const R*)w.v; ea.Cw = sw.Cw; ea.W2 = sw.W2; ea.b2 = sw.b2; ea.w3 = sw.W3;
     ea.delta = (R*)w.delta;
-    const size_t smem = sizeof(R) * (ED * HID + HID * HID + 2 * HID + (size_t)NW * (32 * ED + 32 * HID)) + sizeof(int) * NW * 64;
+    constexpr int EK = EKof<R>::v;
+    const size_t smem = sizeof(R) * (EK * HID + HID * HID + 2 * HID + (size_t)NW * (32 * EK + 32 * HID)) + sizeof(int) * NW * 64;
     cudaError_t e = cudaFuncSetAttribute(epn_pair_kernel<R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int per_sm = sizeof(R) == 4 ? 2 : 1;

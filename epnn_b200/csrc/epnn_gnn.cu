@@ -30,17 +30,18 @@ template <typename R> struct GnnArgs {
 template <typename R, bool LARGE, int NW>
 __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kernel(const GnnArgs<R> a) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
+    constexpr int EK = EKof<R>::v;
     R* sC = reinterpret_cast<R*>(smem_raw);          // [48][32]
-    R* sW2 = sC + ED * HID;                          // [32][32]
+    R* sW2 = sC + EK * HID;                          // [32][32]
     R* sb2 = sW2 + HID * HID;                        // [32]
     R* sb1 = sb2 + HID;                              // [32]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    R* at1 = sb1 + HID + warp * (32 * ED + 32 * HID);   // [32][48] swizzled
-    R* at2 = at1 + 32 * ED;                             // [32][32] swizzled
-    int* slot_j = reinterpret_cast<int*>(sb1 + HID + NW * (32 * ED + 32 * HID)) + warp * 64;
+    R* at1 = sb1 + HID + warp * (32 * EK + 32 * HID);   // [32][48] swizzled
+    R* at2 = at1 + 32 * EK;                             // [32][32] swizzled
+    int* slot_j = reinterpret_cast<int*>(sb1 + HID + NW * (32 * EK + 32 * HID)) + warp * 64;
     int* slot_p = slot_j + 32;
 
-    for (int t = threadIdx.x; t < ED * HID; t += NW * 32) sC[t] = a.Cw[t];
+    for (int t = threadIdx.x; t < EK * HID; t += NW * 32) sC[t] = a.Cw[t];
     for (int t = threadIdx.x; t < HID * HID; t += NW * 32) sW2[t] = a.W2[t];
     if (threadIdx.x < HID) { sb2[threadIdx.x] = a.b2[threadIdx.x]; sb1[threadIdx.x] = a.b1[threadIdx.x]; }
     __syncthreads();
@@ -80,16 +81,16 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kern
                 }
                 __syncwarp();
 #pragma unroll 4
-                for (int f = lane; f < 32 * (ED / 4); f += 32) {       // stage e rows, 12 chunks per slot
-                    const int sl = f / (ED / 4), ch = f - sl * (ED / 4);
+                for (int f = lane; f < 32 * (EK / 4); f += 32) {       // stage e rows, 12 chunks per slot
+                    const int sl = f / (EK / 4), ch = f - sl * (EK / 4);
                     const int pp = slot_p[sl];
                     Vec4<R> ev = vzero<R>();
-                    if (pp >= 0) ev = cvt4<R>(__ldg(reinterpret_cast<const float4*>(a.e + (int64_t)pp * ED) + ch));
-                    stv(at1 + tile_off(sl, ch, ED), ev);
+                    if (pp >= 0) ev = cvt4<R>(__ldg(reinterpret_cast<const float4*>(a.e + (int64_t)pp * EK) + ch));
+                    stv(at1 + tile_off(sl, ch, EK), ev);
                 }
                 __syncwarp();
                 zero_acc(acc);
-                tile_gemm<R, ED, HID>(at1, sC, og * 4, acc, pg);
+                tile_gemm<R, EK, HID>(at1, sC, og * 4, acc, pg);
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     const int jj = slot_j[pg * 8 + s];
@@ -177,7 +178,8 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kern
 }
 
 template <typename R> static size_t gnn_smem_bytes(int nw) {
-    return sizeof(R) * (ED * HID + HID * HID + 2 * HID + (size_t)nw * (32 * ED + 32 * HID)) + sizeof(int) * nw * 64;
+    constexpr int EK = EKof<R>::v;
+    return sizeof(R) * (EK * HID + HID * HID + 2 * HID + (size_t)nw * (32 * EK + 32 * HID)) + sizeof(int) * nw * 64;
 }
 
 template <typename R, bool LARGE, int NW>

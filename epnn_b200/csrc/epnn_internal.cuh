@@ -11,6 +11,7 @@
 #define HID 32          // hidden width of message / pass MLPs
 #define HD 48           // h_dim
 #define ED 48           // e_dim
+#define EDR 16          // numerical rank of the radial-descriptor family at FP32 precision (see epnn_create: rbf_basis)
 #define UPD_IN 80       // [h | M]
 #define SMALL_MAX 48    // systems with n <= SMALL_MAX are packed into warp-private "bundles" (epnn_bundle.cu)
 #define BUNDLE_ATOMS SMALL_MAX   // max atoms of one bundle (whole systems only)
@@ -20,6 +21,10 @@
 // ------------------------------------------------------------------------------------------------
 // Vector of 4 reals: one LDS.128 / LDG.128 for float, two for double.
 template <typename R> struct alignas(4 * sizeof(R)) Vec4 { R x, y, z, w; };
+// Width of the per-pair descriptor row the pair kernels consume: the FP32 path stores the EDR coefficients of e_ij in
+// an orthonormal basis of the (numerically rank-16) family of radial descriptors, the FP64 verification path the 48
+// float32-rounded values themselves.
+template <typename R> struct EKof { static constexpr int v = sizeof(R) == 4 ? EDR : ED; };
 
 template <typename R> __device__ __forceinline__ Vec4<R> vzero() { Vec4<R> v; v.x = v.y = v.z = v.w = R(0); return v; }
 template <typename R> __device__ __forceinline__ Vec4<R> vadd(Vec4<R> a, Vec4<R> b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; return a; }
@@ -137,6 +142,7 @@ __device__ __forceinline__ void tile_gemm_f32x2(const float* __restrict__ at, co
 #pragma unroll
     for (int s = 0; s < 8; ++s) { unpack2(c[s][0], acc[s][0], acc[s][1]); unpack2(c[s][1], acc[s][2], acc[s][3]); }
 }
+template <> __device__ __forceinline__ void tile_gemm<float, EDR, HID>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<EDR, HID>(at, W, wcol, acc, pg); }
 template <> __device__ __forceinline__ void tile_gemm<float, ED, HID>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<ED, HID>(at, W, wcol, acc, pg); }
 template <> __device__ __forceinline__ void tile_gemm<float, HID, HID>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<HID, HID>(at, W, wcol, acc, pg); }
 template <> __device__ __forceinline__ void tile_gemm<float, UPD_IN, HID>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<UPD_IN, HID>(at, W, wcol, acc, pg); }
@@ -157,7 +163,7 @@ template <typename R> struct StepW {      // one message or pass MLP, first laye
     const R* Ah64;   // [48][64]  h-rows of the first layer:  cols 0..31 = a_i block (u), 32..63 = a_j block (v)
     const R* Aq64;   // [64]      q-row
     const R* Ax64;   // [MAX_SPECIES][64]  per-species x contribution, b1 folded into the v half
-    const R* Cw;     // [48][32]  e-rows
+    const R* Cw;     // [EK][32]  e-rows: EK = 48 (FP64: C itself) or 16 (FP32: B^T C, B = reduced basis of the descriptors)
     const R* b1;     // [32]      (v of a padded atom: a_j = 0, e = 0)
     const R* W2;     // [32][32]
     const R* b2;     // [32]
@@ -193,6 +199,7 @@ struct Workspace {
     int* atom_sys;
     int* deg; int* degU; int* rowptr; int* ustart; int* col; int* pid;
     int* pair_i; int* pair_j; double* pair_D; float* e; unsigned char* near;
+    int ek;                            // floats per row of `e`: ED (48 descriptor values) or EDR (16 basis coefficients)
     int* work_counter;                 // device int: dynamic work queue of the bundle kernels
     int2* bundle; int n_bundles;       // (first atom, atom count) of every bundle of small systems (n <= SMALL_MAX)
     int* bundle_nat; unsigned char* perm_j;   // atoms of the bundle (at its first atom); rank of a pair's j inside its tile
@@ -223,6 +230,7 @@ cudaError_t launch_scan_i32(const int* in, int* out, int n, int* tmp, cudaStream
 cudaError_t launch_nbr_fill(const Workspace& w, const CellWork& cw, cudaStream_t st, int* n_launch);
 cudaError_t launch_edges_dense(int n, const float* xyz, float* e, cudaStream_t st);
 cudaError_t upload_rbf_centers(const double* mu);
+cudaError_t upload_rbf_basis(const double* B);      // [ED][EDR]
 
 cudaError_t launch_far_count(const Workspace& w, int* far_cnt, int* atom_b0, cudaStream_t st, int* n_launch);
 cudaError_t launch_far_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* n_launch);

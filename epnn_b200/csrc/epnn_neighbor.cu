@@ -15,7 +15,10 @@
 
 __constant__ double c_mu[ED];
 
+__constant__ double c_B[ED * EDR];       // orthonormal basis of the descriptor family, [k][r]
+
 cudaError_t upload_rbf_centers(const double* mu) { return cudaMemcpyToSymbol(c_mu, mu, sizeof(double) * ED); }
+cudaError_t upload_rbf_basis(const double* B) { return cudaMemcpyToSymbol(c_B, B, sizeof(double) * ED * EDR); }
 
 // float64 distance exactly as scipy computes it; intrinsics forbid FMA contraction.
 __device__ __forceinline__ double dist64(float xi, float yi, float zi, float xj, float yj, float zj) {
@@ -268,7 +271,11 @@ __global__ void nbr_rev_kernel(int n_atoms, const int* __restrict__ rowptr, cons
 // which hold max_k e_k, the quantity the reference's is_near predicate tests (charge_gn.py:90-94) -- are evaluated
 // with the reference's own formula, so the near flag and those entries are bit-exact.
 // Rows are staged in shared memory and written as whole 128-byte lines.
+// EKOUT == ED : the 48 float32 descriptor values (FP64 verification path).
+// EKOUT == EDR: their EDR coefficients c = B^T e in the orthonormal basis B (float64 dot products of the float32-rounded
+//               e, rounded once to float32): what the FP32 pair kernels consume (C^T e = (B^T C)^T c up to 5e-10).
 #define EDGE_PAIRS 128
+template <int EKOUT>
 __global__ void __launch_bounds__(EDGE_PAIRS) edge_desc_kernel(int64_t P, const double* __restrict__ pair_D,
                                                                float* __restrict__ e, unsigned char* __restrict__ near) {
     __shared__ float tile[EDGE_PAIRS][ED + 1];
@@ -299,11 +306,23 @@ __global__ void __launch_bounds__(EDGE_PAIRS) edge_desc_kernel(int64_t P, const 
             emax = fmaxf(emax, ef);
         }
         near[p] = emax > 1e-5f ? 1 : 0;
+        if (EKOUT != ED) {
+            double cr[EDR];
+#pragma unroll
+            for (int r = 0; r < EDR; ++r) cr[r] = 0.0;
+            for (int k = 0; k < ED; ++k) {
+                const double ek = (double)row[k];
+#pragma unroll
+                for (int r = 0; r < EDR; ++r) cr[r] = fma(c_B[k * EDR + r], ek, cr[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < EDR; ++r) row[r] = __double2float_rn(cr[r]);
+        }
     }
     __syncthreads();
     const int rows = (int)min((int64_t)EDGE_PAIRS, P - p0);
-    float* dst = e + p0 * ED;
-    for (int f = threadIdx.x; f < rows * ED; f += EDGE_PAIRS) dst[f] = tile[f / ED][f % ED];
+    float* dst = e + p0 * EKOUT;
+    for (int f = threadIdx.x; f < rows * EKOUT; f += EDGE_PAIRS) dst[f] = tile[f / EKOUT][f % EKOUT];
 }
 
 cudaError_t launch_nbr_fill(const Workspace& w, const CellWork& cw, cudaStream_t st, int* nl) {
@@ -315,7 +334,8 @@ cudaError_t launch_nbr_fill(const Workspace& w, const CellWork& cw, cudaStream_t
     nbr_rev_kernel<<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.rowptr, w.ustart, w.degU, w.col, w.pid);
     ++*nl;
     if (w.P > 0) {
-        edge_desc_kernel<<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near);
+        if (w.ek == ED) edge_desc_kernel<ED><<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near);
+        else            edge_desc_kernel<EDR><<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near);
         ++*nl;
     }
     return cudaGetLastError();

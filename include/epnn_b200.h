@@ -183,6 +183,10 @@ int epnn_measure_fp32_peak(epnn_ctx* ctx, int repeats, double* tflops_out);
 /* The 48 Gaussian centres mu_k = linspace(0.1, 3.0, 48) the kernels use (charge_gn.py:123). */
 int epnn_rbf_centers(double* mu_out48);
 
+/* Orthonormal basis B[48][16] (row-major) of the numerically rank-16 family of radial descriptors; the FP32 pair
+ * kernels carry B^T e (16 coefficients) per pair instead of e (48 values): max |e - B B^T e| < 1e-9 for every D. */
+int epnn_rbf_basis(double* B48x16);
+
 /* Library / build identification, e.g. "epnn_b200 0.1.0 sm_100a". */
 const char* epnn_version(void);
 

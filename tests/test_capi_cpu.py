@@ -53,3 +53,17 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_descriptor_basis_is_orthonormal_and_complete_to_1e9():
+    """The FP32 kernels carry B^T e (16 numbers) per pair instead of e (48): B must be orthonormal and the family of
+    radial descriptors e(D) (charge_gn.py:148-161) must lie in span(B) to far below float32 round-off for EVERY D."""
+    lib = _capi.load()
+    B = np.zeros((48, 16))
+    assert lib.epnn_rbf_basis(B.ctypes.data_as(C.c_void_p)) == 0
+    assert np.abs(B.T @ B - np.eye(16)).max() < 1e-12
+    mu = np.linspace(0.1, 3.0, 48)
+    D = np.concatenate([np.linspace(0.0, 3.0, 100001)[:-1], np.random.default_rng(1).uniform(0, 3, 50000)])
+    Cc = (np.cos(np.pi * D / 3.0) + 1.0) / 2.0
+    E = Cc[:, None] * np.exp(-2.0 * (D[:, None] - mu[None]) ** 2)
+    assert np.abs(E - (E @ B) @ B.T).max() < 1e-9
