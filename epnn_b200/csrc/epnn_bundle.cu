@@ -26,6 +26,9 @@
 #ifndef EPN_NW
 #define EPN_NW 8
 #endif
+#ifndef GNN_NW
+#define GNN_NW 8
+#endif
 
 template <typename R> struct BundleArgs {
     int n_bundles; const int2* bundle; int* work_counter;      // dynamic bundle queue (zeroed before the launch)
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
 template <typename R, bool EPN>
 static cudaError_t launch_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* nl) {
     if (w.n_bundles == 0) return cudaSuccess;
-    constexpr int NW = sizeof(R) == 4 ? (EPN ? EPN_NW : 8) : 4;   // the EPN variant has no S accumulators: more warps fit
+    constexpr int NW = sizeof(R) == 4 ? (EPN ? EPN_NW : GNN_NW) : 4;   // the EPN variant has no S accumulators: more warps fit
     BundleArgs<R> ba;
     ba.n_bundles = w.n_bundles; ba.bundle = w.bundle; ba.work_counter = w.work_counter;
     cudaError_t e0 = cudaMemsetAsync(w.work_counter, 0, sizeof(int), st);
