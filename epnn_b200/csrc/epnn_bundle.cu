@@ -9,7 +9,7 @@
 // which share C^T e_ij (e is symmetric):
 //
 //   GNN step (replaces reference charge_gn.py:62-70, GNN_layer.call, per step t):
-//     near tiles: 32 unordered pairs; ce = C^T e;  m_ij = relu(W2^T relu(ce + u_i + v_j) + b2) -> S_i,
+//     near tiles: 32 unordered pairs; ce = C^T e  (FP32: (B^T C)^T (B^T e) in the rank-16 descriptor basis);  m_ij = relu(W2^T relu(ce + u_i + v_j) + b2) -> S_i,
 //                                                  m_ji = relu(W2^T relu(ce + u_j + v_i) + b2) -> S_j
 //     far tiles : 32 ORDERED pairs (i,j) with e_ij == 0 (self pair, pairs beyond the cutoff) from a precomputed
 //                 per-bundle list, plus one weighted pseudo-pair per atom for the (npad - n) padded atoms
@@ -19,7 +19,7 @@
 //     per-atom kernel's fixed-order CSR reduction).
 //
 // The scatter into S is a warp-private, fixed-order segmented sum over the sorted targets (scatter_sorted): no atomics,
-// bitwise reproducible.  Only the e rows (192 B per pair, streamed once per launch) and the index lists come from
+// bitwise reproducible.  Only the descriptor rows (EK floats per pair: 64 B in FP32, streamed once per launch) and the index lists come from
 // global memory inside the tile loop, and both are prefetched one tile ahead into registers.
 #include "epnn_internal.cuh"
 
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
     R* uv = sx + HID + warp * L::PW;                 // [BUNDLE_ATOMS][64]
     R* S = uv + BUNDLE_ATOMS * 64;                   // [BUNDLE_ATOMS][32]      (GNN only)
     R* padw = S + BUNDLE_ATOMS * HID;                // [BUNDLE_ATOMS]          (GNN only)
-    R* eb = uv + BUNDLE_ATOMS * 64 + (EPN ? 0 : BUNDLE_ATOMS * HID + BUNDLE_ATOMS);   // [32][48] e tile, then [32][32] z tile
+    R* eb = uv + BUNDLE_ATOMS * 64 + (EPN ? 0 : BUNDLE_ATOMS * HID + BUNDLE_ATOMS);   // [32][EK] descriptor tile, then [32][32] z tile
     int* sl_i = reinterpret_cast<int*>(sx + HID + NW * L::PW) + warp * L::PI;
     int* sl_c = sl_i + 32;                           // packed slot code: local i | local j << 8 (0xFF = pad pseudo-atom), -1 = empty
     int* sl_p = sl_i + 64;                           // near: position of the slot when the tile is sorted by j

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) epn_pair_kern
         const int64_t rows_left = a.P - tile * 32;
         const float4* esrc = reinterpret_cast<const float4*>(a.e + tile * 32 * EK);
 #pragma unroll 4
-        for (int f = lane; f < 32 * (EK / 4); f += 32) {           // 32 rows x 192 B, contiguous in HBM
+        for (int f = lane; f < 32 * (EK / 4); f += 32) {           // 32 descriptor rows, contiguous in HBM
             const int sl = f / (EK / 4), ch = f - sl * (EK / 4);
             Vec4<R> ev = vzero<R>();
             if (sl < rows_left) ev = cvt4<R>(__ldg(esrc + f));

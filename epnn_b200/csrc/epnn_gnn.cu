@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kern
     R* sb2 = sW2 + HID * HID;                        // [32]
     R* sb1 = sb2 + HID;                              // [32]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    R* at1 = sb1 + HID + warp * (32 * EK + 32 * HID);   // [32][48] swizzled
+    R* at1 = sb1 + HID + warp * (32 * EK + 32 * HID);   // [32][EK] swizzled
     R* at2 = at1 + 32 * EK;                             // [32][32] swizzled
     int* slot_j = reinterpret_cast<int*>(sb1 + HID + NW * (32 * EK + 32 * HID)) + warp * 64;
     int* slot_p = slot_j + 32;
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kern
                 }
                 __syncwarp();
 #pragma unroll 4
-                for (int f = lane; f < 32 * (EK / 4); f += 32) {       // stage e rows, 12 chunks per slot
+                for (int f = lane; f < 32 * (EK / 4); f += 32) {       // stage the descriptor rows (gathered by pair id)
                     const int sl = f / (EK / 4), ch = f - sl * (EK / 4);
                     const int pp = slot_p[sl];
                     Vec4<R> ev = vzero<R>();
