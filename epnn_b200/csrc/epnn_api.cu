@@ -31,6 +31,7 @@ struct epnn_ctx {
     cudaStream_t stream = nullptr;
     int precision = 32, timing = 0, keep_hidden = 0;
     int far_tensor = 0;          // option "gnn_far_tensor"
+    int dedup_far = 1;           // option "dedup_far": collapse species-equivalent far columns (exact)
     float* w2split = nullptr;    // [T][2][32][32]: hi / lo parts of W2^T of every message MLP (tensor-core far kernel)
     int shard_rank = 0, shard_world = 1;
     epnn_allreduce_fn allreduce = nullptr;
@@ -53,7 +54,7 @@ static thread_local std::string g_create_err;
 
 enum {
     B_XYZ, B_SPECIES, B_OFF, B_Q, B_NPAD, B_ATOMSYS, B_DEG, B_DEGU, B_ROWPTR, B_USTART, B_COL, B_PID, B_PI, B_PJ, B_PD,
-    B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_ATOMB0, B_BNAT, B_PERM, B_LARGESYS, B_GRID, B_CELLCNT, B_CELLSTART, B_CELLATOMS, B_DTMP, B_H, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
+    B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_FAR0CNT, B_FAR0OFF, B_FAR0LIST, B_FAR0W, B_REP, B_ATOMB0, B_BNAT, B_PERM, B_LARGESYS, B_GRID, B_CELLCNT, B_CELLSTART, B_CELLATOMS, B_DTMP, B_H, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
     B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_COUNT
 };
 
@@ -360,6 +361,7 @@ extern "C" int epnn_set_option(epnn_ctx* c, const char* key, double value) {
     } else if (k == "timing") c->timing = value != 0;
     else if (k == "keep_hidden") c->keep_hidden = value != 0;
     else if (k == "gnn_far_tensor") c->far_tensor = value != 0;
+    else if (k == "dedup_far") c->dedup_far = value != 0;
     else if (k == "chunk_atoms") {
         if (value < 64) return fail(c, EPNN_E_INVALID, "chunk_atoms must be >= 64");
         c->chunk_atoms = (int64_t)value;
@@ -462,6 +464,11 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     ENS(B_USTART, sizeof(int) * ((size_t)n_atoms + 1), w.ustart, int*);
     ENS(B_FARCNT, sizeof(int) * ((size_t)n_atoms + 1), far_cnt, int*);
     ENS(B_FAROFF, sizeof(int) * ((size_t)n_atoms + 1), w.far_off, int*);
+    int* far0_cnt;
+    ENS(B_FAR0CNT, sizeof(int) * ((size_t)n_atoms + 1), far0_cnt, int*);
+    ENS(B_FAR0OFF, sizeof(int) * ((size_t)n_atoms + 1), w.far0_off, int*);
+    ENS(B_REP, sizeof(int) * ((size_t)n_atoms + 1), w.rep, int*);
+    w.dedup_far = c->dedup_far;
     ENS(B_ATOMB0, sizeof(int) * ((size_t)n_atoms + 1), atom_b0, int*);
     ENS(B_BNAT, sizeof(int) * ((size_t)n_atoms + 1), w.bundle_nat, int*);
     ENS(B_QD, sizeof(double) * (size_t)n_atoms, w.q, double*);
@@ -539,6 +546,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     if (c->h_flags[0] & 2) return fail(c, EPNN_E_INVALID, "a system with zero (or negative) atoms was passed");
     if (c->h_flags[0] & 4) return fail(c, EPNN_E_INVALID, "species index outside the element table (n_x=%d has %d species)", c->n_x, c->n_species);
     w.nnz = c->h_flags[1]; w.P = c->h_flags[2]; w.n_far = c->h_flags[3]; w.n_rg_large = c->h_flags[4];
+    w.n_far0 = (int64_t)(MAX_SPECIES + 1) * n_atoms;      // capacity: at most one slot per species + the pad slot per row
     if (w.nnz < 0 || w.P < 0 || w.n_far < 0) return fail(c, EPNN_E_UNSUPPORTED, "pair lists of one chunk exceed 2^31 entries; lower chunk_atoms");
     w.nsplit = 1;
     w.far_tc = 0;
@@ -563,6 +571,8 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     ENS(B_NEAR, (size_t)(w.P + 16), w.near, unsigned char*);
     ENS(B_PERM, (size_t)(w.P + 16), w.perm_j, unsigned char*);
     ENS(B_FARLIST, sizeof(unsigned short) * (size_t)(w.n_far + 2), w.far_list, unsigned short*);
+    ENS(B_FAR0LIST, sizeof(unsigned short) * (size_t)(w.n_far0 + 2), w.far0_list, unsigned short*);
+    ENS(B_FAR0W, (size_t)(w.n_far0 + 16), w.far0_w, unsigned char*);
     ENS(B_RGL, sizeof(int) * (size_t)(w.n_rg_large + 1), w.rg_large, int*);
     rg_fill_kernel<<<div_up(n_sys, 256), 256, 0, st>>>(n_sys, off_local, rgl_off, w.rg_large);
     ++*n_launch;
@@ -570,6 +580,10 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     if (cw.n_large) ENS(B_DTMP, sizeof(double) * (size_t)(w.nnz + 1), cw.Dtmp, double*);
     CU(c, launch_nbr_fill(w, cw, st, n_launch));
     CU(c, launch_far_fill(w, atom_b0, st, n_launch));
+    // species-compressed far list (needs the filled CSR): counts -> offsets -> slots; its size is bounded, no host sync
+    CU(c, launch_far0_count(w, far0_cnt, st, n_launch));
+    CU(c, launch_scan_i32(far0_cnt, w.far0_off, n_atoms, scantmp, st, n_launch));
+    CU(c, launch_far0_fill(w, atom_b0, st, n_launch));
     tm.mark(2);
     if (stats) {
         stats->n_pairs_e += w.P;

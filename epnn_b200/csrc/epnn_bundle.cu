@@ -35,6 +35,9 @@ template <typename R> struct BundleArgs {
     const int* ustart; const int* pair_i; const int* pair_j; const unsigned char* near; const float* e;
     const unsigned char* perm_j;                              // per pair: rank of its j among the pairs of its tile
     const int* far_off; const unsigned short* far_list;
+    // species-compressed far list: one weighted slot per (row, species of the column) -- used when the v rows of a
+    // bundle depend on the species only (always true at step 0; at every step if the hidden state is species-wise constant)
+    const int* far0_off; const unsigned short* far0_list; const unsigned char* far0_w; const int* rep; int dedup;
     const int* atom_sys; const int* sys_off; const int* npad;
     const R* u; const R* v;
     const R* Cw; const R* W2; const R* b2; const R* x32;      // x32 = b1 (GNN) or w3 (EPN)
@@ -310,10 +313,30 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
 
         if (!EPN) {
             // ------------------------------------------------------------ far tiles (ordered pairs with e == 0, pad pseudo-pairs)
-            const int f0 = a.far_off[atom0], f1 = a.far_off[atom0 + nat];
+            // Exact de-duplication: a far message depends on the column j only through v_j.  If every atom of the bundle
+            // has the same v row (bit for bit) as the first atom of its system with the same species, the far columns of a
+            // row collapse to one weighted slot per species: sum_j m(u_i, v_j) = sum_s count_is * m(u_i, v_rep(s)).
+            bool use0 = a.dedup != 0;
+            if (use0) {
+                bool same = true;
+                for (int r = lane; r < nat; r += 32) {
+                    const int rp = a.rep[atom0 + r] - atom0;
+                    if (rp != r) {
+#pragma unroll
+                        for (int c = 0; c < HID / 4; ++c) {
+                            const Vec4<R> x = ldv(uv + r * 64 + HID + c * 4), y = ldv(uv + rp * 64 + HID + c * 4);
+                            same = same && x.x == y.x && x.y == y.y && x.z == y.z && x.w == y.w;
+                        }
+                    }
+                }
+                use0 = __all_sync(0xffffffffu, same);
+            }
+            const unsigned short* flist = use0 ? a.far0_list : a.far_list;
+            const int f0 = use0 ? a.far0_off[atom0] : a.far_off[atom0], f1 = use0 ? a.far0_off[atom0 + nat] : a.far_off[atom0 + nat];
             const int nft = (f1 - f0 + 31) >> 5;
             R acc[8][4];
-            int n_code = (f0 + lane < f1) ? (int)a.far_list[f0 + lane] : -1;
+            int n_code = (f0 + lane < f1) ? (int)flist[f0 + lane] : -1;
+            int n_cnt = (use0 && f0 + lane < f1) ? (int)a.far0_w[f0 + lane] : 1;
             for (int t = 0; t < nft; ++t) {
                 int my_code;
                 R my_w;
@@ -322,13 +345,14 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                     R wv = R(1);
                     if (n_code >= 0) {
                         li = n_code >> 8; lj = n_code & 0xFF;
-                        if (lj == 0xFF) wv = padw[li];
+                        wv = lj == 0xFF ? padw[li] : (R)n_cnt;        // pad pseudo-pair: npad - n; compressed slot: column count
                     }
                     my_code = li < 0 ? -1 : (li | (lj << 8)); my_w = wv;
                 }
                 {
                     const int k = f0 + (t + 1) * 32 + lane;
-                    n_code = k < f1 ? (int)a.far_list[k] : -1;
+                    n_code = k < f1 ? (int)flist[k] : -1;
+                    n_cnt = (use0 && k < f1) ? (int)a.far0_w[k] : 1;
                 }
                 int tg[8];
                 R wcode[8];
@@ -381,6 +405,7 @@ static cudaError_t launch_bundle(const Workspace& w, const StepW<R>& sw, cudaStr
     ba.ustart = w.ustart; ba.pair_i = w.pair_i; ba.pair_j = w.pair_j; ba.near = w.near; ba.e = w.e;
     ba.perm_j = w.perm_j;
     ba.far_off = w.far_off; ba.far_list = w.far_list;
+    ba.far0_off = w.far0_off; ba.far0_list = w.far0_list; ba.far0_w = w.far0_w; ba.rep = w.rep; ba.dedup = w.dedup_far;
     ba.atom_sys = w.atom_sys; ba.sys_off = w.sys_off; ba.npad = w.npad;
     ba.u = (const R*)w.u; ba.v = (const R*)w.v;
     ba.Cw = sw.Cw; ba.W2 = sw.W2; ba.b2 = sw.b2; ba.x32 = EPN ? sw.W3 : sw.b1;
@@ -460,6 +485,63 @@ __global__ void far_fill_kernel(int n_atoms, const int* __restrict__ atom_sys, c
         far_list[w++] = (unsigned short)(hi | (j - b0));
     }
     if (npad[s] > a1 - a0) far_list[w++] = (unsigned short)(hi | 0xFF);
+}
+
+// Species-compressed far list.  PASS 0: rep[i] (first atom of i's system with i's species) and the number of slots of
+// row i = #{species s with at least one far column} + (pad ? 1 : 0).  PASS 1: the slots, species ascending:
+// code = (i - b0) << 8 | (rep_s - b0), weight = number of far columns of species s (the self pair counts as far).
+template <int PASS>
+__global__ void far0_kernel(int n_atoms, const int* __restrict__ atom_sys, const int* __restrict__ sys_off,
+                            const int* __restrict__ npad, const int* __restrict__ species, const int* __restrict__ rowptr,
+                            const int* __restrict__ col, const int* __restrict__ atom_b0, int* __restrict__ rep,
+                            int* __restrict__ cnt_out, const int* __restrict__ off, unsigned short* __restrict__ list,
+                            unsigned char* __restrict__ wgt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_atoms) return;
+    const int s = atom_sys[i];
+    const int a0 = sys_off[s], a1 = sys_off[s + 1];
+    if (a1 - a0 > SMALL_MAX) { if (PASS == 0) { cnt_out[i] = 0; rep[i] = i; } return; }
+    int cnt[MAX_SPECIES], first[MAX_SPECIES];
+#pragma unroll
+    for (int k = 0; k < MAX_SPECIES; ++k) { cnt[k] = 0; first[k] = -1; }
+    for (int j = a0; j < a1; ++j) {
+        const int sj = species[j] & (MAX_SPECIES - 1);
+        ++cnt[sj];
+        if (first[sj] < 0) first[sj] = j;
+    }
+    for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) --cnt[species[col[k]] & (MAX_SPECIES - 1)];
+    const bool pad = npad[s] > a1 - a0;
+    if (PASS == 0) {
+        int n = pad ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < MAX_SPECIES; ++k) n += cnt[k] > 0;
+        cnt_out[i] = n;
+        rep[i] = first[species[i] & (MAX_SPECIES - 1)];
+    } else {
+        const int b0 = atom_b0[i];
+        const int hi = (i - b0) << 8;
+        int w = off[i];
+#pragma unroll
+        for (int k = 0; k < MAX_SPECIES; ++k)
+            if (cnt[k] > 0) { list[w] = (unsigned short)(hi | (first[k] - b0)); wgt[w] = (unsigned char)cnt[k]; ++w; }
+        if (pad) { list[w] = (unsigned short)(hi | 0xFF); wgt[w] = 0; }
+    }
+}
+
+cudaError_t launch_far0_count(const Workspace& w, int* cnt, cudaStream_t st, int* nl) {
+    if (w.n_atoms == 0) return cudaSuccess;
+    far0_kernel<0><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.npad, w.species, w.rowptr, w.col,
+                                                           nullptr, w.rep, cnt, nullptr, nullptr, nullptr);
+    ++*nl;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_far0_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* nl) {
+    if (w.n_atoms == 0 || w.n_bundles == 0) return cudaSuccess;
+    far0_kernel<1><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.npad, w.species, w.rowptr, w.col,
+                                                           atom_b0, nullptr, nullptr, w.far0_off, w.far0_list, w.far0_w);
+    ++*nl;
+    return cudaGetLastError();
 }
 
 // perm_j[p] = position of pair p inside its 32-pair tile when the tile's valid pairs are ordered by (j, slot).  Tiles

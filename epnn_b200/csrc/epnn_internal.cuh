@@ -203,7 +203,8 @@ struct Workspace {
     int* work_counter;                 // device int: dynamic work queue of the bundle kernels
     int2* bundle; int n_bundles;       // (first atom, atom count) of every bundle of small systems (n <= SMALL_MAX)
     int* bundle_nat; unsigned char* perm_j;   // atoms of the bundle (at its first atom); rank of a pair's j inside its tile
-    int* far_off; unsigned short* far_list; int64_t n_far;   // per-bundle list of the GNN's e == 0 ("far") ordered pairs
+    int* far_off; unsigned short* far_list; int64_t n_far;
+    int* far0_off; unsigned short* far0_list; unsigned char* far0_w; int* rep; int64_t n_far0; int dedup_far;   // species-compressed far list   // per-bundle list of the GNN's e == 0 ("far") ordered pairs
     int* rg_large; int n_rg_large; int nsplit;    // 4-row groups of the large systems
     int far_tc;                                   // 1: the far part of the big-system message sum runs on the tensor cores;
                                                   //    planes [0, nsplit-1) of S are theirs, the SIMT kernel (near only) owns the last
@@ -234,6 +235,8 @@ cudaError_t upload_rbf_basis(const double* B);      // [ED][EDR]
 
 cudaError_t launch_far_count(const Workspace& w, int* far_cnt, int* atom_b0, cudaStream_t st, int* n_launch);
 cudaError_t launch_far_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* n_launch);
+cudaError_t launch_far0_count(const Workspace& w, int* cnt, cudaStream_t st, int* n_launch);
+cudaError_t launch_far0_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_gnn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_epn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 cudaError_t launch_gnn_far_tc(const Workspace& w, const float* Whi, const float* Wlo, const float* b2, int nsplit_tc,

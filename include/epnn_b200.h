@@ -79,6 +79,9 @@ const char* epnn_last_error(const epnn_ctx* ctx);
 /* Options: "precision" 32 (default, FP32 SIMT, FP64 accumulation of message sums and charges) or
  * 64 (every kernel in FP64: the verification variant); "timing" 0/1; "chunk_atoms" (internal batch size);
  * "keep_hidden" 0/1 (retain the final GNN hidden state for epnn_get_hidden);
+ * "dedup_far" 1 (default) / 0: small systems collapse far columns whose v rows are bit-identical (same system, same
+ * species, same hidden state -- always the case at the first message-passing step) into one weighted slot per species:
+ * an exact reuse of identical messages, switched off only for ablation;
  * "gnn_far_tensor" 0 (default) / 1: systems with more than 48 atoms evaluate the e == 0 ("far") part of the
  * message sum -- the O(n^2) part -- on the tcgen05 tensor cores with a 3xTF32 error-compensated split and FP32
  * accumulation in tensor memory instead of FP32 SIMT (precision 32 only; results differ from the SIMT path at

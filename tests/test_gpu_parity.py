@@ -402,3 +402,23 @@ def test_synthetic_qm9_stream_properties(engines, weights):
         assert np.abs(back - q64).max() < 2e-5
     finally:
         eng.set_option("chunk_atoms", 4 * 1024 * 1024)
+
+
+@pytest.mark.parametrize("name", ["decay_model_weights", "model2_weights", "model_weights"])
+def test_far_dedup_is_exact(engines, weights, mixed, name):
+    """Collapsing species-equivalent far columns (dedup_far, default on) reuses bit-identical messages: it must change
+    nothing beyond the order of a few additions -- FP64 kernels agree to 1e-12, FP32 to FP32 round-off -- whether the
+    hidden state is live (model2 / model_weights: only step 0 collapses) or species-wise constant (decay: every step)."""
+    w = weights[name]
+    rng = np.random.default_rng(21)
+    idx = sorted(rng.choice(mixed.usable(w.n_x), 120, replace=False).tolist())
+    offs, xyz, sp, Q = mixed.batch(idx, w.n_x)
+    for precision, tol in ((64, 1e-12), (32, 3e-6 if name != "model_weights" else 3e-4)):
+        eng = engines(name, precision)
+        on = eng.infer_batch(offs, xyz, sp, Q, 41, want_f64=True)[1].copy()
+        eng.set_option("dedup_far", 0)
+        try:
+            off = eng.infer_batch(offs, xyz, sp, Q, 41, want_f64=True)[1].copy()
+        finally:
+            eng.set_option("dedup_far", 1)
+        assert np.abs(on - off).max() < tol * max(1.0, np.abs(off).max()), (name, precision, np.abs(on - off).max())
