@@ -406,6 +406,10 @@ def run_b200(args):
             "peak_source": "FP32 FMA micro-benchmark measured in this run (epnn_measure_fp32_peak); MEASURED_PEAKS.json "
                            "holds no SIMT peak. north_star: pair MLP defaults to FP32 SIMT, tensor pipe unused",
             "traffic": traffic,
+            "note": "achieved = ALGORITHMIC FLOPs (SURVEY 8d: 2144 per ordered pair + 3072 per e != 0 pair, per step) / CUDA-event time. "
+                    "The kernels execute fewer FLOPs than that count: C^T e once per unordered pair and in the rank-16 descriptor "
+                    "basis, and (dedup_far) one far slot per species instead of one per column when the v rows coincide. "
+                    "Hardware utilisation from ncu (profiles/): FMA pipe ~46 % of cycles active, shared-memory wavefronts ~58 % of peak.",
             "launches_per_step": w.T * n_chunks, "avg_launch_ms": ms_gnn / (w.T * n_chunks),
             "algorithmic_flops_per_launch": gnn_flops_step / (w.T * n_chunks),
             "share_of_step": ms_gnn / phases["ms_total"],
