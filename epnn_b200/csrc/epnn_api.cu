@@ -20,9 +20,9 @@ struct DevBuf {
 };
 
 struct PackedOffsets {           // element offsets into the packed device weight buffer (same for float/double)
-    struct Step { size_t Ah64, Aq64, Ax64, Wx64, Cw, Cw16, b1, W2, b2, W3, b3; };
+    struct Step { size_t Ah64, Aq64, Ax64, Wx64, Cw, Cw16, b1, W2, b2, W3, b3, Pf, Axf, HG, g; };
     std::vector<Step> msg, pas;
-    size_t U1, c1, U2, c2, U3, c3;
+    size_t U1, c1, U2, c2, U3, c3, cb1;
     size_t total;
 };
 
@@ -54,7 +54,7 @@ static thread_local std::string g_create_err;
 
 enum {
     B_XYZ, B_SPECIES, B_OFF, B_Q, B_NPAD, B_ATOMSYS, B_DEG, B_DEGU, B_ROWPTR, B_USTART, B_COL, B_PID, B_PI, B_PJ, B_PD,
-    B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_FAR0CNT, B_FAR0OFF, B_FAR0LIST, B_FAR0W, B_REP, B_ATOMB0, B_BNAT, B_PERM, B_LARGESYS, B_GRID, B_CELLCNT, B_CELLSTART, B_CELLATOMS, B_DTMP, B_H, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
+    B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_FAR0CNT, B_FAR0OFF, B_FAR0LIST, B_FAR0W, B_REP, B_ATOMB0, B_BNAT, B_PERM, B_LARGESYS, B_GRID, B_CELLCNT, B_CELLSTART, B_CELLATOMS, B_DTMP, B_H, B_L2, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
     B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_COUNT
 };
 
@@ -140,6 +140,7 @@ template <typename R> static StepW<R> step_view(const R* base, const PackedOffse
     s.Ah64 = base + o.Ah64; s.Aq64 = base + o.Aq64; s.Ax64 = base + o.Ax64; s.b1 = base + o.b1;
     s.Cw = base + (sizeof(R) == 4 ? o.Cw16 : o.Cw);      // FP32 pair kernels work in the reduced descriptor basis
     s.W2 = base + o.W2; s.b2 = base + o.b2; s.W3 = base + o.W3; s.b3 = base + o.b3;
+    s.Pf = base + o.Pf; s.Axf = base + o.Axf; s.HG = base + o.HG; s.g = base + o.g;
     return s;
 }
 template <typename R> static DenseW<R> dense_view(const R* base, const PackedOffsets::Step& o) {
@@ -151,6 +152,7 @@ template <typename R> static DenseW<R> dense_view(const R* base, const PackedOff
 template <typename R> static UpdW<R> upd_view(const R* base, const PackedOffsets& po) {
     UpdW<R> u;
     u.U1 = base + po.U1; u.c1 = base + po.c1; u.U2 = base + po.U2; u.c2 = base + po.c2; u.U3 = base + po.U3; u.c3 = base + po.c3;
+    u.cb1 = base + po.cb1;
     return u;
 }
 
@@ -288,11 +290,13 @@ extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_
         o.Cw = take(cur, 48 * 32); o.Cw16 = take(cur, EDR * 32);
         o.b1 = take(cur, 32); o.W2 = take(cur, 32 * 32); o.b2 = take(cur, 32);
         o.W3 = take(cur, is_pass ? 32 : 32 * 32); o.b3 = take(cur, is_pass ? 1 : 32);
+        o.Pf = take(cur, 32 * 64); o.Axf = take(cur, MAX_SPECIES * 64);
+        o.HG = take(cur, is_pass ? 0 : 64 * 32); o.g = take(cur, is_pass ? 0 : 32);
         return o;
     };
     for (int t = 0; t < T; ++t) po.msg.push_back(step_offsets(false));
     po.U1 = take(cur, 80 * 32); po.c1 = take(cur, 32); po.U2 = take(cur, 32 * 32); po.c2 = take(cur, 32);
-    po.U3 = take(cur, 32 * 48); po.c3 = take(cur, 48);
+    po.U3 = take(cur, 32 * 48); po.c3 = take(cur, 48); po.cb1 = take(cur, 32);
     for (int t = 0; t < T; ++t) po.pas.push_back(step_offsets(true));
     po.total = cur;
     std::vector<double> P(po.total, 0.0);
@@ -326,6 +330,44 @@ extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_
                 }
         CUC(cudaMalloc(&c->w2split, ws.size() * sizeof(float)));
         CUC(cudaMemcpy(c->w2split, ws.data(), ws.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    {   // fold the linear layers around the update MLP (float64, exact algebra): see StepW / UpdW
+        const double* U1 = &P[po.U1]; const double* U3 = &P[po.U3]; const double* c3 = &P[po.c3]; const double* c1 = &P[po.c1];
+        for (int c = 0; c < 32; ++c) {                               // cb1 = c1 + U1_h^T c3
+            double sacc = c1[c];
+            for (int k = 0; k < 48; ++k) sacc += U1[k * 32 + c] * c3[k];
+            P[po.cb1 + c] = sacc;
+        }
+        auto fold_proj = [&](const PackedOffsets::Step& o) {        // Pf = U3 . Ah64 ; Axf = Ax64 + c3^T Ah64
+            for (int r = 0; r < 32; ++r)
+                for (int c = 0; c < 64; ++c) {
+                    double sacc = 0.0;
+                    for (int k = 0; k < 48; ++k) sacc += U3[r * 48 + k] * P[o.Ah64 + k * 64 + c];
+                    P[o.Pf + r * 64 + c] = sacc;
+                }
+            for (int c = 0; c < 64; ++c) {
+                double sacc = 0.0;
+                for (int k = 0; k < 48; ++k) sacc += c3[k] * P[o.Ah64 + k * 64 + c];
+                for (int sp = 0; sp < MAX_SPECIES; ++sp) P[o.Axf + sp * 64 + c] = P[o.Ax64 + sp * 64 + c] + sacc;
+            }
+        };
+        for (int t = 0; t < T; ++t) {
+            fold_proj(po.msg[t]); fold_proj(po.pas[t]);
+            const PackedOffsets::Step& o = po.msg[t];
+            for (int r = 0; r < 32; ++r)
+                for (int c = 0; c < 32; ++c) {
+                    double h1 = 0.0, gg = 0.0;
+                    for (int k = 0; k < 48; ++k) h1 += U3[r * 48 + k] * U1[k * 32 + c];                        // (U3 . U1_h)[r][c]
+                    for (int k = 0; k < 32; ++k) gg += P[o.W3 + r * 32 + k] * U1[(48 + k) * 32 + c];           // (W3 . U1_M)[r][c]
+                    P[o.HG + r * 32 + c] = h1;
+                    P[o.HG + (32 + r) * 32 + c] = gg;
+                }
+            for (int c = 0; c < 32; ++c) {
+                double sacc = 0.0;
+                for (int k = 0; k < 32; ++k) sacc += P[o.b3 + k] * U1[(48 + k) * 32 + c];                      // U1_M^T b3
+                P[o.g + c] = sacc;
+            }
+        }
     }
     std::vector<float> Pf(po.total);
     for (size_t i = 0; i < po.total; ++i) Pf[i] = (float)P[i];
@@ -593,6 +635,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     if (neighbors_only) return EPNN_OK;
 
     ENS(B_H, sizeof(R) * HD * (size_t)n_atoms, w.h, void*);
+    ENS(B_L2, sizeof(R) * HID * (size_t)n_atoms, w.l2, void*);
     ENS(B_S, sizeof(R) * HID * (size_t)n_atoms * w.nsplit, w.S, void*);
     ENS(B_U, sizeof(R) * HID * (size_t)n_atoms, w.u, void*);
     ENS(B_V, sizeof(R) * HID * (size_t)n_atoms, w.v, void*);
@@ -622,7 +665,8 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
             return fail(c, EPNN_E_CUDA, "allreduce callback failed (GNN step %d)", t);
         tm.mark(3);
         const StepW<R>* next = t + 1 < c->T ? &msg[t + 1] : &pas[0];
-        CU(c, launch_atom<R>(w, ATOM_UPDATE | ATOM_PROJECT, &msg[t], &upd, next, 0, nullptr, nullptr, st, n_launch));
+        CU(c, launch_atom<R>(w, ATOM_UPDATE | ATOM_PROJECT | (t == 0 ? ATOM_FIRST : 0) | (t + 1 == c->T ? ATOM_WRITE_H : 0),
+                             &msg[t], &upd, next, 0, nullptr, nullptr, st, n_launch));
         tm.mark(t + 1 < c->T ? 4 : 6);
     }
     // ---- EPN layer: T electron-passing passes (charge_gn.py:98-118)

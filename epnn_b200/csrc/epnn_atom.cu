@@ -4,6 +4,12 @@
 //                  M_i = W3^T S_i + npad * b3        (linear last message layer hoisted out of sum_j)
 //                  h_i = update_fn([h_i | M_i])      80 -> 32 relu -> 32 relu -> 48
 //                (node_mask is 1 for every atom that exists here; padded atoms are never materialised)
+//                The linear maps around the two ReLU layers are composed on the host (float64, exact algebra): with
+//                l2 = the update MLP's last hidden layer (the state carried between steps instead of h),
+//                  l1  = relu([U3 U1_h ; W3 U1_M]^T [l2_prev | S] + c1 + U1_h^T c3 + npad U1_M^T b3)     64 -> 32
+//                  l2  = relu(U2^T l1 + c2)                                                             32 -> 32
+//                  u|v = (U3 Ah)^T l2 + (Ax[species] + c3^T Ah) + q Aq                                  32 -> 64
+//                -- 5 120 MAC per atom and step instead of 9 216; h = U3^T l2 + c3 itself is only formed at the last step.
 //   ATOM_QUPDATE finishes electron-passing pass t (charge_gn.py:116-118):
 //                  q_i += sum over the CSR row of i, in column order, of sign(j - i) * delta_pair
 //                fixed order, FP64, no atomics: deterministic, and sum_i q_i is conserved by construction.
@@ -18,53 +24,53 @@
 template <typename R> struct AtomArgs {
     int n_atoms, mode, nsplit, h_is_zero;
     const int* atom_sys; const int* sys_off; const int* npad; const int* species;
-    const R* Spart; R* h; const R* W3; const R* b3; UpdW<R> upd;
+    const R* Spart; R* h; R* l2; const R* HG; const R* g; const R* cb; UpdW<R> upd;
     const int* rowptr; const int* col; const int* pid; const R* delta; double* q;
-    const R* Ah64; const R* Aq64; const R* Ax64; R* u; R* v;
+    const R* Pf; const R* Aq64; const R* Ax; R* u; R* v;
     float* q_out; double* q_out64;
 };
 
 #ifndef ATOM_NW
 #define ATOM_NW 12
 #endif
-#define ATOM_W_UPD (HID * HID + HID + UPD_IN * HID + HID + HID * HID + HID + HID * HD + HD)   // 6288
-#define ATOM_W_PROJ (HD * 64 + 64 + MAX_SPECIES * 64)                                       // 4160
-#define ATOM_TILE (32 * UPD_IN + 32 * HID)                                                  // 3584 per warp
+#define ATOM_W_UPD (64 * HID + 2 * HID + HID * HID + HID + HID * HD + HD)                    // 4752
+#define ATOM_W_PROJ (HID * 64 + 64 + MAX_SPECIES * 64)                                      // 3136
+#define ATOM_TILE (32 * 64 + 32 * HID)                                                      // 3072 per warp
 
 template <typename R, int NW>
 __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
     extern __shared__ __align__(32) unsigned char smem_raw[];
-    R* sW3 = reinterpret_cast<R*>(smem_raw);   // [32][32]
-    R* sb3 = sW3 + HID * HID;                  // [32]
-    R* sU1 = sb3 + HID;                        // [80][32]
-    R* sc1 = sU1 + UPD_IN * HID;               // [32]
-    R* sU2 = sc1 + HID;                        // [32][32]
+    R* sHG = reinterpret_cast<R*>(smem_raw);   // [64][32]  [U3 U1_h ; W3 U1_M]
+    R* scb = sHG + 64 * HID;                   // [32]      first-layer bias of this step
+    R* sg = scb + HID;                         // [32]      U1_M^T b3
+    R* sU2 = sg + HID;                         // [32][32]
     R* sc2 = sU2 + HID * HID;                  // [32]
     R* sU3 = sc2 + HID;                        // [32][48]
     R* sc3 = sU3 + HID * HD;                   // [48]
-    R* sAh = sc3 + HD;                         // [48][64]
-    R* sAq = sAh + HD * 64;                    // [64]
+    R* sP = sc3 + HD;                          // [32][64]  U3 Ah64 of the next pair kernel
+    R* sAq = sP + HID * 64;                    // [64]
     R* sAx = sAq + 64;                         // [MAX_SPECIES][64]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    R* T80 = sAx + MAX_SPECIES * 64 + warp * ATOM_TILE;    // [32][80]; later [32][48] + [32][32]
-    R* T32 = T80 + 32 * UPD_IN;                            // [32][32]
-    R* T32b = T80 + 32 * HD;                               // aliases the tail of T80 once U1 has been applied
+    R* T64 = sAx + MAX_SPECIES * 64 + warp * ATOM_TILE;    // [32][64] = [l2_prev | S]
+    R* T32 = T64 + 32 * 64;                                // [32][32]
+    R* T32b = T64;                                         // [32][32] l2 tile; aliases T64 once the first layer is done
     R* slot_q = sAx + MAX_SPECIES * 64 + NW * ATOM_TILE + warp * 64;   // [32]
     R* slot_np = slot_q + 32;                                         // [32] npad as real
     int* slot_sp = reinterpret_cast<int*>(sAx + MAX_SPECIES * 64 + NW * ATOM_TILE + NW * 64) + warp * 64;   // [32]
     int* slot_ns = slot_sp + 32;                                      // [32] number of S partial planes
 
     const bool do_upd = a.mode & ATOM_UPDATE, do_q = a.mode & ATOM_QUPDATE, do_proj = a.mode & ATOM_PROJECT;
+    const bool first = a.mode & ATOM_FIRST, write_h = a.mode & ATOM_WRITE_H;
     if (do_upd) {
-        for (int t = threadIdx.x; t < HID * HID; t += NW * 32) { sW3[t] = a.W3[t]; sU2[t] = a.upd.U2[t]; }
-        for (int t = threadIdx.x; t < UPD_IN * HID; t += NW * 32) sU1[t] = a.upd.U1[t];
-        for (int t = threadIdx.x; t < HID * HD; t += NW * 32) sU3[t] = a.upd.U3[t];
-        if (threadIdx.x < HID) { sb3[threadIdx.x] = a.b3[threadIdx.x]; sc1[threadIdx.x] = a.upd.c1[threadIdx.x]; sc2[threadIdx.x] = a.upd.c2[threadIdx.x]; }
+        for (int t = threadIdx.x; t < 64 * HID; t += NW * 32) sHG[t] = a.HG[t];
+        for (int t = threadIdx.x; t < HID * HID; t += NW * 32) sU2[t] = a.upd.U2[t];
+        if (write_h) for (int t = threadIdx.x; t < HID * HD; t += NW * 32) sU3[t] = a.upd.U3[t];
+        if (threadIdx.x < HID) { scb[threadIdx.x] = a.cb[threadIdx.x]; sg[threadIdx.x] = a.g[threadIdx.x]; sc2[threadIdx.x] = a.upd.c2[threadIdx.x]; }
         if (threadIdx.x < HD) sc3[threadIdx.x] = a.upd.c3[threadIdx.x];
     }
     if (do_proj) {
-        for (int t = threadIdx.x; t < HD * 64; t += NW * 32) sAh[t] = a.Ah64[t];
-        for (int t = threadIdx.x; t < MAX_SPECIES * 64; t += NW * 32) sAx[t] = a.Ax64[t];
+        if (!a.h_is_zero) for (int t = threadIdx.x; t < HID * 64; t += NW * 32) sP[t] = a.Pf[t];
+        for (int t = threadIdx.x; t < MAX_SPECIES * 64; t += NW * 32) sAx[t] = a.Ax[t];
         if (threadIdx.x < 64) sAq[threadIdx.x] = a.Aq64[threadIdx.x];
     }
     __syncthreads();
@@ -107,57 +113,39 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
         if (!do_upd && !do_proj) continue;
 
         if (do_upd) {
-            // (1) S tile (sum of the partial planes in fixed order)
+            // (1) [l2_prev | S] tile: l2 of the previous step (zeros at the first step: h = 0), S = partial planes summed in fixed order
 #pragma unroll 2
             for (int f = lane; f < 32 * (HID / 4); f += 32) {
                 const int sl = f >> 3, ch = f & 7;
                 const int at = base + sl;
-                Vec4<R> sv = vzero<R>();
+                Vec4<R> lv = vzero<R>(), sv = vzero<R>();
                 if (at < a.n_atoms) {
+                    if (!first) lv = ldv(a.l2 + (int64_t)at * HID + ch * 4);
                     const int ns = slot_ns[sl];
                     for (int sp = 0; sp < ns; ++sp)
                         sv = vadd(sv, ldv(a.Spart + ((int64_t)sp * a.n_atoms + at) * HID + ch * 4));
                 }
-                stv(T32 + tile_off(sl, ch, HID), sv);
-            }
-            // (3a) h part of the [h | M] tile
-#pragma unroll 4
-            for (int f = lane; f < 32 * (HD / 4); f += 32) {
-                const int sl = f / (HD / 4), ch = f - sl * (HD / 4);
-                const int at = base + sl;
-                Vec4<R> hv = vzero<R>();
-                if (at < a.n_atoms) hv = ldv(a.h + (int64_t)at * HD + ch * 4);
-                stv(T80 + tile_off(sl, ch, UPD_IN), hv);
+                stv(T64 + tile_off(sl, ch, 64), lv);
+                stv(T64 + tile_off(sl, 8 + ch, 64), sv);
             }
             __syncwarp();
-            // (2) M = W3^T S + npad * b3
+            // (2) first layer with W3 / U3 folded in: relu([U3 U1_h ; W3 U1_M]^T [l2_prev | S] + cb + npad * g)
             zero_acc(acc);
-            tile_gemm<R, HID, HID>(T32, sW3, og * 4, acc, pg);
+            tile_gemm<R, 64, HID>(T64, sHG, og * 4, acc, pg);
             {
-                const Vec4<R> b3v = ldv(sb3 + og * 4);
+                const Vec4<R> cv = ldv(scb + og * 4);
+                const Vec4<R> gv = ldv(sg + og * 4);
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     const R np = slot_np[pg * 8 + s];
-                    Vec4<R> m;
-                    m.x = fma(np, b3v.x, acc[s][0]); m.y = fma(np, b3v.y, acc[s][1]);
-                    m.z = fma(np, b3v.z, acc[s][2]); m.w = fma(np, b3v.w, acc[s][3]);
-                    stv(T80 + tile_off(pg * 8 + s, HD / 4 + og, UPD_IN), m);      // (3b) M part
-                }
-            }
-            __syncwarp();
-            // (4) layer 1: 80 -> 32, relu
-            zero_acc(acc);
-            tile_gemm<R, UPD_IN, HID>(T80, sU1, og * 4, acc, pg);
-            {
-                const Vec4<R> cv = ldv(sc1 + og * 4);
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    Vec4<R> z; z.x = relu(acc[s][0] + cv.x); z.y = relu(acc[s][1] + cv.y); z.z = relu(acc[s][2] + cv.z); z.w = relu(acc[s][3] + cv.w);
+                    Vec4<R> z;
+                    z.x = relu(fma(np, gv.x, acc[s][0] + cv.x)); z.y = relu(fma(np, gv.y, acc[s][1] + cv.y));
+                    z.z = relu(fma(np, gv.z, acc[s][2] + cv.z)); z.w = relu(fma(np, gv.w, acc[s][3] + cv.w));
                     stv(T32 + tile_off(pg * 8 + s, og, HID), z);
                 }
             }
             __syncwarp();
-            // (5) layer 2: 32 -> 32, relu   (T80 is dead now; T32b aliases its tail)
+            // (3) second layer: l2 = relu(U2^T l1 + c2)   (T64 is dead now; the l2 tile reuses its head)
             zero_acc(acc);
             tile_gemm<R, HID, HID>(T32, sU2, og * 4, acc, pg);
             {
@@ -165,44 +153,45 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     Vec4<R> z; z.x = relu(acc[s][0] + cv.x); z.y = relu(acc[s][1] + cv.y); z.z = relu(acc[s][2] + cv.z); z.w = relu(acc[s][3] + cv.w);
+                    const int at = base + pg * 8 + s;
+                    if (at < a.n_atoms) stv(a.l2 + (int64_t)at * HID + og * 4, z);
                     stv(T32b + tile_off(pg * 8 + s, og, HID), z);
                 }
             }
             __syncwarp();
-            // (6) layer 3: 32 -> 48, linear; columns 0..31 then 32..47 (computed by every og, written by og < 4)
-            zero_acc(acc);
-            tile_gemm<R, HID, HD>(T32b, sU3, og * 4, acc, pg);
-            {
-                const Vec4<R> cv = ldv(sc3 + og * 4);
+            // (4) last message-passing step only: the hidden state itself, h = U3^T l2 + c3 (columns 0..31, then 32..47)
+            if (write_h) {
+                zero_acc(acc);
+                tile_gemm<R, HID, HD>(T32b, sU3, og * 4, acc, pg);
+                {
+                    const Vec4<R> cv = ldv(sc3 + og * 4);
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    Vec4<R> hv; hv.x = acc[s][0] + cv.x; hv.y = acc[s][1] + cv.y; hv.z = acc[s][2] + cv.z; hv.w = acc[s][3] + cv.w;
-                    const int at = base + pg * 8 + s;
-                    if (at < a.n_atoms) stv(a.h + (int64_t)at * HD + og * 4, hv);
-                    stv(T80 + tile_off(pg * 8 + s, og, HD), hv);           // [32][48] tile for the projection
+                    for (int s = 0; s < 8; ++s) {
+                        Vec4<R> hv; hv.x = acc[s][0] + cv.x; hv.y = acc[s][1] + cv.y; hv.z = acc[s][2] + cv.z; hv.w = acc[s][3] + cv.w;
+                        const int at = base + pg * 8 + s;
+                        if (at < a.n_atoms) stv(a.h + (int64_t)at * HD + og * 4, hv);
+                    }
+                }
+                zero_acc(acc);
+                tile_gemm<R, HID, HD>(T32b, sU3, HID + (og & 3) * 4, acc, pg);
+                if (og < 4) {
+                    const Vec4<R> cv = ldv(sc3 + HID + og * 4);
+#pragma unroll
+                    for (int s = 0; s < 8; ++s) {
+                        Vec4<R> hv; hv.x = acc[s][0] + cv.x; hv.y = acc[s][1] + cv.y; hv.z = acc[s][2] + cv.z; hv.w = acc[s][3] + cv.w;
+                        const int at = base + pg * 8 + s;
+                        if (at < a.n_atoms) stv(a.h + (int64_t)at * HD + HID + og * 4, hv);
+                    }
                 }
             }
-            zero_acc(acc);
-            tile_gemm<R, HID, HD>(T32b, sU3, HID + (og & 3) * 4, acc, pg);
-            if (og < 4) {
-                const Vec4<R> cv = ldv(sc3 + HID + og * 4);
-#pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    Vec4<R> hv; hv.x = acc[s][0] + cv.x; hv.y = acc[s][1] + cv.y; hv.z = acc[s][2] + cv.z; hv.w = acc[s][3] + cv.w;
-                    const int at = base + pg * 8 + s;
-                    if (at < a.n_atoms) stv(a.h + (int64_t)at * HD + HID + og * 4, hv);
-                    stv(T80 + tile_off(pg * 8 + s, 8 + og, HD), hv);
-                }
-            }
-            __syncwarp();
         } else if (do_proj && !a.h_is_zero) {
-#pragma unroll 4
-            for (int f = lane; f < 32 * (HD / 4); f += 32) {
-                const int sl = f / (HD / 4), ch = f - sl * (HD / 4);
+#pragma unroll 2
+            for (int f = lane; f < 32 * (HID / 4); f += 32) {            // l2 of the last message-passing step
+                const int sl = f >> 3, ch = f & 7;
                 const int at = base + sl;
-                Vec4<R> hv = vzero<R>();
-                if (at < a.n_atoms) hv = ldv(a.h + (int64_t)at * HD + ch * 4);
-                stv(T80 + tile_off(sl, ch, HD), hv);
+                Vec4<R> lv = vzero<R>();
+                if (at < a.n_atoms) lv = ldv(a.l2 + (int64_t)at * HID + ch * 4);
+                stv(T32b + tile_off(sl, ch, HID), lv);
             }
             __syncwarp();
         }
@@ -211,7 +200,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {           // half 0 -> u (a_i block), half 1 -> v (a_j block, + b1)
                 zero_acc(acc);
-                if (!a.h_is_zero) tile_gemm<R, HD, 64>(T80, sAh, half * HID + og * 4, acc, pg);
+                if (!a.h_is_zero) tile_gemm<R, HID, 64>(T32b, sP, half * HID + og * 4, acc, pg);
                 const Vec4<R> aq = ldv(sAq + half * HID + og * 4);
                 R* dst = half == 0 ? a.u : a.v;
 #pragma unroll
@@ -241,10 +230,10 @@ cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, cons
     memset(&aa, 0, sizeof(aa));
     aa.n_atoms = w.n_atoms; aa.mode = mode; aa.nsplit = w.nsplit; aa.h_is_zero = h_is_zero;
     aa.atom_sys = w.atom_sys; aa.sys_off = w.sys_off; aa.npad = w.npad; aa.species = w.species;
-    aa.Spart = (const R*)w.S; aa.h = (R*)w.h;
-    if (mode & ATOM_UPDATE) { aa.W3 = prev->W3; aa.b3 = prev->b3; aa.upd = *upd; }
+    aa.Spart = (const R*)w.S; aa.h = (R*)w.h; aa.l2 = (R*)w.l2;
+    if (mode & ATOM_UPDATE) { aa.HG = prev->HG; aa.g = prev->g; aa.upd = *upd; aa.cb = (mode & ATOM_FIRST) ? upd->c1 : upd->cb1; }
     aa.rowptr = w.rowptr; aa.col = w.col; aa.pid = w.pid; aa.delta = (const R*)w.delta; aa.q = w.q;
-    if (mode & ATOM_PROJECT) { aa.Ah64 = next->Ah64; aa.Aq64 = next->Aq64; aa.Ax64 = next->Ax64; }
+    if (mode & ATOM_PROJECT) { aa.Pf = next->Pf; aa.Aq64 = next->Aq64; aa.Ax = h_is_zero ? next->Ax64 : next->Axf; }
     aa.u = (R*)w.u; aa.v = (R*)w.v; aa.q_out = q_out; aa.q_out64 = q_out64;
     const size_t smem = sizeof(R) * (ATOM_W_UPD + ATOM_W_PROJ + (size_t)NW * ATOM_TILE + NW * 64) + sizeof(int) * NW * 64;
     cudaError_t e = cudaFuncSetAttribute(atom_kernel<R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -147,6 +147,8 @@ template <> __device__ __forceinline__ void tile_gemm<float, ED, HID>(const floa
 template <> __device__ __forceinline__ void tile_gemm<float, HID, HID>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<HID, HID>(at, W, wcol, acc, pg); }
 template <> __device__ __forceinline__ void tile_gemm<float, UPD_IN, HID>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<UPD_IN, HID>(at, W, wcol, acc, pg); }
 template <> __device__ __forceinline__ void tile_gemm<float, HID, HD>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<HID, HD>(at, W, wcol, acc, pg); }
+template <> __device__ __forceinline__ void tile_gemm<float, 64, HID>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<64, HID>(at, W, wcol, acc, pg); }
+template <> __device__ __forceinline__ void tile_gemm<float, HID, 64>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<HID, 64>(at, W, wcol, acc, pg); }
 template <> __device__ __forceinline__ void tile_gemm<float, HD, 64>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<HD, 64>(at, W, wcol, acc, pg); }
 
 template <typename R> __device__ __forceinline__ void zero_acc(R (&acc)[8][4]) {
@@ -169,9 +171,15 @@ template <typename R> struct StepW {      // one message or pass MLP, first laye
     const R* b2;     // [32]
     const R* W3;     // [32][32] (message) or [32] (pass)
     const R* b3;     // [32] or [1]
+    // per-atom kernel, linear layers folded on the host (exact algebra, float64):
+    const R* Pf;     // [32][64]  U3 . Ah64        : u|v of the NEXT pair kernel straight from the update MLP's last hidden layer l2
+    const R* Axf;    // [MAX_SPECIES][64]  Ax64 + c3^T Ah64
+    const R* HG;     // [64][32]  [U3 . U1_h ; W3 . U1_M] : first update layer applied to [l2_prev | S]   (message steps only)
+    const R* g;      // [32]      U1_M^T b3               : times npad, the hoisted last-layer bias        (message steps only)
 };
 template <typename R> struct UpdW {       // shared update MLP 80 -> 32 -> 32 -> 48
     const R* U1; const R* c1; const R* U2; const R* c2; const R* U3; const R* c3;
+    const R* cb1;    // [32]  c1 + U1_h^T c3 : first-layer bias of every step after the first (h = U3^T l2 + c3 folded in)
 };
 
 template <typename R> struct DenseW {      // raw (un-split) views of one MLP step
@@ -210,6 +218,7 @@ struct Workspace {
                                                   //    planes [0, nsplit-1) of S are theirs, the SIMT kernel (near only) owns the last
     int shard_rank, shard_world;                  // this rank's slice of the large-system pair kernels (world 1 = everything)
     void* h; void* S; void* u; void* v; void* delta;   // precision-dependent (float or double)
+    void* l2;                          // [n][32] last hidden layer of the update MLP: the state carried between steps
     double* q;
 };
 
@@ -248,6 +257,8 @@ template <typename R> cudaError_t launch_epn_pair(const Workspace& w, const Step
 #define ATOM_QUPDATE 2     // q <- q + sum_j (+/-) delta               (finishes an electron-passing pass)
 #define ATOM_PROJECT 4     // u,v <- first-layer projections for the next pair kernel
 #define ATOM_OUTPUT  8     // write q to the output buffers
+#define ATOM_FIRST   16    // first message-passing step: h = 0, there is no previous l2
+#define ATOM_WRITE_H 32    // also materialise h = U3^T l2 + c3 (last message-passing step: epnn_get_hidden)
 template <typename R> cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd,
                                               const StepW<R>* next, int h_is_zero, float* q_out, double* q_out64,
                                               cudaStream_t st, int* n_launch);
