@@ -24,7 +24,8 @@ class Stats(C.Structure):
     _fields_ = [("n_systems", C.c_int64), ("n_atoms", C.c_int64), ("n_pairs_e", C.c_int64), ("n_pairs_near", C.c_int64),
                 ("n_row_groups", C.c_int64), ("n_chunks", C.c_int64), ("n_launches", C.c_int64),
                 ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_neighbor", C.c_float), ("ms_gnn_pair", C.c_float),
-                ("ms_gnn_atom", C.c_float), ("ms_epn_pair", C.c_float), ("ms_epn_atom", C.c_float), ("ms_d2h", C.c_float)]
+                ("ms_gnn_atom", C.c_float), ("ms_epn_pair", C.c_float), ("ms_epn_atom", C.c_float), ("ms_d2h", C.c_float),
+                ("n_far_dedup_rows", C.c_int64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -55,7 +55,7 @@ static thread_local std::string g_create_err;
 enum {
     B_XYZ, B_SPECIES, B_OFF, B_Q, B_NPAD, B_ATOMSYS, B_DEG, B_DEGU, B_ROWPTR, B_USTART, B_COL, B_PID, B_PI, B_PJ, B_PD,
     B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_FAR0CNT, B_FAR0OFF, B_FAR0LIST, B_FAR0W, B_REP, B_ATOMB0, B_BNAT, B_PERM, B_LARGESYS, B_GRID, B_CELLCNT, B_CELLSTART, B_CELLATOMS, B_DTMP, B_H, B_L2, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
-    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_COUNT
+    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_COUNT
 };
 
 static int fail(epnn_ctx* c, int code, const char* fmt, ...) {
@@ -487,6 +487,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     w.n_atoms = n_atoms; w.n_sys = n_sys; w.sm_count = c->sm_count;
     w.shard_rank = c->shard_rank; w.shard_world = c->shard_world;
     w.ek = EKof<R>::v;
+    w.n_species = c->n_species;
     w.work_counter = c->d_flags + 7;
     w.xyz = d_xyz; w.species = d_species; w.Qsys = d_Q;
     void* p;
@@ -619,6 +620,14 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     rg_fill_kernel<<<div_up(n_sys, 256), 256, 0, st>>>(n_sys, off_local, rgl_off, w.rg_large);
     ++*n_launch;
     CU(c, cudaGetLastError());
+    w.rgl_off = rgl_off;
+    if (w.n_rg_large > 0 && c->dedup_far && !neighbors_only) {      // species tables of the large systems (far-column de-duplication)
+        w.n_sp_tab = w.n_rg_large / 8 + 2;
+        ENS(B_SPTAB, sizeof(int) * 32 * (size_t)w.n_sp_tab, w.sp_tab, int*);
+        ENS(B_SPSTAMP, sizeof(int) * 2 * (size_t)w.n_sp_tab, w.sp_stamp, int*);
+        CU(c, launch_sp_tab_build(w, st, n_launch));
+        w.dedup_rows = stats ? (unsigned long long*)c->bufs[B_MISC].p + 1 : nullptr;
+    }
     if (cw.n_large) ENS(B_DTMP, sizeof(double) * (size_t)(w.nnz + 1), cw.Dtmp, double*);
     CU(c, launch_nbr_fill(w, cw, st, n_launch));
     CU(c, launch_far_fill(w, atom_b0, st, n_launch));
@@ -657,6 +666,8 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     for (int t = 0; t < c->T; ++t) {
         if (sharded) CU(c, cudaMemsetAsync(w.S, 0, sizeof(R) * HID * (size_t)n_atoms * w.nsplit, st));
         if (!sharded || c->shard_rank == 0) CU(c, launch_gnn_bundle<R>(w, msg[t], st, n_launch));
+        w.stamp = w.sp_tab ? t + 1 : 0;             // large systems: are this step's v rows equal species by species?
+        CU(c, launch_sp_check<R>(w, st, n_launch));
         if (w.far_tc)
             CU(c, launch_gnn_far_tc(w, c->w2split + (size_t)t * 2048, c->w2split + (size_t)t * 2048 + 1024, (const float*)msg[t].b2,
                                     w.nsplit - 1, st, n_launch));
@@ -735,7 +746,7 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
     void* p;
     if ((rc = ensure(c, B_MISC, 64, &p)) != EPNN_OK) return rc;
     d_near_count = (unsigned long long*)p;
-    CU(c, cudaMemsetAsync(d_near_count, 0, sizeof(unsigned long long), st));
+    CU(c, cudaMemsetAsync(d_near_count, 0, 2 * sizeof(unsigned long long), st));      // [0] near pairs, [1] de-duplicated rows
     tm.mark(0);
     for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
         const int64_t s0 = bounds[ci], s1 = bounds[ci + 1];
@@ -788,9 +799,10 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
     }
     CU(c, cudaStreamSynchronize(st));
     if (stats) {
-        unsigned long long nn = 0;
-        CU(c, cudaMemcpy(&nn, d_near_count, sizeof(nn), cudaMemcpyDeviceToHost));
-        stats->n_pairs_near = (int64_t)nn;
+        unsigned long long nn[2] = {0, 0};
+        CU(c, cudaMemcpy(nn, d_near_count, sizeof(nn), cudaMemcpyDeviceToHost));
+        stats->n_pairs_near = (int64_t)nn[0];
+        stats->n_far_dedup_rows = (int64_t)nn[1];
         stats->n_systems = n_sys; stats->n_atoms = off[n_sys]; stats->n_chunks = (int64_t)bounds.size() - 1;
         stats->n_launches = n_launch;
     }

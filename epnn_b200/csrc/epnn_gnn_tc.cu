@@ -34,6 +34,7 @@ struct GnnTcArgs {
     const float* Whi; const float* Wlo;        // [32 n][32 k] = hi / lo parts of W2^T, plain row-major
     const float* b2;
     float* S;
+    const int* rgl_off; const int* sp_stamp; int stamp;      // far-column de-duplication (epnn_gnn.cu); stamp == 0: off
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -157,7 +158,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gnn_far_tc_kernel(const GnnTcAr
         const int n = a1 - a0;
         int clen = (n + a.nsplit - 1) / a.nsplit;
         clen = (clen + TC_TILE - 1) / TC_TILE * TC_TILE;
-        const int jlo = min(a1, a0 + split * clen), jhi = min(a1, jlo + clen);
+        const int jlo = min(a1, a0 + split * clen);
+        int jhi = min(a1, jlo + clen);
+        if (a.stamp) {                 // the SIMT kernel sums this system's far columns species by species: nothing to do here
+            const int ti = a.rgl_off[sys] >> 3;         // (the zero sums are still written: the planes are added per atom)
+            if (a.sp_stamp[2 * ti] != a.stamp && a.sp_stamp[2 * ti + 1] == 0) jhi = jlo;
+        }
         __syncthreads();                                          // previous unit's reduction buffer / u rows are free
         if (tid < TC_ROWS * HID) {
             const int r = tid >> 5;
@@ -324,6 +330,7 @@ cudaError_t launch_gnn_far_tc(const Workspace& w, const float* Whi, const float*
     ga.rg_atom = w.rg_large; ga.nsplit = nsplit_tc; ga.n_atoms = w.n_atoms;
     ga.atom_sys = w.atom_sys; ga.sys_off = w.sys_off; ga.rowptr = w.rowptr; ga.col = w.col;
     ga.u = (const float*)w.u; ga.v = (const float*)w.v; ga.Whi = Whi; ga.Wlo = Wlo; ga.b2 = b2; ga.S = (float*)w.S;
+    ga.rgl_off = w.rgl_off; ga.sp_stamp = w.sp_stamp; ga.stamp = w.stamp;
     const int64_t total = (int64_t)w.n_rg_large * nsplit_tc;
     ga.unit_begin = (int)(total * w.shard_rank / w.shard_world); ga.unit_end = (int)(total * (w.shard_rank + 1) / w.shard_world);
     int grid = ga.unit_end - ga.unit_begin;

@@ -217,6 +217,14 @@ struct Workspace {
     int far_tc;                                   // 1: the far part of the big-system message sum runs on the tensor cores;
                                                   //    planes [0, nsplit-1) of S are theirs, the SIMT kernel (near only) owns the last
     int shard_rank, shard_world;                  // this rank's slice of the large-system pair kernels (world 1 = everything)
+    // species tables of the large systems (exact de-duplication of their far columns, epnn_gnn.cu): entry
+    // rgl_off[sys] >> 3 (a large system has >= 13 row groups, so the entries of two systems never collide)
+    const int* rgl_off;                           // [n_sys + 1] first row group of every system
+    int* sp_tab; int n_sp_tab;                    // [n_sp_tab][32]: atoms per species [16] | first atom of the species [16]
+    int* sp_stamp;                                // [n_sp_tab][2]: stamp of the last step whose v rows were NOT species-wise equal | dedup forbidden
+    int stamp;                                    // stamp of the current message-passing step (t + 1); 0 = de-duplication off
+    int n_species;                                // species of the element table in use (8 or 9)
+    unsigned long long* dedup_rows;               // device counter (statistics): rows whose far part was collapsed, summed over steps
     void* h; void* S; void* u; void* v; void* delta;   // precision-dependent (float or double)
     void* l2;                          // [n][32] last hidden layer of the update MLP: the state carried between steps
     double* q;
@@ -251,6 +259,8 @@ template <typename R> cudaError_t launch_epn_bundle(const Workspace& w, const St
 cudaError_t launch_gnn_far_tc(const Workspace& w, const float* Whi, const float* Wlo, const float* b2, int nsplit_tc,
                               cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
+cudaError_t launch_sp_tab_build(const Workspace& w, cudaStream_t st, int* n_launch);                    // once per chunk
+template <typename R> cudaError_t launch_sp_check(const Workspace& w, cudaStream_t st, int* n_launch);  // once per step (needs w.stamp)
 template <typename R> cudaError_t launch_epn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 // mode bits for the per-atom kernel
 #define ATOM_UPDATE  1     // h <- update_fn([h | W3^T S + npad*b3])   (finishes a message-passing step)

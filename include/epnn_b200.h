@@ -57,6 +57,8 @@ typedef struct epnn_stats {
     float ms_epn_pair;        /* sum over the T electron-passing pair kernels */
     float ms_epn_atom;        /* segmented charge reductions + projections of the EPN layer */
     float ms_d2h;
+    int64_t n_far_dedup_rows; /* rows of systems with more than 48 atoms whose far (e == 0) columns were collapsed to one
+                                 weighted slot per species, summed over the T message-passing steps ("dedup_far") */
 } epnn_stats;
 
 /* Build a context on CUDA device `device` and upload the model once.
@@ -79,9 +81,12 @@ const char* epnn_last_error(const epnn_ctx* ctx);
 /* Options: "precision" 32 (default, FP32 SIMT, FP64 accumulation of message sums and charges) or
  * 64 (every kernel in FP64: the verification variant); "timing" 0/1; "chunk_atoms" (internal batch size);
  * "keep_hidden" 0/1 (retain the final GNN hidden state for epnn_get_hidden);
- * "dedup_far" 1 (default) / 0: small systems collapse far columns whose v rows are bit-identical (same system, same
- * species, same hidden state -- always the case at the first message-passing step) into one weighted slot per species:
- * an exact reuse of identical messages, switched off only for ablation;
+ * "dedup_far" 1 (default) / 0: far columns whose v rows are identical (same system, same species, same hidden
+ * state -- always the case at the first message-passing step, and at every step for checkpoints whose hidden state is
+ * species-wise constant, e.g. the reference's default decay_model_weights) are collapsed into one weighted slot per
+ * species: an exact reuse of identical messages, checked on the device at every step, switched off only for
+ * ablation.  For systems with more than 48 atoms this turns the O(n^2) unmasked message sum of a step into
+ * O(n * species) whenever the check holds; otherwise the full sum runs;
  * "gnn_far_tensor" 0 (default) / 1: systems with more than 48 atoms evaluate the e == 0 ("far") part of the
  * message sum -- the O(n^2) part -- on the tcgen05 tensor cores with a 3xTF32 error-compensated split and FP32
  * accumulation in tensor memory instead of FP32 SIMT (precision 32 only; results differ from the SIMT path at
