@@ -22,8 +22,9 @@
 // (sp_check_kernel compares every row with the first atom of its species, every step) the O(n) far columns of a row
 // collapse to one weighted slot per species:
 //     sum_{j far} m(u_i, v_j) = sum_s (N_s - #{near neighbours of i with species s}) * m(u_i, v_rep(s))
-// -- O(n * species) instead of O(n^2) for the step.  That is always the case at step 0 (h = 0) and at every step for
-// checkpoints whose hidden state is species-wise constant (the reference's default decay_model_weights, SURVEY trap 6);
+// -- O(n * species) instead of O(n^2) for the step.  That is always the case at step 0 (h = 0) and after every step whose
+// update left h species-wise constant (3 of the 5 steps of the reference's default decay_model_weights, whose update MLP
+// is dead at some steps -- SURVEY trap 6);
 // otherwise the full far phase below runs.  No approximation: identical messages are evaluated once and multiplied.
 #include "epnn_internal.cuh"
 

@@ -82,8 +82,8 @@ const char* epnn_last_error(const epnn_ctx* ctx);
  * 64 (every kernel in FP64: the verification variant); "timing" 0/1; "chunk_atoms" (internal batch size);
  * "keep_hidden" 0/1 (retain the final GNN hidden state for epnn_get_hidden);
  * "dedup_far" 1 (default) / 0: far columns whose v rows are identical (same system, same species, same hidden
- * state -- always the case at the first message-passing step, and at every step for checkpoints whose hidden state is
- * species-wise constant, e.g. the reference's default decay_model_weights) are collapsed into one weighted slot per
+ * state -- always the case at the first message-passing step, and after every step that leaves the hidden state
+ * species-wise constant: 3 of the 5 steps of the reference's default decay_model_weights) are collapsed into one weighted slot per
  * species: an exact reuse of identical messages, checked on the device at every step, switched off only for
  * ablation.  For systems with more than 48 atoms this turns the O(n^2) unmasked message sum of a step into
  * O(n * species) whenever the check holds; otherwise the full sum runs;
