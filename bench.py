@@ -9,6 +9,11 @@ electron-passing passes -> charges) over one batch of synthetic input:
                      Q = 0, pad N = 29, decay_model_weights.  Molecules are independent, so N GPUs hold N
                      disjoint shards of the same stream (molecule k depends only on (seed, k)) and there is
                      no data-path collective: "scaling": "weak".
+  workload "qm9_test" / "ssi" (BASELINE.json configs[0]/[1]): the reference's own data -- the 1338 QM9 molecules of
+                     data/mixed with model_weights, the 2979 SSI dimers (net charge 0, +-1, +-2) with model2_weights --
+                     from the packed fixture tests/golden/mixed.npz, pad N = 41 (the pad of the reference's mixed set).
+                     Small batches (24 k / 66 k atoms): these lines are latency-bound and secondary; parity on the
+                     same systems is tests/test_gpu_parity.py.  Every rank runs the whole set (replicas only).
   workload "protein" (BASELINE.json configs[2]/[4])      : one protein-like system of --atoms atoms (Galectin-3C
                      tiled), exact all-pairs GNN.  With --gpus N the SAME system is sharded over the N ranks
                      (epnn_set_shard: pair kernels split by ranges, one NCCL all-reduce per step / pass): "scaling":
@@ -51,11 +56,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="qm9", choices=["qm9", "protein"])
+    ap.add_argument("--workload", default="qm9", choices=["qm9", "protein", "qm9_test", "ssi"])
     ap.add_argument("--molecules", type=int, default=1_000_000, help="QM9-shaped molecules per GPU per step")
     ap.add_argument("--atoms", type=int, default=2220, help="atoms of the protein-like system (workload protein)")
     ap.add_argument("--npad", type=int, default=29, help="pad size N of the reference's dense model (qm9 workload)")
-    ap.add_argument("--checkpoint", default="decay_model_weights")
+    ap.add_argument("--checkpoint", default=None, help="default: decay_model_weights (qm9, protein), model_weights (qm9_test), model2_weights (ssi)")
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
     ap.add_argument("--chunk-atoms", type=int, default=0, help="override the library's internal batch size")
     ap.add_argument("--ref-molecules", type=int, default=2048, help="molecules per step of the CPU reference arm")
@@ -65,7 +70,12 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.checkpoint is None:
+        args.checkpoint = {"qm9_test": "model_weights", "ssi": "model2_weights"}.get(args.workload, "decay_model_weights")
+    if args.workload in ("qm9_test", "ssi") and args.npad == 29:
+        args.npad = 41
+    return args
 
 
 # ------------------------------------------------------------------------------------------------ workloads
@@ -76,12 +86,39 @@ def make_workload(args, w, rank):
         npad = np.full(args.molecules, args.npad, np.int32)
         desc = {"workload": f"synthetic QM9-shaped molecules (<=29 atoms), {args.molecules} per GPU per step, pad N={args.npad}",
                 "molecules_per_gpu": args.molecules}
+    elif args.workload in ("qm9_test", "ssi"):
+        offs, xyz, sp, Q, n_sel = real_set(args.workload, w.n_x, limit=getattr(args, "limit_systems", 0))
+        npad = np.full(n_sel, args.npad, np.int32)
+        desc = {"workload": f"{'QM9 molecules' if args.workload == 'qm9_test' else 'SSI dimers'} of the reference's data/mixed "
+                            f"({n_sel} systems, {int(offs[-1])} atoms per step), pad N={args.npad}", "systems_per_gpu": n_sel}
     else:
         offs, xyz, sp, Q = synth.protein_like(args.atoms, w.n_x, seed=1)      # the SAME system on every rank (sharded)
         npad = np.array([args.atoms], np.int32)
         desc = {"workload": f"protein-like single system, {args.atoms} atoms (Galectin-3C tiled), pad N=n, exact all-pairs GNN",
                 "atoms": args.atoms}
     return offs, np.ascontiguousarray(xyz, np.float32), sp, Q, npad, desc
+
+
+def data_kind(args):
+    return "synthetic" if args.workload in ("qm9", "protein") else "reference data/mixed (tests/golden/mixed.npz)"
+
+
+def real_set(which, n_x, limit=0):
+    """Packed arrays of the reference's own QM9 molecules / SSI dimers (tests/golden/mixed.npz, made by
+    tests/golden/make_fixtures.py from data/mixed.tar.gz), in fixture order."""
+    from epnn_b200 import synth
+    d = np.load(os.path.join(GOLDEN, "mixed.npz"))
+    names = [str(x) for x in d["names"]]
+    prefix = "dsgdb9nsd_" if which == "qm9_test" else "SSI-"
+    sel = [i for i, nm in enumerate(names) if nm.startswith(prefix)]
+    if limit:
+        sel = sel[:limit]
+    o = d["offsets"]
+    idx = np.concatenate([np.arange(o[i], o[i + 1]) for i in sel])
+    sizes = np.array([o[i + 1] - o[i] for i in sel])
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    return (offs, np.ascontiguousarray(d["xyz"][idx], np.float32), synth.species_from_Z(d["Z"][idx], n_x).astype(np.int32),
+            np.ascontiguousarray(d["Q"][sel], np.float32), len(sel))
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -175,6 +212,9 @@ def run_reference(args):
     if args.workload == "qm9":
         sub.molecules = args.ref_molecules
         sample = f"{args.ref_molecules} molecules of the same synthetic stream per step (of {args.molecules} per GPU)"
+    elif args.workload in ("qm9_test", "ssi"):
+        sub.limit_systems = min(args.ref_molecules, 512)
+        sample = f"the first {sub.limit_systems} systems of the set per step"
     else:
         sub.atoms = min(args.atoms, 2220)
         sample = f"one {sub.atoms}-atom system per step"
@@ -211,7 +251,7 @@ def run_reference(args):
     _, _, _, _, _, full_desc = make_workload_desc_only(args)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": full_desc,
+            "vs_baseline": None, "dtype": "f32", "data": data_kind(args), "config": full_desc,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
                              "what": "numpy float32 restatement of the reference formulation (oracle.forward_literal: "
                                      "get_init_edges + dense padded pair tensors + 3 Dense layers per MLP); TensorFlow is "
@@ -225,6 +265,8 @@ def make_workload_desc_only(args):
     if args.workload == "qm9":
         desc = {"workload": f"synthetic QM9-shaped molecules (<=29 atoms), {args.molecules} per GPU per step, pad N={args.npad}",
                 "molecules_per_gpu": args.molecules}
+    elif args.workload in ("qm9_test", "ssi"):
+        desc = {"workload": f"{'QM9 molecules' if args.workload == 'qm9_test' else 'SSI dimers'} of the reference's data/mixed, pad N={args.npad}"}
     else:
         desc = {"workload": f"protein-like single system, {args.atoms} atoms (Galectin-3C tiled), pad N=n, exact all-pairs GNN",
                 "atoms_per_gpu": args.atoms}
@@ -469,7 +511,7 @@ def run_b200(args):
         line = {"metric": METRIC, "value": tot_atoms * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
                 "scaling": "strong" if sharded_system else "weak", "vs_baseline": None,
-                "dtype": "f32" if args.precision == 32 else "f64", "data": "synthetic", "config": desc, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "dtype": "f32" if args.precision == 32 else "f64", "data": data_kind(args), "config": desc, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
                 "cpu_baseline": cpu_base, "phases_ms_per_step": phases,
                 "checks": {"max_abs_sum_q_minus_Q": max_dQ}}
         print(json.dumps(line), flush=True)
