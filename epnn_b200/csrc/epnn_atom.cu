@@ -33,6 +33,10 @@ template <typename R> struct AtomArgs {
 #ifndef ATOM_NW
 #define ATOM_NW 12
 #endif
+#ifndef ATOM_PREFETCH
+#define ATOM_PREFETCH 1      // measured: per-atom kernels -5 % (tools/gpu_ab_atom.sh); keeping 4 CSR entries in flight or 14 warps: no change
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #define ATOM_W_UPD (64 * HID + 2 * HID + HID * HID + HID + HID * HD + HD)                    // 4752
 #define ATOM_W_PROJ (HID * 64 + 64 + MAX_SPECIES * 64)                                      // 3136
 #define ATOM_TILE (32 * 64 + 32 * HID)                                                      // 3072 per warp
@@ -83,6 +87,16 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
         const int base = tile * 32;
         const int me = base + lane;
         const bool me_ok = me < a.n_atoms;
+#if ATOM_PREFETCH
+        {   // this warp's NEXT tile -> L2 while the current one computes: its l2 rows (4 KB, one 128-byte line per lane) and,
+            // for the update, the first partial-sum plane of S (the only plane small systems have)
+            const int64_t nb = (int64_t)(tile + gridDim.x * NW) * 32;
+            if (nb + lane < a.n_atoms) {
+                if ((do_upd && !first) || (do_proj && !do_upd && !a.h_is_zero)) prefetch_l2(a.l2 + (nb + lane) * HID);
+                if (do_upd) prefetch_l2(a.Spart + (nb + lane) * HID);
+            }
+        }
+#endif
         // ---------------- per-slot scalars (lane = slot)
         {
             int sp = 0, ns = 1; R npf = R(0);
