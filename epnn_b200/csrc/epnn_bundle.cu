@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
             __syncwarp();
             R ce[8][4];
             zero_acc(ce);
-            tile_gemm<R, EK, HID>(eb, sC, og * 4, ce, pg);
+            tile_gemm_unr<R, EK, HID, EPN ? 8 : 2>(eb, sC, og * 4, ce, pg);
             __syncwarp();                                              // e tile consumed; eb becomes the z tile
 
             R part[8];
@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                 }
                 __syncwarp();
                 zero_acc(acc);
-                tile_gemm<R, HID, HID>(zt, sW2, og * 4, acc, pg);
+                tile_gemm_unr<R, HID, HID, EPN ? 8 : 2>(zt, sW2, og * 4, acc, pg);
                 __syncwarp();
                 if (EPN) {
 #pragma unroll

@@ -114,14 +114,14 @@ __device__ __forceinline__ void fma2(f32x2_t& d, f32x2_t wpair, float a) {
     const f32x2_t aa = pack2(a, a);
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(wpair), "l"(aa));
 }
-template <int K, int WLD>
+template <int K, int WLD, int UNR = 2>
 __device__ __forceinline__ void tile_gemm_f32x2(const float* __restrict__ at, const float* __restrict__ W, int wcol,
                                                 float (&acc)[8][4], int pg) {
     const float* arow = at + pg * 8 * K;
     f32x2_t c[8][2];
 #pragma unroll
     for (int s = 0; s < 8; ++s) { c[s][0] = pack2(acc[s][0], acc[s][1]); c[s][1] = pack2(acc[s][2], acc[s][3]); }
-#pragma unroll 2
+#pragma unroll UNR
     for (int kc = 0; kc < K / 4; ++kc) {
         f32x2_t w[4][2];
 #pragma unroll
@@ -150,6 +150,15 @@ template <> __device__ __forceinline__ void tile_gemm<float, HID, HD>(const floa
 template <> __device__ __forceinline__ void tile_gemm<float, 64, HID>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<64, HID>(at, W, wcol, acc, pg); }
 template <> __device__ __forceinline__ void tile_gemm<float, HID, 64>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<HID, 64>(at, W, wcol, acc, pg); }
 template <> __device__ __forceinline__ void tile_gemm<float, HD, 64>(const float* __restrict__ at, const float* __restrict__ W, int wcol, float (&acc)[8][4], int pg) { tile_gemm_f32x2<HD, 64>(at, W, wcol, acc, pg); }
+
+// Same product with an explicit unroll factor of the k loop (FP32 only; the FP64 verification path keeps the generic core).
+// Measured (tools/gpu_ab_unroll.sh): the EPN bundle kernel gains 8 % from a fully unrolled loop, the (larger) GNN bundle
+// kernel and the per-atom kernel lose 6..25 % -- hence a per-call-site choice, default 2.
+template <typename R, int K, int WLD, int UNR>
+__device__ __forceinline__ void tile_gemm_unr(const R* __restrict__ at, const R* __restrict__ W, int wcol, R (&acc)[8][4], int pg) {
+    if constexpr (sizeof(R) == 4) tile_gemm_f32x2<K, WLD, UNR>(at, W, wcol, acc, pg);
+    else tile_gemm<R, K, WLD>(at, W, wcol, acc, pg);
+}
 
 template <typename R> __device__ __forceinline__ void zero_acc(R (&acc)[8][4]) {
 #pragma unroll
