@@ -33,6 +33,9 @@ template <typename R> struct AtomArgs {
 #ifndef ATOM_NW
 #define ATOM_NW 12
 #endif
+#ifndef ATOM_UNR
+#define ATOM_UNR 2
+#endif
 #ifndef ATOM_PREFETCH
 #define ATOM_PREFETCH 1      // measured: per-atom kernels -5 % (tools/gpu_ab_atom.sh); keeping 4 CSR entries in flight or 14 warps: no change
 #endif
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
             __syncwarp();
             // (2) first layer with W3 / U3 folded in: relu([U3 U1_h ; W3 U1_M]^T [l2_prev | S] + cb + npad * g)
             zero_acc(acc);
-            tile_gemm<R, 64, HID>(T64, sHG, og * 4, acc, pg);
+            tile_gemm_unr<R, 64, HID, ATOM_UNR>(T64, sHG, og * 4, acc, pg);
             {
                 const Vec4<R> cv = ldv(scb + og * 4);
                 const Vec4<R> gv = ldv(sg + og * 4);
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
             __syncwarp();
             // (3) second layer: l2 = relu(U2^T l1 + c2)   (T64 is dead now; the l2 tile reuses its head)
             zero_acc(acc);
-            tile_gemm<R, HID, HID>(T32, sU2, og * 4, acc, pg);
+            tile_gemm_unr<R, HID, HID, ATOM_UNR>(T32, sU2, og * 4, acc, pg);
             {
                 const Vec4<R> cv = ldv(sc2 + og * 4);
 #pragma unroll
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
 #pragma unroll
             for (int half = 0; half < 2; ++half) {           // half 0 -> u (a_i block), half 1 -> v (a_j block, + b1)
                 zero_acc(acc);
-                if (!a.h_is_zero) tile_gemm<R, HID, 64>(T32b, sP, half * HID + og * 4, acc, pg);
+                if (!a.h_is_zero) tile_gemm_unr<R, HID, 64, ATOM_UNR>(T32b, sP, half * HID + og * 4, acc, pg);
                 const Vec4<R> aq = ldv(sAq + half * HID + og * 4);
                 R* dst = half == 0 ? a.u : a.v;
 #pragma unroll

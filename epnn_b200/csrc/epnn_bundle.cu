@@ -29,6 +29,12 @@
 #ifndef GNN_NW
 #define GNN_NW 8
 #endif
+#ifndef GNN_UNR
+#define GNN_UNR 2            // k-loop unroll of the GNN variant's tile products (EPN: fully unrolled, see tile_gemm_unr)
+#endif
+#ifndef EPN_DIR_UNROLL
+#define EPN_DIR_UNROLL 1     // 2: also unroll the EPN variant's direction loop
+#endif
 
 template <typename R> struct BundleArgs {
     int n_bundles; const int2* bundle; int* work_counter;      // dynamic bundle queue (zeroed before the launch)
@@ -223,7 +229,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
             __syncwarp();
             R ce[8][4];
             zero_acc(ce);
-            tile_gemm_unr<R, EK, HID, EPN ? 8 : 2>(eb, sC, og * 4, ce, pg);
+            tile_gemm_unr<R, EK, HID, EPN ? 8 : GNN_UNR>(eb, sC, og * 4, ce, pg);
             __syncwarp();                                              // e tile consumed; eb becomes the z tile
 
             R part[8];
@@ -235,7 +241,8 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                 code[0] = c0.x; code[1] = c0.y; code[2] = c0.z; code[3] = c0.w;
                 code[4] = c1.x; code[5] = c1.y; code[6] = c1.z; code[7] = c1.w;
             }
-#pragma unroll 1
+            constexpr int DIR_UNR = EPN ? EPN_DIR_UNROLL : 1;
+#pragma unroll DIR_UNR
             for (int dir = 0; dir < 2; ++dir) {
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                 }
                 __syncwarp();
                 zero_acc(acc);
-                tile_gemm_unr<R, HID, HID, EPN ? 8 : 2>(zt, sW2, og * 4, acc, pg);
+                tile_gemm_unr<R, HID, HID, EPN ? 8 : GNN_UNR>(zt, sW2, og * 4, acc, pg);
                 __syncwarp();
                 if (EPN) {
 #pragma unroll
@@ -377,7 +384,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
                 }
                 __syncwarp();
                 zero_acc(acc);
-                tile_gemm<R, HID, HID>(zt, sW2, og * 4, acc, pg);
+                tile_gemm_unr<R, HID, HID, GNN_UNR>(zt, sW2, og * 4, acc, pg);
                 Vec4<R> val[8];
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
