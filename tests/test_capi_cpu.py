@@ -67,3 +67,29 @@ def test_descriptor_basis_is_orthonormal_and_complete_to_1e9():
     Cc = (np.cos(np.pi * D / 3.0) + 1.0) / 2.0
     E = Cc[:, None] * np.exp(-2.0 * (D[:, None] - mu[None]) ** 2)
     assert np.abs(E - (E @ B) @ B.T).max() < 1e-9
+
+
+def test_stats_struct_matches_the_header():
+    """The ctypes mirror of epnn_stats must list the header's fields in the same order with the same C types."""
+    text = open(os.path.join(ROOT, "include", "epnn_b200.h")).read()
+    body = re.search(r"typedef struct epnn_stats \{(.*?)\} epnn_stats;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(int64_t|float)\s+([a-z0-9_]+)\s*;", body)
+    ctype = {"int64_t": C.c_int64, "float": C.c_float}
+    assert [(n, ctype[t]) for t, n in fields] == list(_capi.Stats._fields_)
+    assert C.sizeof(_capi.Stats) == 8 * sum(t == "int64_t" for t, _ in fields) + 4 * sum(t == "float" for t, _ in fields)
+
+
+def test_bench_real_data_workloads_are_the_reference_sets():
+    """bench.py --workload qm9_test / ssi: the 1338 QM9 molecules / 2979 SSI dimers of data/mixed, packed consistently."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    for which, n_x, n_sys, n_atoms in (("qm9_test", 10, 1338, 24033), ("ssi", 9, 2979, 65904)):
+        offs, xyz, sp, Q, n = bench.real_set(which, n_x)
+        assert (n, int(offs[-1])) == (n_sys, n_atoms)
+        assert xyz.shape == (n_atoms, 3) and sp.shape == (n_atoms,) and Q.shape == (n_sys,)
+        assert np.diff(offs).min() >= 3 and np.diff(offs).max() <= 41 and sp.min() >= 0 and sp.max() < n_x - 1
+    offs, _, _, Q, n = bench.real_set("ssi", 9, limit=16)
+    assert n == 16 and len(offs) == 17
+    assert set(np.unique(bench.real_set("ssi", 9)[3]).tolist()) == {-2.0, -1.0, 0.0, 1.0, 2.0}
