@@ -32,6 +32,7 @@ struct epnn_ctx {
     int precision = 32, timing = 0, keep_hidden = 0;
     int far_tensor = 0;          // option "gnn_far_tensor"
     int dedup_far = 1;           // option "dedup_far": collapse species-equivalent far columns (exact)
+    int pair_tensor = 0;         // option "pair_tensor": EPN bundle kernel on mma.sync 3xTF32 (precision 32 only)
     float* w2split = nullptr;    // [T][2][32][32]: hi / lo parts of W2^T of every message MLP (tensor-core far kernel)
     int shard_rank = 0, shard_world = 1;
     epnn_allreduce_fn allreduce = nullptr;
@@ -404,6 +405,7 @@ extern "C" int epnn_set_option(epnn_ctx* c, const char* key, double value) {
     else if (k == "keep_hidden") c->keep_hidden = value != 0;
     else if (k == "gnn_far_tensor") c->far_tensor = value != 0;
     else if (k == "dedup_far") c->dedup_far = value != 0;
+    else if (k == "pair_tensor") c->pair_tensor = value != 0;
     else if (k == "chunk_atoms") {
         if (value < 64) return fail(c, EPNN_E_INVALID, "chunk_atoms must be >= 64");
         c->chunk_atoms = (int64_t)value;
@@ -488,6 +490,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     w.shard_rank = c->shard_rank; w.shard_world = c->shard_world;
     w.ek = EKof<R>::v;
     w.n_species = c->n_species;
+    w.pair_tensor = c->pair_tensor && sizeof(R) == 4;
     w.work_counter = c->d_flags + 7;
     w.xyz = d_xyz; w.species = d_species; w.Qsys = d_Q;
     void* p;

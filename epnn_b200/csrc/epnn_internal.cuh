@@ -233,6 +233,7 @@ struct Workspace {
     int* sp_stamp;                                // [n_sp_tab][2]: stamp of the last step whose v rows were NOT species-wise equal | dedup forbidden
     int stamp;                                    // stamp of the current message-passing step (t + 1); 0 = de-duplication off
     int n_species;                                // species of the element table in use (8 or 9)
+    int pair_tensor;                              // 1: electron-passing bundle kernel on the warp-level tensor path (3xTF32, FP32 only)
     unsigned long long* dedup_rows;               // device counter (statistics): rows whose far part was collapsed, summed over steps
     void* h; void* S; void* u; void* v; void* delta;   // precision-dependent (float or double)
     void* l2;                          // [n][32] last hidden layer of the update MLP: the state carried between steps
@@ -265,6 +266,7 @@ cudaError_t launch_far0_count(const Workspace& w, int* cnt, cudaStream_t st, int
 cudaError_t launch_far0_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_gnn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_epn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
+cudaError_t launch_epn_bundle_mma(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* n_launch);   // option pair_tensor
 cudaError_t launch_gnn_far_tc(const Workspace& w, const float* Whi, const float* Wlo, const float* b2, int nsplit_tc,
                               cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);

@@ -90,7 +90,10 @@ const char* epnn_last_error(const epnn_ctx* ctx);
  * "gnn_far_tensor" 0 (default) / 1: systems with more than 48 atoms evaluate the e == 0 ("far") part of the
  * message sum -- the O(n^2) part -- on the tcgen05 tensor cores with a 3xTF32 error-compensated split and FP32
  * accumulation in tensor memory instead of FP32 SIMT (precision 32 only; results differ from the SIMT path at
- * the level of FP32 round-off, about 1e-6 relative in the hidden state). */
+ * the level of FP32 round-off, about 1e-6 relative in the hidden state);
+ * "pair_tensor" 0 (default) / 1: systems with at most 48 atoms evaluate the electron-passing pair MLP on the warp-level
+ * tensor path (mma.sync m16n8k8 TF32 inputs, 3xTF32 split, FP32 accumulation, operands chained through registers)
+ * instead of FP32 SIMT (precision 32 only; per-pair transfers differ from the SIMT path by about 1e-6 relative). */
 int epnn_set_option(epnn_ctx* ctx, const char* key, double value);
 
 /* Charge inference for a packed batch of systems, host buffers.
