@@ -68,6 +68,8 @@ def parse_args():
                     help="big systems: far part of the message sum on tcgen05 tensor cores (3xTF32) instead of FP32 SIMT")
     ap.add_argument("--pair-tensor", type=int, default=0, choices=[0, 1],
                     help="small systems: electron-passing pair MLP on mma.sync 3xTF32 instead of FP32 SIMT (opt-in)")
+    ap.add_argument("--pair-const", type=int, default=0, choices=[0, 1],
+                    help="EXPERIMENTAL (unvalidated): pair-per-thread FP32 bundle kernels with weights as uniform operands")
     ap.add_argument("--dedup-far", type=int, default=1, choices=[0, 1], help="collapse species-equivalent far columns (exact; 0 = ablation)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -331,6 +333,8 @@ def run_b200(args):
         eng.set_option("dedup_far", 0)
     if args.pair_tensor:
         eng.set_option("pair_tensor", 1)
+    if args.pair_const:
+        eng.set_option("pair_const", 1)
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
     sharded_system = args.workload == "protein" and world > 1
     if sharded_system:                       # one big system: pair kernels split over the ranks, all-reduce per step / pass
@@ -511,7 +515,7 @@ def run_b200(args):
         desc.update({"checkpoint": args.checkpoint, "parallelism": par,
                      "l2": "inputs larger than L2 (no flush needed)" if n_atoms * 16 > 126e6 else "inputs smaller than L2",
                      "atoms_per_gpu_per_step": n_atoms, "T": w.T, "precision": args.precision,
-                     "gnn_far_tensor": args.gnn_far_tensor, "dedup_far": args.dedup_far, "pair_tensor": args.pair_tensor})
+                     "gnn_far_tensor": args.gnn_far_tensor, "dedup_far": args.dedup_far, "pair_tensor": args.pair_tensor, "pair_const": args.pair_const})
         line = {"metric": METRIC, "value": tot_atoms * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
                 "scaling": "strong" if sharded_system else "weak", "vs_baseline": None,

@@ -33,6 +33,8 @@ struct epnn_ctx {
     int far_tensor = 0;          // option "gnn_far_tensor"
     int dedup_far = 1;           // option "dedup_far": collapse species-equivalent far columns (exact)
     int pair_tensor = 0;         // option "pair_tensor": EPN bundle kernel on mma.sync 3xTF32 (precision 32 only)
+    int pair_const = 0;          // option "pair_const": EXPERIMENTAL pair-per-thread bundle kernels (precision 32 only)
+    std::vector<float> wf_host;  // host mirror of wf (pair_const passes a step's weights as kernel parameters)
     float* w2split = nullptr;    // [T][2][32][32]: hi / lo parts of W2^T of every message MLP (tensor-core far kernel)
     int shard_rank = 0, shard_world = 1;
     epnn_allreduce_fn allreduce = nullptr;
@@ -375,6 +377,7 @@ extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_
     CUC(cudaMalloc(&c->wf, po.total * sizeof(float)));
     CUC(cudaMalloc(&c->wd, po.total * sizeof(double)));
     CUC(cudaMemcpy(c->wf, Pf.data(), po.total * sizeof(float), cudaMemcpyHostToDevice));
+    c->wf_host = Pf;
     CUC(cudaMemcpy(c->wd, P.data(), po.total * sizeof(double), cudaMemcpyHostToDevice));
 #undef CUC
     *out = c;
@@ -406,6 +409,7 @@ extern "C" int epnn_set_option(epnn_ctx* c, const char* key, double value) {
     else if (k == "gnn_far_tensor") c->far_tensor = value != 0;
     else if (k == "dedup_far") c->dedup_far = value != 0;
     else if (k == "pair_tensor") c->pair_tensor = value != 0;
+    else if (k == "pair_const") c->pair_const = value != 0;
     else if (k == "chunk_atoms") {
         if (value < 64) return fail(c, EPNN_E_INVALID, "chunk_atoms must be >= 64");
         c->chunk_atoms = (int64_t)value;
@@ -491,6 +495,8 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     w.ek = EKof<R>::v;
     w.n_species = c->n_species;
     w.pair_tensor = c->pair_tensor && sizeof(R) == 4;
+    w.pair_const = c->pair_const && sizeof(R) == 4;
+    w.wf_host = c->wf_host.data(); w.wf_dev = c->wf;
     w.work_counter = c->d_flags + 7;
     w.xyz = d_xyz; w.species = d_species; w.Qsys = d_Q;
     void* p;

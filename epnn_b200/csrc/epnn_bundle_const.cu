@@ -1,0 +1,260 @@
+// EXPERIMENTAL FP32 variant of both bundle kernels (option "pair_const" = 1, precision 32 only, default OFF).
+// Written at the end of round 1 after the GPU budget was spent: it compiles for sm_100a, its inner loops are those of the
+// measured prototype tools/proto_pair_const.cu (9.9 G pairs/s, 73 % of the FFMA peak, 1.9e-7 relative to float64), but the
+// kernel as a whole has NOT run on a GPU yet -- its tests (tests/test_gpu_pair_const.py) are gated behind
+// EPNN_TEST_EXPERIMENTAL=1 until it has.
+//
+// Same arithmetic and the same per-bundle flow as bundle_kernel<float, NW, EPN> (epnn_bundle.cu; reference
+// charge_gn.py:62-70 and :101-116), with a different mapping of the work onto the warp:
+//   * ONE THREAD OWNS ONE PAIR SLOT of a 32-slot tile and keeps the slot's 32 first-layer pre-activations and its 32
+//     second-layer accumulators in registers;
+//   * every lane needs the same weight at the same time, so the weights are a __grid_constant__ kernel parameter
+//     (6.4 KB, constant bank 0): ptxas loads them into uniform registers (LDCU.128) and emits
+//     FFMA2 R, R.F32, UR.F32x2, R.F32x2 -- the weight pair is the uniform operand, the activation the broadcast scalar.
+//     No shared-memory operand traffic (the bound of tile_gemm), no z stage, no shuffles in the
+//     products;
+//   * electron passing: the w3 dot product is in-thread, delta is written by the slot's own lane;
+//   * message passing: the 32 message columns of a slot go through a 32 x 33 shared-memory transpose, then lane c adds
+//     column c into the bundle's S rows slot by slot, in slot order (runs of equal targets are summed in a register
+//     first) -- fixed order, no atomics, bitwise reproducible; scatter_sorted / perm_j are not needed here.
+// Shared memory per warp: the bundle's u | v rows (row stride 68 floats, + one row holding b1 for the pad pseudo-atom),
+// and for the GNN variant the S accumulators, the transpose tile and the pad weights.
+#include "epnn_internal.cuh"
+
+#define CONST_NW 8
+#define CUVS 68                         // row stride of the staged u | v rows (64 + 4: rows start in different bank groups)
+#define PAD_ROW BUNDLE_ATOMS            // extra row: v = b1 (a_j = 0, e = 0), the pad pseudo-atom of the GNN's far tiles
+
+struct PairW { float Cw[EDR * HID]; float W2[HID * HID]; float b2[HID]; float x32[HID]; };      // x32 = b1 (GNN) / w3 (EPN)
+
+struct ConstArgs {
+    int n_bundles; const int2* bundle; int* work_counter;
+    const int* ustart; const int* pair_i; const int* pair_j; const unsigned char* near; const float* e;
+    const int* far_off; const unsigned short* far_list;
+    const int* far0_off; const unsigned short* far0_list; const unsigned char* far0_w; const int* rep; int dedup;
+    const int* atom_sys; const int* sys_off; const int* npad;
+    const float* u; const float* v;
+    float* S; float* delta;
+};
+
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t cpack2(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void cunpack2(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void cfma2(f2_t& d, f2_t wpair, float a) {
+    const f2_t aa = cpack2(a, a);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(wpair), "l"(aa));
+}
+
+// acc[c] = b2[c] + sum_k relu(ce[k] + urow[k] + vrow[k]) * W2[k][c]   (ce == nullptr-like: pass zeros for far slots)
+template <bool WITH_CE>
+__device__ __forceinline__ void second_layer(const PairW& W, const float (&ce)[HID], const float* urow, const float* vrow, f2_t (&acc2)[HID / 2]) {
+#pragma unroll
+    for (int o = 0; o < HID / 2; ++o) acc2[o] = cpack2(W.b2[2 * o], W.b2[2 * o + 1]);
+#pragma unroll
+    for (int k4 = 0; k4 < HID / 4; ++k4) {
+        const float4 u4 = *reinterpret_cast<const float4*>(urow + 4 * k4);
+        const float4 v4 = *reinterpret_cast<const float4*>(vrow + 4 * k4);
+        float z[4];
+        if (WITH_CE) {
+            z[0] = fmaxf((ce[4 * k4] + u4.x) + v4.x, 0.f); z[1] = fmaxf((ce[4 * k4 + 1] + u4.y) + v4.y, 0.f);
+            z[2] = fmaxf((ce[4 * k4 + 2] + u4.z) + v4.z, 0.f); z[3] = fmaxf((ce[4 * k4 + 3] + u4.w) + v4.w, 0.f);
+        } else {
+            z[0] = fmaxf(u4.x + v4.x, 0.f); z[1] = fmaxf(u4.y + v4.y, 0.f); z[2] = fmaxf(u4.z + v4.z, 0.f); z[3] = fmaxf(u4.w + v4.w, 0.f);
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+            for (int o = 0; o < HID / 2; ++o) cfma2(acc2[o], *reinterpret_cast<const f2_t*>(&W.W2[(4 * k4 + kk) * HID + 2 * o]), z[kk]);
+    }
+}
+
+// Adds  wgt * relu(acc)  of every slot into S[tgt] (tgt < 0: slot unused).  Lane = slot on entry; lane = column while adding.
+__device__ __forceinline__ void add_messages(const f2_t (&acc2)[HID / 2], float wgt, int tgt, float* __restrict__ Mt, float* __restrict__ S, int lane) {
+#pragma unroll
+    for (int o = 0; o < HID / 2; ++o) {
+        float x, y;
+        cunpack2(acc2[o], x, y);
+        Mt[lane * 33 + 2 * o] = fmaxf(x, 0.f) * wgt;               // bank (lane + column) mod 32: conflict-free
+        Mt[lane * 33 + 2 * o + 1] = fmaxf(y, 0.f) * wgt;
+    }
+    __syncwarp();
+    int cur = -1;
+    float run = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < 32; ++s) {                                  // warp-uniform control flow: every lane sees the same targets
+        const int t = __shfl_sync(0xffffffffu, tgt, s);
+        if (t != cur) {
+            if (cur >= 0) S[cur * HID + lane] += run;
+            run = 0.f; cur = t;
+        }
+        if (t >= 0) run += Mt[s * 33 + lane];
+    }
+    if (cur >= 0) S[cur * HID + lane] += run;
+    __syncwarp();
+}
+
+template <bool EPN> struct ConstSmem {
+    static constexpr int PW = (BUNDLE_ATOMS + 1) * CUVS + (EPN ? 0 : BUNDLE_ATOMS * HID + 32 * 33 + BUNDLE_ATOMS);   // floats per warp
+    static size_t bytes() { return sizeof(float) * (size_t)CONST_NW * PW; }
+};
+
+template <bool EPN>
+__global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kernel(const __grid_constant__ PairW W, const ConstArgs a) {
+    extern __shared__ __align__(16) float csm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* uv = csm + warp * ConstSmem<EPN>::PW;                   // [BUNDLE_ATOMS + 1][CUVS]
+    float* S = uv + (BUNDLE_ATOMS + 1) * CUVS;                     // [BUNDLE_ATOMS][32]   (GNN)
+    float* Mt = S + BUNDLE_ATOMS * HID;                            // [32][33]             (GNN)
+    float* padw = Mt + 32 * 33;                                    // [BUNDLE_ATOMS]       (GNN)
+    if (!EPN) uv[PAD_ROW * CUVS + HID + lane] = W.x32[lane];       // v of the pad pseudo-atom = b1 (written once per warp)
+
+    auto grab = [&]() {
+        int x = 0;
+        if (lane == 0) x = atomicAdd(a.work_counter, 1);
+        return __shfl_sync(0xffffffffu, x, 0);
+    };
+    for (int b = grab(); b < a.n_bundles; b = grab()) {
+        const int2 bd = a.bundle[b];
+        const int atom0 = bd.x, nat = bd.y;
+        const int p0 = a.ustart[atom0], p1 = a.ustart[atom0 + nat];
+        __syncwarp();
+        for (int f = lane; f < nat * 16; f += 32) {                // stage u | v (coalesced 16-byte loads)
+            const int row = f >> 4, c4 = f & 15;
+            const float* src = (c4 < 8 ? a.u : a.v) + (int64_t)(atom0 + row) * HID + (c4 & 7) * 4;
+            *reinterpret_cast<float4*>(uv + row * CUVS + c4 * 4) = *reinterpret_cast<const float4*>(src);
+        }
+        if (!EPN) {
+            for (int f = lane; f < nat * HID; f += 32) S[f] = 0.f;
+            for (int r = lane; r < nat; r += 32) {
+                const int sys = a.atom_sys[atom0 + r];
+                padw[r] = (float)(a.npad[sys] - (a.sys_off[sys + 1] - a.sys_off[sys]));
+            }
+        }
+        __syncwarp();
+
+        // ---------------------------------------------------------------- near tiles: lane = unordered e != 0 pair
+        for (int tb = p0; tb < p1; tb += 32) {
+            const bool ok = tb + lane < p1;
+            int li = 0, lj = 0;
+            float nearf = 0.f;
+            float cf[EDR];
+#pragma unroll
+            for (int k = 0; k < EDR; ++k) cf[k] = 0.f;
+            if (ok) {
+                li = a.pair_i[tb + lane] - atom0; lj = a.pair_j[tb + lane] - atom0;
+                if (EPN) nearf = (float)a.near[tb + lane];
+#pragma unroll
+                for (int q = 0; q < EDR / 4; ++q) {
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(a.e + (int64_t)(tb + lane) * EDR) + q);
+                    cf[4 * q] = x.x; cf[4 * q + 1] = x.y; cf[4 * q + 2] = x.z; cf[4 * q + 3] = x.w;
+                }
+            }
+            float ce[HID];
+            {
+                f2_t ce2[HID / 2];
+#pragma unroll
+                for (int o = 0; o < HID / 2; ++o) ce2[o] = 0ull;
+#pragma unroll
+                for (int k = 0; k < EDR; ++k)
+#pragma unroll
+                    for (int o = 0; o < HID / 2; ++o) cfma2(ce2[o], *reinterpret_cast<const f2_t*>(&W.Cw[k * HID + 2 * o]), cf[k]);
+#pragma unroll
+                for (int o = 0; o < HID / 2; ++o) cunpack2(ce2[o], ce[2 * o], ce[2 * o + 1]);
+            }
+            float fd = 0.f;
+#pragma unroll 1
+            for (int dir = 0; dir < 2; ++dir) {                    // dir 0: i receives from j;  dir 1: j receives from i
+                const int ir = dir ? lj : li, is = dir ? li : lj;
+                f2_t acc2[HID / 2];
+                second_layer<true>(W, ce, uv + ir * CUVS, uv + is * CUVS + HID, acc2);
+                if (EPN) {
+                    float f = 0.f;
+#pragma unroll
+                    for (int o = 0; o < HID / 2; ++o) {
+                        float x, y;
+                        cunpack2(acc2[o], x, y);
+                        f = fmaf(fmaxf(x, 0.f), W.x32[2 * o], f);
+                        f = fmaf(fmaxf(y, 0.f), W.x32[2 * o + 1], f);
+                    }
+                    fd = dir ? fd - f : f;
+                } else {
+                    add_messages(acc2, 1.f, ok ? ir : -1, Mt, S, lane);
+                }
+            }
+            if (EPN && ok) a.delta[tb + lane] = 0.5f * fd * nearf;          // charge_gn.py:116
+        }
+
+        if (!EPN) {
+            // ------------------------------------------------------------ far tiles: lane = ordered e == 0 slot (or species slot)
+            bool use0 = a.dedup != 0;
+            if (use0) {                                            // same check as bundle_kernel: v rows equal species by species?
+                bool same = true;
+                for (int r = lane; r < nat; r += 32) {
+                    const int rp = a.rep[atom0 + r] - atom0;
+                    if (rp != r) {
+#pragma unroll
+                        for (int c = 0; c < HID / 4; ++c) {
+                            const float4 x = *reinterpret_cast<const float4*>(uv + r * CUVS + HID + c * 4);
+                            const float4 y = *reinterpret_cast<const float4*>(uv + rp * CUVS + HID + c * 4);
+                            same = same && x.x == y.x && x.y == y.y && x.z == y.z && x.w == y.w;
+                        }
+                    }
+                }
+                use0 = __all_sync(0xffffffffu, same);
+            }
+            const unsigned short* flist = use0 ? a.far0_list : a.far_list;
+            const int f0 = use0 ? a.far0_off[atom0] : a.far_off[atom0], f1 = use0 ? a.far0_off[atom0 + nat] : a.far_off[atom0 + nat];
+            const float zero_ce[HID] = {};
+            for (int fb = f0; fb < f1; fb += 32) {
+                const bool ok = fb + lane < f1;
+                int li = 0, lj = 0;
+                float wv = 0.f;
+                if (ok) {
+                    const int code = (int)flist[fb + lane];
+                    li = code >> 8; lj = code & 0xFF;
+                    if (lj == 0xFF) { lj = PAD_ROW; wv = padw[li]; }        // pad pseudo-pair: weight npad - n, v = b1
+                    else wv = use0 ? (float)a.far0_w[fb + lane] : 1.f;      // species slot: number of far columns of that species
+                }
+                f2_t acc2[HID / 2];
+                second_layer<false>(W, zero_ce, uv + li * CUVS, uv + lj * CUVS + HID, acc2);
+                add_messages(acc2, wv, ok ? li : -1, Mt, S, lane);
+            }
+            // ---- S -> global (plane 0 of the partial-sum planes the per-atom kernel reads)
+            for (int f = lane; f < nat * (HID / 4); f += 32)
+                *reinterpret_cast<float4*>(a.S + (int64_t)atom0 * HID + f * 4) = *reinterpret_cast<const float4*>(S + f * 4);
+        }
+    }
+}
+
+template <bool EPN>
+static cudaError_t launch_const(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* nl) {
+    if (w.n_bundles == 0) return cudaSuccess;
+    if (!w.wf_host || !w.wf_dev) return cudaErrorInvalidValue;
+    PairW W;                                                       // this launch's weights; copied into the launch's parameter buffer
+    auto host = [&](const float* dev) { return w.wf_host + (dev - w.wf_dev); };
+    memcpy(W.Cw, host(sw.Cw), sizeof(W.Cw));
+    memcpy(W.W2, host(sw.W2), sizeof(W.W2));
+    memcpy(W.b2, host(sw.b2), sizeof(W.b2));
+    memcpy(W.x32, host(EPN ? sw.W3 : sw.b1), sizeof(W.x32));
+    ConstArgs ca;
+    ca.n_bundles = w.n_bundles; ca.bundle = w.bundle; ca.work_counter = w.work_counter;
+    cudaError_t e = cudaMemsetAsync(w.work_counter, 0, sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    ca.ustart = w.ustart; ca.pair_i = w.pair_i; ca.pair_j = w.pair_j; ca.near = w.near; ca.e = w.e;
+    ca.far_off = w.far_off; ca.far_list = w.far_list;
+    ca.far0_off = w.far0_off; ca.far0_list = w.far0_list; ca.far0_w = w.far0_w; ca.rep = w.rep; ca.dedup = w.dedup_far;
+    ca.atom_sys = w.atom_sys; ca.sys_off = w.sys_off; ca.npad = w.npad;
+    ca.u = (const float*)w.u; ca.v = (const float*)w.v; ca.S = (float*)w.S; ca.delta = (float*)w.delta;
+    const size_t smem = ConstSmem<EPN>::bytes();
+    e = cudaFuncSetAttribute(bundle_const_kernel<EPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int per_sm = EPN ? 2 : 1;
+    int grid = div_up(w.n_bundles, CONST_NW);
+    if (grid > w.sm_count * per_sm) grid = w.sm_count * per_sm;
+    bundle_const_kernel<EPN><<<grid, CONST_NW * 32, smem, st>>>(W, ca);
+    ++*nl;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gnn_bundle_const(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* nl) { return launch_const<false>(w, sw, st, nl); }
+cudaError_t launch_epn_bundle_const(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* nl) { return launch_const<true>(w, sw, st, nl); }

@@ -234,6 +234,8 @@ struct Workspace {
     int stamp;                                    // stamp of the current message-passing step (t + 1); 0 = de-duplication off
     int n_species;                                // species of the element table in use (8 or 9)
     int pair_tensor;                              // 1: electron-passing bundle kernel on the warp-level tensor path (3xTF32, FP32 only)
+    int pair_const;                               // 1: EXPERIMENTAL pair-per-thread bundle kernels, weights as uniform operands (FP32 only)
+    const float* wf_host; const float* wf_dev;    // packed FP32 weights: host mirror and device base (pair_const passes weights as kernel parameters)
     unsigned long long* dedup_rows;               // device counter (statistics): rows whose far part was collapsed, summed over steps
     void* h; void* S; void* u; void* v; void* delta;   // precision-dependent (float or double)
     void* l2;                          // [n][32] last hidden layer of the update MLP: the state carried between steps
@@ -267,6 +269,8 @@ cudaError_t launch_far0_fill(const Workspace& w, const int* atom_b0, cudaStream_
 template <typename R> cudaError_t launch_gnn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_epn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 cudaError_t launch_epn_bundle_mma(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* n_launch);   // option pair_tensor
+cudaError_t launch_gnn_bundle_const(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* n_launch); // option pair_const
+cudaError_t launch_epn_bundle_const(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* n_launch);
 cudaError_t launch_gnn_far_tc(const Workspace& w, const float* Whi, const float* Wlo, const float* b2, int nsplit_tc,
                               cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);

@@ -93,7 +93,10 @@ const char* epnn_last_error(const epnn_ctx* ctx);
  * the level of FP32 round-off, about 1e-6 relative in the hidden state);
  * "pair_tensor" 0 (default) / 1: systems with at most 48 atoms evaluate the electron-passing pair MLP on the warp-level
  * tensor path (mma.sync m16n8k8 TF32 inputs, 3xTF32 split, FP32 accumulation, operands chained through registers)
- * instead of FP32 SIMT (precision 32 only; per-pair transfers differ from the SIMT path by about 1e-6 relative). */
+ * instead of FP32 SIMT (precision 32 only; per-pair transfers differ from the SIMT path by about 1e-6 relative);
+ * "pair_const" 0 (default) / 1: EXPERIMENTAL, not yet validated on a GPU (see epnn_bundle_const.cu): plain-FP32
+ * variant of both small-system pair kernels in which one thread owns one pair and the weights are uniform operands
+ * passed as kernel parameters (precision 32 only). */
 int epnn_set_option(epnn_ctx* ctx, const char* key, double value);
 
 /* Charge inference for a packed batch of systems, host buffers.
