@@ -19,7 +19,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import elements, xyzio
-from .checkpoint import Weights, load_weights as _load_checkpoint
+from .checkpoint import Weights, load_weights as _load_checkpoint, save_weights as _save_checkpoint
 from .engine import Engine
 
 # reference charge_gn.py:9-28 (10-wide convention); the 9-wide table of infer.py:13-30 is elements.symbols_for(9)
@@ -122,7 +122,17 @@ class Model:
         if self.engine is not None:
             self.engine.close()
         self.weights = w
+        self._loaded_from = prefix
         self.engine = Engine(w, device=self.device, precision=self.precision)
+        return self
+
+    def save_weights(self, prefix: str, template: Optional[str] = None):
+        """``model.save_weights(prefix)`` (reference ``charge_gn.py:462``): a TF tensor-bundle checkpoint TensorFlow's own
+        ``load_weights`` can restore.  The Keras object graph and the file layout come from ``template`` (default: the
+        checkpoint this model was loaded from); see :func:`epnn_b200.checkpoint.save_weights`."""
+        if self.weights is None:
+            raise RuntimeError("nothing to save: call load_weights(prefix) first")
+        _save_checkpoint(self.weights, prefix, template or self._loaded_from)
         return self
 
     def _need(self) -> Engine:

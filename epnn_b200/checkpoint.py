@@ -1,7 +1,7 @@
-"""Pure-Python reader for the TensorFlow "tensor bundle" checkpoints the reference ships.
+"""Pure-Python reader (and template-based writer) for the TensorFlow "tensor bundle" checkpoints the reference ships.
 
-Replaces ``model.load_weights('./models/decay_model_weights')`` (reference ``infer.py:57``) without
-TensorFlow.  Format:
+Replaces ``model.load_weights('./models/decay_model_weights')`` (reference ``infer.py:57``) and
+``model.save_weights(...)`` (reference ``charge_gn.py:462``) without TensorFlow.  Format:
 
 * ``<prefix>.index`` is a LevelDB-style SSTable: 48-byte footer (metaindex handle, index handle,
   magic 0xdb4775248b80fb57), prefix-compressed key/value blocks, each followed by a 1-byte compression
@@ -319,3 +319,139 @@ def load_weights(prefix: str, verify_crc: bool = True) -> Weights:
     if [x.shape for x in upd.W] != [(h_dim + 32, 32), (32, 32), (32, h_dim)]:
         raise CheckpointError("unexpected update MLP shapes")
     return w
+
+
+# ----------------------------------------------------------------------------- writer (template based)
+def _put_varint(v: int) -> bytes:
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        if v:
+            out.append(b | 0x80)
+        else:
+            out.append(b)
+            return bytes(out)
+
+
+def _build_block(entries: List[Tuple[bytes, bytes]], restart_interval: int = 16) -> bytes:
+    """LevelDB block: prefix-compressed entries, a restart point every ``restart_interval`` entries."""
+    buf = bytearray()
+    restarts = []
+    last = b""
+    for n, (key, val) in enumerate(entries):
+        shared = 0
+        if n % restart_interval == 0:
+            restarts.append(len(buf))
+        else:
+            m = min(len(last), len(key))
+            while shared < m and last[shared] == key[shared]:
+                shared += 1
+        buf += _put_varint(shared) + _put_varint(len(key) - shared) + _put_varint(len(val)) + key[shared:] + val
+        last = key
+    if not restarts:
+        restarts = [0]
+    for r in restarts:
+        buf += struct.pack("<I", r)
+    buf += struct.pack("<I", len(restarts))
+    return bytes(buf)
+
+
+def _short_successor(key: bytes) -> bytes:
+    """BytewiseComparator::FindShortSuccessor: first byte that is not 0xff incremented, the rest dropped."""
+    for i, b in enumerate(key):
+        if b != 0xFF:
+            return key[:i] + bytes([b + 1])
+    return key
+
+
+def _write_index(path: str, entries: List[Tuple[bytes, bytes]]):
+    """One-data-block SSTable exactly as TensorFlow's TableBuilder lays it out for a bundle this small:
+    data block, empty metaindex block, index block with one entry (short successor of the last key), 48-byte footer."""
+    out = bytearray()
+
+    def emit(block: bytes) -> Tuple[int, int]:
+        off = len(out)
+        out.extend(block)
+        out.append(0)                                                   # no compression
+        out.extend(struct.pack("<I", masked_crc32c(block + b"\x00")))
+        return off, len(block)
+
+    data = _build_block(entries)
+    if len(data) > 256 * 1024:
+        raise CheckpointError("index would need more than one data block (not produced by the reference's models)")
+    d_off, d_size = emit(data)
+    m_off, m_size = emit(_build_block([]))
+    handle = _put_varint(d_off) + _put_varint(d_size)
+    i_off, i_size = emit(_build_block([(_short_successor(entries[-1][0]), handle)], restart_interval=1))
+    footer = _put_varint(m_off) + _put_varint(m_size) + _put_varint(i_off) + _put_varint(i_size)
+    footer += b"\x00" * (40 - len(footer)) + struct.pack("<Q", _MAGIC)
+    out.extend(footer)
+    with open(path, "wb") as f:
+        f.write(bytes(out))
+
+
+def _mlp_tensors(w: Weights) -> Dict[str, np.ndarray]:
+    """{variable key: array} under the reference's naming, including the step aliasing (module docstring)."""
+    g, p = "layer_with_weights-0", "layer_with_weights-1"
+    out: Dict[str, np.ndarray] = {}
+
+    def put(base: str, mlp: MLP):
+        for i, (W, b) in enumerate(zip(mlp.W, mlp.b)):
+            out[f"{base}/layer_set/{i}/kernel{_SUFFIX}"] = W
+            out[f"{base}/layer_set/{i}/bias{_SUFFIX}"] = b
+
+    for t in range(w.T - 1):
+        put(f"{g}/message_fns/{t}", w.msg[t])
+        put(f"{p}/pass_fns/{t}", w.pas[t])
+    put(f"{g}/message_fn", w.msg[-1])
+    put(f"{p}/pass_fn", w.pas[-1])
+    put(f"{g}/update_fn", w.upd)
+    return out
+
+
+def save_weights(w: Weights, prefix: str, template_prefix: str):
+    """Write ``w`` as a TF tensor-bundle checkpoint ``prefix`` (replaces ``model.save_weights``, reference
+    ``charge_gn.py:462``), using the checkpoint ``template_prefix`` of the SAME architecture as the layout template:
+    the Keras object graph (``_CHECKPOINTABLE_OBJECT_GRAPH``, which TensorFlow needs to restore by object), every key,
+    shape, shard and offset are taken from the template; only the float tensors' bytes and CRCs are replaced.
+    Re-saving an unmodified checkpoint reproduces the reference's files byte for byte (tests/test_checkpoint_io.py)."""
+    index = read_index(template_prefix + ".index")
+    if "" not in index:
+        raise CheckpointError("template: bundle header entry missing")
+    num_shards = 1
+    for fnum, _, val in _proto_fields(index[""]):
+        if fnum == 1:
+            num_shards = val
+    shards = {}
+    for sid in range(num_shards):
+        with open(f"{template_prefix}.data-{sid:05d}-of-{num_shards:05d}", "rb") as f:
+            shards[sid] = bytearray(f.read())
+    tensors = _mlp_tensors(w)
+    entries: List[Tuple[bytes, bytes]] = []
+    seen = set()
+    for key in sorted(index, key=lambda k: k.encode("utf-8")):
+        raw = index[key]
+        ent = _parse_entry(raw) if key else None
+        if ent is not None and ent.dtype == 1:
+            if key not in tensors:
+                raise CheckpointError(f"template variable {key} has no counterpart in the model (different architecture?)")
+            arr = np.ascontiguousarray(tensors[key], dtype="<f4")
+            if tuple(arr.shape) != ent.shape:
+                raise CheckpointError(f"{key}: shape {arr.shape} does not match the template's {ent.shape}")
+            blob = arr.tobytes()
+            shards[ent.shard_id][ent.offset:ent.offset + ent.size] = blob
+            # BundleEntryProto ends with field 6 (crc32c, fixed32: tag 0x35 + 4 bytes); everything before it is unchanged
+            if len(raw) < 5 or raw[-5] != 0x35:
+                raise CheckpointError(f"{key}: unexpected BundleEntryProto layout in the template")
+            raw = raw[:-4] + struct.pack("<I", masked_crc32c(blob))
+            seen.add(key)
+        entries.append((key.encode("utf-8"), raw))
+    missing = set(tensors) - seen
+    if missing:
+        raise CheckpointError(f"model variables absent from the template: {sorted(missing)[:3]} ...")
+    os.makedirs(os.path.dirname(os.path.abspath(prefix)), exist_ok=True)
+    for sid, blob in shards.items():
+        with open(f"{prefix}.data-{sid:05d}-of-{num_shards:05d}", "wb") as f:
+            f.write(bytes(blob))
+    _write_index(prefix + ".index", entries)

@@ -77,3 +77,47 @@ def test_element_tables():
         elements.species_index(["P"], 9)          # P is not in the 9-wide table (reference raises KeyError too)
     with pytest.raises(KeyError):
         elements.species_index(["Xx"], 10)
+
+
+@pytest.mark.parametrize("name", ["decay_model_weights", "model_weights", "model2_weights"])
+def test_save_weights_reproduces_the_shipped_files_byte_for_byte(golden_dir, tmp_path, name):
+    """checkpoint.save_weights (replaces model.save_weights, charge_gn.py:462): re-saving an unmodified shipped checkpoint
+    must give the reference's own .index and .data shards back, byte for byte (SSTable layout, restart points, block
+    CRCs, BundleEntryProto bytes, tensor bytes and CRCs)."""
+    src = os.path.join(golden_dir, "checkpoints", name)
+    w = checkpoint.load_weights(src)
+    dst = str(tmp_path / "resaved")
+    checkpoint.save_weights(w, dst, src)
+    files = sorted(f for f in os.listdir(os.path.dirname(src)) if f.startswith(name + "."))
+    assert len(files) >= 2
+    for f in files:
+        a = open(os.path.join(os.path.dirname(src), f), "rb").read()
+        b = open(dst + f[len(name):], "rb").read()
+        assert a == b, f
+
+
+def test_save_weights_round_trip_of_modified_weights(golden_dir, tmp_path):
+    src = os.path.join(golden_dir, "checkpoints", "model2_weights")
+    w = checkpoint.load_weights(src)
+    rng = np.random.default_rng(3)
+    for mlp in w.msg + w.pas + [w.upd]:
+        for k in range(len(mlp.W)):
+            mlp.W[k] = (mlp.W[k] + rng.normal(size=mlp.W[k].shape)).astype(np.float32)
+            mlp.b[k] = (mlp.b[k] - 1.0).astype(np.float32)
+    dst = str(tmp_path / "edited")
+    checkpoint.save_weights(w, dst, src)
+    back = checkpoint.load_weights(dst)                     # verifies every block and tensor CRC on the way
+    assert np.array_equal(back.packed(), w.packed())
+    assert not np.array_equal(back.packed(), checkpoint.load_weights(src).packed())
+    # the Keras object graph (what TensorFlow restores by) is carried over untouched
+    assert checkpoint.read_index(dst + ".index")["_CHECKPOINTABLE_OBJECT_GRAPH"] == \
+        checkpoint.read_index(src + ".index")["_CHECKPOINTABLE_OBJECT_GRAPH"]
+
+
+def test_save_weights_rejects_a_template_of_another_architecture(golden_dir, tmp_path):
+    w = checkpoint.load_weights(os.path.join(golden_dir, "checkpoints", "model2_weights"))      # T = 3
+    with pytest.raises(checkpoint.CheckpointError):
+        checkpoint.save_weights(w, str(tmp_path / "x"), os.path.join(golden_dir, "checkpoints", "decay_model_weights"))   # T = 5
+    w10 = checkpoint.load_weights(os.path.join(golden_dir, "checkpoints", "model_weights"))     # n_x = 10
+    with pytest.raises(checkpoint.CheckpointError):
+        checkpoint.save_weights(w10, str(tmp_path / "y"), os.path.join(golden_dir, "checkpoints", "decay_model_weights"))
