@@ -19,7 +19,11 @@
 //     first) -- fixed order, no atomics, bitwise reproducible; scatter_sorted / perm_j are not needed here.
 // Shared memory per warp: the bundle's u | v rows (row stride 68 floats, + one row holding b1 for the pad pseudo-atom),
 // and for the GNN variant the S accumulators, the transpose tile and the pad weights.
+#ifdef EPNN_CPU_EMU
+#include "../../tools/emu/cuda_emu.h"      // CPU warp emulation (tests/test_emu_pair_const.py): same kernel body, lanes = host threads
+#else
 #include "epnn_internal.cuh"
+#endif
 
 #define CONST_NW 8
 #define CUVS 68                         // row stride of the staged u | v rows (64 + 4: rows start in different bank groups)
@@ -38,12 +42,22 @@ struct ConstArgs {
 };
 
 typedef unsigned long long f2_t;
+#ifdef EPNN_CPU_EMU      // inline PTX replaced by its definition: two IEEE fma.rn on the packed halves
+__device__ __forceinline__ f2_t cpack2(float lo, float hi) { unsigned a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4); return (f2_t)a | ((f2_t)b << 32); }
+__device__ __forceinline__ void cunpack2(f2_t v, float& lo, float& hi) { const unsigned a = (unsigned)v, b = (unsigned)(v >> 32); memcpy(&lo, &a, 4); memcpy(&hi, &b, 4); }
+__device__ __forceinline__ void cfma2(f2_t& d, f2_t wpair, float a) {
+    float d0, d1, w0, w1;
+    cunpack2(d, d0, d1); cunpack2(wpair, w0, w1);
+    d = cpack2(fmaf(w0, a, d0), fmaf(w1, a, d1));
+}
+#else
 __device__ __forceinline__ f2_t cpack2(float lo, float hi) { f2_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void cunpack2(f2_t v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ void cfma2(f2_t& d, f2_t wpair, float a) {
     const f2_t aa = cpack2(a, a);
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(wpair), "l"(aa));
 }
+#endif
 
 // acc[c] = b2[c] + sum_k relu(ce[k] + urow[k] + vrow[k]) * W2[k][c]   (ce == nullptr-like: pass zeros for far slots)
 template <bool WITH_CE>
@@ -100,7 +114,11 @@ template <bool EPN> struct ConstSmem {
 
 template <bool EPN>
 __global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kernel(const __grid_constant__ PairW W, const ConstArgs a) {
+#ifdef EPNN_CPU_EMU
+    float* csm = emu_smem;
+#else
     extern __shared__ __align__(16) float csm[];
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* uv = csm + warp * ConstSmem<EPN>::PW;                   // [BUNDLE_ATOMS + 1][CUVS]
     float* S = uv + (BUNDLE_ATOMS + 1) * CUVS;                     // [BUNDLE_ATOMS][32]   (GNN)
@@ -226,6 +244,7 @@ __global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kerne
     }
 }
 
+#ifndef EPNN_CPU_EMU
 template <bool EPN>
 static cudaError_t launch_const(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* nl) {
     if (w.n_bundles == 0) return cudaSuccess;
@@ -258,3 +277,4 @@ static cudaError_t launch_const(const Workspace& w, const StepW<float>& sw, cuda
 
 cudaError_t launch_gnn_bundle_const(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* nl) { return launch_const<false>(w, sw, st, nl); }
 cudaError_t launch_epn_bundle_const(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* nl) { return launch_const<true>(w, sw, st, nl); }
+#endif   // !EPNN_CPU_EMU

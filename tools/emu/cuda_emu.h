@@ -1,0 +1,86 @@
+// CPU warp emulation for the warp-synchronous kernels of epnn_b200 (test infrastructure, CPU only).
+//
+// A kernel source compiled with -DEPNN_CPU_EMU includes this header instead of epnn_internal.cuh.  Every lane of a warp
+// is a host thread running the UNMODIFIED kernel body; the warp-level primitives the kernels use (__shfl_sync,
+// __all_sync, __syncwarp) are implemented with a per-warp barrier, shared memory is a per-CTA host buffer, atomicAdd is
+// a GCC atomic.  Inline PTX has to be replaced by the kernel source itself (#ifdef EPNN_CPU_EMU around its asm helpers).
+// This checks indexing, control flow, shared-memory layout and the order of the arithmetic -- not performance.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "../../epnn_b200/csrc/epnn_consts.h"
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __align__(n)
+
+struct alignas(16) float4 { float x, y, z, w; };
+struct int2 { int x, y; };
+struct EmuDim3 { unsigned x = 0, y = 0, z = 0; };
+
+struct EmuBarrier {                       // reusable barrier for the 32 lanes of a warp
+    std::mutex m; std::condition_variable cv; int count = 0, gen = 0;
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const int g = gen;
+        if (++count == 32) { count = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+struct EmuWarp { EmuBarrier bar; uint32_t xbuf[32]; };
+
+inline thread_local EmuDim3 threadIdx, blockIdx, gridDim, blockDim;
+inline thread_local EmuWarp* emu_warp = nullptr;
+inline thread_local float* emu_smem = nullptr;
+#define EPNN_EMU_LANE ((int)(threadIdx.x & 31))
+
+template <typename T> inline T __shfl_sync(unsigned, T v, int src) {
+    static_assert(sizeof(T) == 4, "emulated shuffles move 32-bit values");
+    std::memcpy(&emu_warp->xbuf[EPNN_EMU_LANE], &v, 4);
+    emu_warp->bar.wait();
+    T r;
+    std::memcpy(&r, &emu_warp->xbuf[src & 31], 4);
+    emu_warp->bar.wait();
+    return r;
+}
+template <typename T> inline T __shfl_xor_sync(unsigned m, T v, int x) { return __shfl_sync(m, v, EPNN_EMU_LANE ^ x); }
+inline int __all_sync(unsigned, int pred) {
+    emu_warp->xbuf[EPNN_EMU_LANE] = pred ? 1u : 0u;
+    emu_warp->bar.wait();
+    int r = 1;
+    for (int l = 0; l < 32; ++l) r &= (int)emu_warp->xbuf[l];
+    emu_warp->bar.wait();
+    return r;
+}
+inline void __syncwarp() { emu_warp->bar.wait(); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+template <typename T> inline T __ldg(const T* p) { return *p; }
+using std::max;
+using std::min;
+
+// Runs `kernel(args...)` for one CTA of `n_warps` warps (all warps concurrently, 32 host threads each).
+template <typename F> inline void emu_launch_cta(int n_warps, size_t smem_floats, F kernel) {
+    std::vector<float> smem(smem_floats, 0.f);
+    std::vector<EmuWarp> warps(n_warps);
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_warps * 32; ++t)
+        th.emplace_back([&, t] {
+            threadIdx.x = (unsigned)t; blockIdx.x = 0; gridDim.x = 1; blockDim.x = (unsigned)(n_warps * 32);
+            emu_warp = &warps[t >> 5];
+            emu_smem = smem.data();
+            kernel();
+        });
+    for (auto& x : th) x.join();
+}
