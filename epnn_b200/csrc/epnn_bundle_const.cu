@@ -151,22 +151,30 @@ __global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kerne
         __syncwarp();
 
         // ---------------------------------------------------------------- near tiles: lane = unordered e != 0 pair
-        for (int tb = p0; tb < p1; tb += 32) {
-            const bool ok = tb + lane < p1;
-            int li = 0, lj = 0;
-            float nearf = 0.f;
-            float cf[EDR];
+        // software prefetch: the next tile's indices and coefficient row are requested as soon as the current tile's
+        // first product has consumed its coefficients (same registers), and arrive during the two second-layer products
+        int n_i = atom0, n_j = atom0;
+        float n_near = 0.f;
+        float cf[EDR];
+        auto fetch_tile = [&](int t0) {
+            n_i = atom0; n_j = atom0; n_near = 0.f;
 #pragma unroll
             for (int k = 0; k < EDR; ++k) cf[k] = 0.f;
-            if (ok) {
-                li = a.pair_i[tb + lane] - atom0; lj = a.pair_j[tb + lane] - atom0;
-                if (EPN) nearf = (float)a.near[tb + lane];
+            if (t0 + lane < p1) {
+                n_i = a.pair_i[t0 + lane]; n_j = a.pair_j[t0 + lane];
+                if (EPN) n_near = (float)a.near[t0 + lane];
 #pragma unroll
                 for (int q = 0; q < EDR / 4; ++q) {
-                    const float4 x = __ldg(reinterpret_cast<const float4*>(a.e + (int64_t)(tb + lane) * EDR) + q);
+                    const float4 x = __ldg(reinterpret_cast<const float4*>(a.e + (int64_t)(t0 + lane) * EDR) + q);
                     cf[4 * q] = x.x; cf[4 * q + 1] = x.y; cf[4 * q + 2] = x.z; cf[4 * q + 3] = x.w;
                 }
             }
+        };
+        if (p0 < p1) fetch_tile(p0);
+        for (int tb = p0; tb < p1; tb += 32) {
+            const bool ok = tb + lane < p1;
+            const int li = n_i - atom0, lj = n_j - atom0;          // slots beyond the tile point at atom 0 (results dropped)
+            const float nearf = n_near;
             float ce[HID];
             {
                 f2_t ce2[HID / 2];
@@ -179,6 +187,7 @@ __global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kerne
 #pragma unroll
                 for (int o = 0; o < HID / 2; ++o) cunpack2(ce2[o], ce[2 * o], ce[2 * o + 1]);
             }
+            if (tb + 32 < p1) fetch_tile(tb + 32);                 // cf is dead from here on
             float fd = 0.f;
 #pragma unroll 1
             for (int dir = 0; dir < 2; ++dir) {                    // dir 0: i receives from j;  dir 1: j receives from i
