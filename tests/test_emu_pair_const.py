@@ -32,10 +32,14 @@ def emu():
 
 
 def _build_lists(mixed, idx, n_x, npad, rng, equal_v_systems):
-    """Everything the bundle kernels read, built on the host the way the CUDA prep kernels define it."""
     offs, xyz, sp, _ = mixed.batch(idx, n_x)
+    return _build_lists_raw(offs, xyz, sp, npad, rng, equal_v_systems)
+
+
+def _build_lists_raw(offs, xyz, sp, npad, rng, equal_v_systems):
+    """Everything the bundle kernels read, built on the host the way the CUDA prep kernels define it."""
     n = int(offs[-1])
-    n_sys = len(idx)
+    n_sys = len(offs) - 1
     atom_sys = np.repeat(np.arange(n_sys), np.diff(offs)).astype(np.int32)
     B = np.zeros((48, 16))
     assert _capi.load().epnn_rbf_basis(B.ctypes.data_as(C.c_void_p)) == 0
@@ -55,7 +59,7 @@ def _build_lists(mixed, idx, n_x, npad, rng, equal_v_systems):
                         near.append(1 if e[i, j].max() > np.float32(1e-5) else 0)
                         coef.append((B.T @ e[i, j].astype(np.float64)).astype(np.float32))   # edge_desc_kernel: B^T e, rounded once
     P = len(pair_i)
-    degU = np.bincount(np.array(pair_i), minlength=n)
+    degU = np.bincount(np.array(pair_i, dtype=np.int64), minlength=n)
     ustart = np.concatenate([[0], np.cumsum(degU)]).astype(np.int32)
     # bundles: greedy runs of whole systems with <= BUNDLE_ATOMS atoms (run_chunk in epnn_api.cu)
     bundles, cur0, cur_n = [], -1, 0
@@ -106,7 +110,7 @@ def _build_lists(mixed, idx, n_x, npad, rng, equal_v_systems):
         v[offs[s]:offs[s + 1]] = table[sp[offs[s]:offs[s + 1]]]
     return dict(offs=offs.astype(np.int32), sp=sp, n=n, n_sys=n_sys, atom_sys=atom_sys, rows=rows, P=P,
                 pair_i=np.array(pair_i, np.int32), pair_j=np.array(pair_j, np.int32), near=np.array(near, np.uint8),
-                coef=np.ascontiguousarray(np.array(coef, np.float32).reshape(P, 16)), ustart=ustart,
+                coef=np.ascontiguousarray(np.array(coef, np.float32).reshape(P, 16)) if P else np.zeros((1, 16), np.float32), ustart=ustart,
                 bundles=np.array(bundles, np.int32), far_off=np.array(far_off, np.int32), far_list=np.array(far_list, np.uint16),
                 far0_off=np.array(far0_off, np.int32), far0_list=np.array(far0_list, np.uint16), far0_w=np.array(far0_w, np.uint8),
                 rep=rep, u=u, v=v, npad=np.asarray(npad, np.int32))
@@ -183,3 +187,44 @@ def test_emulated_epn_bundle_kernel_matches_the_definition(emu, mixed):
     assert L["near"].min() == 0 and L["near"].max() == 1               # both kinds of pair are present
     assert np.isfinite(delta).all()
     assert np.abs(delta - ref).max() < 2e-5 * max(1.0, np.abs(ref).max()), np.abs(delta - ref).max()
+
+
+def _gnn_reference(L, W, npad):
+    Cw, W2, b2, b1 = (W[k].astype(np.float64) for k in ("Cw", "W2", "b2", "x32"))
+    u, v = L["u"].astype(np.float64), L["v"].astype(np.float64)
+    ce = {}
+    for p in range(L["P"]):
+        c = L["coef"][p].astype(np.float64) @ Cw
+        ce[(L["pair_i"][p], L["pair_j"][p])] = c
+        ce[(L["pair_j"][p], L["pair_i"][p])] = c
+    ref = np.zeros((L["n"], 32))
+    for i in range(L["n"]):
+        s = L["atom_sys"][i]
+        for j in range(L["offs"][s], L["offs"][s + 1]):
+            ref[i] += _relu(_relu(ce.get((i, j), 0.0) + u[i] + v[j]) @ W2 + b2)
+        ref[i] += (npad[s] - (L["offs"][s + 1] - L["offs"][s])) * _relu(_relu(u[i] + b1) @ W2 + b2)
+    return ref
+
+
+@pytest.mark.parametrize("dedup", [0, 1])
+def test_emulated_gnn_edge_cases(emu, mixed, dedup):
+    """A single atom, two atoms beyond the cutoff (no e != 0 pair at all), a bundle filled to exactly 48 atoms (last
+    staged row next to the pad row), a bundle without any padded system, more warps than bundles."""
+    rng = np.random.default_rng(11)
+    ok = mixed.usable(9)
+    sizes = np.diff(mixed.offsets)[ok]
+    i29 = int(ok[np.nonzero(sizes == 29)[0][0]])
+    i19 = int(ok[np.nonzero(sizes == 19)[0][0]])
+    o2, x2, s2, _ = mixed.batch([i29, i19], 9)
+    o3, x3, s3, _ = mixed.batch([int(ok[3])], 9)
+    offs = np.concatenate([o2, [49, 51], 51 + o3[1:]]).astype(np.int32)                 # 29 | 19 | 1 | 2 | n
+    xyz = np.concatenate([x2, [[0.0, 0.0, 0.0]], [[0.0, 0.0, 0.0], [5.0, 0.0, 0.0]], x3]).astype(np.float32)
+    sp = np.concatenate([s2, [1], [0, 3], s3]).astype(np.int32)
+    npad = np.array([29, 19, 1, 7, 41], np.int32)                      # systems 0, 1, 2 unpadded: the first bundle has no pad slot
+    L = _build_lists_raw(offs, xyz, sp, npad, rng, equal_v_systems=[0, 1, 2, 3])
+    assert int(L["bundles"][0][1]) == 48 and len(L["bundles"]) == 2
+    W = _weights(rng)
+    S, _ = _run(emu, L, W, epn=False, dedup=dedup, n_warps=8)
+    ref = _gnn_reference(L, W, npad)
+    assert np.isfinite(S).all()
+    assert np.abs(S - ref).max() < 2e-5 * np.abs(ref).max(), np.abs(S - ref).max()
