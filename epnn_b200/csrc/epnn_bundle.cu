@@ -50,7 +50,11 @@ template <typename R> struct BundleArgs {
     R* S; R* delta;
 };
 
+#ifdef EPNN_CPU_EMU
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+#else
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 
 // Segmented add of one sorted tile into S.  Thread (pg, og) holds, for the tile positions pg*8 .. pg*8+7, the values
 // val[s] (hidden columns og*4 .. og*4+3) and the target rows tgt[s]; targets ascend over the 32 positions and
@@ -124,7 +128,11 @@ template <typename R, bool EPN> struct BundleSmem {
 
 template <typename R, int NW, bool EPN>
 __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> a) {
+#ifdef EPNN_CPU_EMU
+    unsigned char* smem_raw = reinterpret_cast<unsigned char*>(emu_smem);
+#else
     extern __shared__ __align__(32) unsigned char smem_raw[];
+#endif
     using L = BundleSmem<R, EPN>;
     constexpr int EK = L::EK;
     R* sC = reinterpret_cast<R*>(smem_raw);          // [EK][32]
@@ -401,6 +409,7 @@ __global__ void __launch_bounds__(NW * 32, 1) bundle_kernel(const BundleArgs<R> 
     }
 }
 
+#ifndef EPNN_CPU_EMU
 template <typename R, bool EPN>
 static cudaError_t launch_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* nl) {
     if (w.n_bundles == 0) return cudaSuccess;
@@ -426,7 +435,9 @@ static cudaError_t launch_bundle(const Workspace& w, const StepW<R>& sw, cudaStr
     ++*nl;
     return cudaGetLastError();
 }
+#endif
 
+#ifndef EPNN_CPU_EMU
 template <typename R> cudaError_t launch_gnn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* nl) {
     if constexpr (sizeof(R) == 4) {
         if (w.pair_const) return launch_gnn_bundle_const(w, sw, st, nl);    // experimental pair-per-thread variant (epnn_bundle_const.cu)
@@ -444,6 +455,7 @@ template cudaError_t launch_gnn_bundle<float>(const Workspace&, const StepW<floa
 template cudaError_t launch_gnn_bundle<double>(const Workspace&, const StepW<double>&, cudaStream_t, int*);
 template cudaError_t launch_epn_bundle<float>(const Workspace&, const StepW<float>&, cudaStream_t, int*);
 template cudaError_t launch_epn_bundle<double>(const Workspace&, const StepW<double>&, cudaStream_t, int*);
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Far-pair lists, built once per chunk (geometry does not change between steps).
@@ -467,6 +479,7 @@ __global__ void bundle_mark_kernel(int n_bundles, const int2* __restrict__ bundl
     bundle_nat[bd.x] = bd.y;                     // atom count of the bundle, stored at its first atom
 }
 
+#ifndef EPNN_CPU_EMU
 cudaError_t launch_far_count(const Workspace& w, int* far_cnt, int* atom_b0, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0) return cudaSuccess;
     far_count_kernel<<<div_up(w.n_atoms, 256), 256, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.npad, w.rowptr, far_cnt);
@@ -477,6 +490,7 @@ cudaError_t launch_far_count(const Workspace& w, int* far_cnt, int* atom_b0, cud
     }
     return cudaGetLastError();
 }
+#endif
 
 // code = (i - b0) << 8 | (j - b0), j ascending over the complement of row i's CSR columns within its system
 // (includes j == i); then 0xFF in the low byte for the weighted pad pseudo-pair.
@@ -542,6 +556,7 @@ __global__ void far0_kernel(int n_atoms, const int* __restrict__ atom_sys, const
     }
 }
 
+#ifndef EPNN_CPU_EMU
 cudaError_t launch_far0_count(const Workspace& w, int* cnt, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0) return cudaSuccess;
     far0_kernel<0><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.npad, w.species, w.rowptr, w.col,
@@ -549,7 +564,9 @@ cudaError_t launch_far0_count(const Workspace& w, int* cnt, cudaStream_t st, int
     ++*nl;
     return cudaGetLastError();
 }
+#endif
 
+#ifndef EPNN_CPU_EMU
 cudaError_t launch_far0_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0 || w.n_bundles == 0) return cudaSuccess;
     far0_kernel<1><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.npad, w.species, w.rowptr, w.col,
@@ -557,6 +574,7 @@ cudaError_t launch_far0_fill(const Workspace& w, const int* atom_b0, cudaStream_
     ++*nl;
     return cudaGetLastError();
 }
+#endif
 
 // perm_j[p] = position of pair p inside its 32-pair tile when the tile's valid pairs are ordered by (j, slot).  Tiles
 // start at the first pair of the bundle (ustart[b0]); one thread per pair, the <= 31 other j's come from L1.
@@ -584,6 +602,7 @@ __global__ void tile_perm_kernel(int64_t P, const int* __restrict__ pair_i, cons
     perm[p] = (unsigned char)rank;
 }
 
+#ifndef EPNN_CPU_EMU
 cudaError_t launch_far_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0 || w.n_bundles == 0) return cudaSuccess;
     if (w.P > 0) {
@@ -596,3 +615,4 @@ cudaError_t launch_far_fill(const Workspace& w, const int* atom_b0, cudaStream_t
     ++*nl;
     return cudaGetLastError();
 }
+#endif

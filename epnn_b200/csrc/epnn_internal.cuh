@@ -1,7 +1,11 @@
 // Internal declarations shared by the translation units of libepnn_b200.so (not installed).
 #pragma once
 
+#ifdef EPNN_CPU_EMU
+#include "../../tools/emu/cuda_emu.h"      // CPU warp emulation of the kernels (tests/test_emu_*.py): lanes = host threads
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -20,6 +24,7 @@ template <typename R> struct EKof { static constexpr int v = sizeof(R) == 4 ? ED
 
 template <typename R> __device__ __forceinline__ Vec4<R> vzero() { Vec4<R> v; v.x = v.y = v.z = v.w = R(0); return v; }
 template <typename R> __device__ __forceinline__ Vec4<R> vadd(Vec4<R> a, Vec4<R> b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; return a; }
+#ifndef EPNN_CPU_EMU
 // FP32: two packed adds (Blackwell add.rn.f32x2, bit-identical to four scalar FADDs, half the FMA-pipe slots)
 template <> __device__ __forceinline__ Vec4<float> vadd<float>(Vec4<float> a, Vec4<float> b) {
     unsigned long long a0, a1, b0, b1;
@@ -34,7 +39,9 @@ template <> __device__ __forceinline__ Vec4<float> vadd<float>(Vec4<float> a, Ve
     asm("mov.b64 {%0,%1}, %2;" : "=f"(r.z), "=f"(r.w) : "l"(a1));
     return r;
 }
+#endif
 template <typename R> __device__ __forceinline__ Vec4<R> vscale(Vec4<R> a, R s) { a.x *= s; a.y *= s; a.z *= s; a.w *= s; return a; }
+#ifndef EPNN_CPU_EMU
 template <> __device__ __forceinline__ Vec4<float> vscale<float>(Vec4<float> a, float s) {
     unsigned long long a0, a1, ss;
     asm("mov.b64 %0, {%1,%2};" : "=l"(a0) : "f"(a.x), "f"(a.y));
@@ -47,6 +54,7 @@ template <> __device__ __forceinline__ Vec4<float> vscale<float>(Vec4<float> a, 
     asm("mov.b64 {%0,%1}, %2;" : "=f"(r.z), "=f"(r.w) : "l"(a1));
     return r;
 }
+#endif
 template <typename R> __device__ __forceinline__ Vec4<R> vrelu(Vec4<R> a) {
     a.x = a.x > R(0) ? a.x : R(0); a.y = a.y > R(0) ? a.y : R(0);
     a.z = a.z > R(0) ? a.z : R(0); a.w = a.w > R(0) ? a.w : R(0); return a;
@@ -100,12 +108,22 @@ __device__ __forceinline__ void tile_gemm(const R* __restrict__ at, const R* __r
 // goes away.  The pair operand is the weight pair (w[c], w[c+1]); the activation is the scalar that ptxas
 // folds into FFMA2's broadcast ".F32" operand form (no MOV is emitted for the duplicated pair).
 typedef unsigned long long f32x2_t;
+#ifdef EPNN_CPU_EMU      // the packed instructions replaced by their definition: two IEEE fma.rn on the halves
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) { unsigned a, b; memcpy(&a, &lo, 4); memcpy(&b, &hi, 4); return (f32x2_t)a | ((f32x2_t)b << 32); }
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) { const unsigned a = (unsigned)v, b = (unsigned)(v >> 32); memcpy(&lo, &a, 4); memcpy(&hi, &b, 4); }
+__device__ __forceinline__ void fma2(f32x2_t& d, f32x2_t wpair, float a) {
+    float d0, d1, w0, w1;
+    unpack2(d, d0, d1); unpack2(wpair, w0, w1);
+    d = pack2(fmaf(w0, a, d0), fmaf(w1, a, d1));
+}
+#else
 __device__ __forceinline__ f32x2_t pack2(float lo, float hi) { f32x2_t r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) { asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ void fma2(f32x2_t& d, f32x2_t wpair, float a) {
     const f32x2_t aa = pack2(a, a);
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(wpair), "l"(aa));
 }
+#endif
 template <int K, int WLD, int UNR = 2>
 __device__ __forceinline__ void tile_gemm_f32x2(const float* __restrict__ at, const float* __restrict__ W, int wcol,
                                                 float (&acc)[8][4], int pg) {
@@ -192,10 +210,12 @@ template <typename R> struct DenseW {      // raw (un-split) views of one MLP st
     const R* W2; const R* b2; const R* W3; const R* b3;
 };
 
+#ifndef EPNN_CPU_EMU
 template <typename R>
 cudaError_t launch_dense_forward(int B, int N, int n_x, int T, const float* h, const float* e, const float* x, const float* q,
                                  const float* mask, const DenseW<R>* msgw, const UpdW<R>& upd, const DenseW<R>* pasw,
                                  R* a, R* node_mask, R* uv, R* msg, float* q_out, cudaStream_t st);
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Per-chunk device workspace (pointers into grow-only buffers owned by the ctx).
@@ -243,6 +263,7 @@ struct CellWork {
     int* cell_cnt; int* cell_start; int* cell_atoms; double* Dtmp;
 };
 
+#ifndef EPNN_CPU_EMU
 // ------------------------------------------------------------------------------------------------
 // Launchers (defined in the .cu files; every one enqueues on `st` and returns cudaGetLastError()).
 cudaError_t launch_prep(const Workspace& w, cudaStream_t st, int* n_launch);
@@ -280,4 +301,5 @@ template <typename R> cudaError_t launch_atom(const Workspace& w, int mode, cons
                                               const StepW<R>* next, int h_is_zero, float* q_out, double* q_out64,
                                               cudaStream_t st, int* n_launch);
 
+#endif   // !EPNN_CPU_EMU
 static inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

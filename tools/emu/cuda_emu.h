@@ -27,15 +27,19 @@
 #define __align__(n)
 
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(16) ulonglong2 { unsigned long long x, y; };
 struct int2 { int x, y; };
+inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+inline int2 make_int2(int x, int y) { int2 r; r.x = x; r.y = y; return r; }
 struct EmuDim3 { unsigned x = 0, y = 0, z = 0; };
 
-struct EmuBarrier {                       // reusable barrier for the 32 lanes of a warp
-    std::mutex m; std::condition_variable cv; int count = 0, gen = 0;
+struct EmuBarrier {                       // reusable barrier: the 32 lanes of a warp, or all threads of a CTA
+    std::mutex m; std::condition_variable cv; int count = 0, gen = 0, parties = 32;
     void wait() {
         std::unique_lock<std::mutex> lk(m);
         const int g = gen;
-        if (++count == 32) { count = 0; ++gen; cv.notify_all(); }
+        if (++count == parties) { count = 0; ++gen; cv.notify_all(); }
         else cv.wait(lk, [&] { return gen != g; });
     }
 };
@@ -43,6 +47,7 @@ struct EmuWarp { EmuBarrier bar; uint32_t xbuf[32]; };
 
 inline thread_local EmuDim3 threadIdx, blockIdx, gridDim, blockDim;
 inline thread_local EmuWarp* emu_warp = nullptr;
+inline thread_local EmuBarrier* emu_cta_bar = nullptr;
 inline thread_local float* emu_smem = nullptr;
 #define EPNN_EMU_LANE ((int)(threadIdx.x & 31))
 
@@ -56,6 +61,9 @@ template <typename T> inline T __shfl_sync(unsigned, T v, int src) {
     return r;
 }
 template <typename T> inline T __shfl_xor_sync(unsigned m, T v, int x) { return __shfl_sync(m, v, EPNN_EMU_LANE ^ x); }
+// lanes whose source falls outside the warp keep their own value (CUDA semantics for width 32)
+template <typename T> inline T __shfl_up_sync(unsigned m, T v, unsigned d) { const int src = EPNN_EMU_LANE - (int)d; return __shfl_sync(m, v, src >= 0 ? src : EPNN_EMU_LANE); }
+template <typename T> inline T __shfl_down_sync(unsigned m, T v, unsigned d) { const int src = EPNN_EMU_LANE + (int)d; return __shfl_sync(m, v, src < 32 ? src : EPNN_EMU_LANE); }
 inline int __all_sync(unsigned, int pred) {
     emu_warp->xbuf[EPNN_EMU_LANE] = pred ? 1u : 0u;
     emu_warp->bar.wait();
@@ -65,20 +73,32 @@ inline int __all_sync(unsigned, int pred) {
     return r;
 }
 inline void __syncwarp() { emu_warp->bar.wait(); }
+inline void __syncthreads() { emu_cta_bar->wait(); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 template <typename T> inline T __ldg(const T* p) { return *p; }
 using std::max;
 using std::min;
 
+// Runs a kernel WITHOUT warp-level primitives or shared memory (the one-thread-per-item prep kernels): every thread of
+// the grid is executed sequentially on the calling host thread.
+template <typename F> inline void emu_launch_simple(int grid, int block, F kernel) {
+    gridDim.x = (unsigned)grid; blockDim.x = (unsigned)block;
+    for (int b = 0; b < grid; ++b)
+        for (int t = 0; t < block; ++t) { blockIdx.x = (unsigned)b; threadIdx.x = (unsigned)t; kernel(); }
+}
+
 // Runs `kernel(args...)` for one CTA of `n_warps` warps (all warps concurrently, 32 host threads each).
 template <typename F> inline void emu_launch_cta(int n_warps, size_t smem_floats, F kernel) {
     std::vector<float> smem(smem_floats, 0.f);
     std::vector<EmuWarp> warps(n_warps);
+    EmuBarrier cta;
+    cta.parties = n_warps * 32;
     std::vector<std::thread> th;
     for (int t = 0; t < n_warps * 32; ++t)
         th.emplace_back([&, t] {
             threadIdx.x = (unsigned)t; blockIdx.x = 0; gridDim.x = 1; blockDim.x = (unsigned)(n_warps * 32);
             emu_warp = &warps[t >> 5];
+            emu_cta_bar = &cta;
             emu_smem = smem.data();
             kernel();
         });
