@@ -42,7 +42,11 @@ template <typename R> struct GnnArgs {
 
 template <typename R, bool LARGE, int NW>
 __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) gnn_pair_kernel(const GnnArgs<R> a) {
+#ifdef EPNN_CPU_EMU
+    unsigned char* smem_raw = reinterpret_cast<unsigned char*>(emu_smem);
+#else
     extern __shared__ __align__(32) unsigned char smem_raw[];
+#endif
     constexpr int EK = EKof<R>::v;
     R* sC = reinterpret_cast<R*>(smem_raw);          // [48][32]
     R* sW2 = sC + EK * HID;                          // [32][32]
@@ -279,6 +283,7 @@ template <typename R> static size_t gnn_smem_bytes(int nw) {
     return sizeof(R) * (EK * HID + HID * HID + 2 * HID + (size_t)nw * (32 * EK + 32 * HID)) + sizeof(int) * nw * 64;
 }
 
+#ifndef EPNN_CPU_EMU
 template <typename R, bool LARGE, int NW>
 static cudaError_t launch_one(const GnnArgs<R>& ga, int sm_count, cudaStream_t st) {
     const size_t smem = gnn_smem_bytes<R>(NW);
@@ -317,6 +322,7 @@ cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t
 
 template cudaError_t launch_gnn_pair<float>(const Workspace&, const StepW<float>&, cudaStream_t, int*);
 template cudaError_t launch_gnn_pair<double>(const Workspace&, const StepW<double>&, cudaStream_t, int*);
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Species tables of the large systems (built once per chunk) and the per-step equality check of their v rows.
@@ -379,6 +385,7 @@ __global__ void sp_tally_kernel(int n_entries, const int* __restrict__ tab, cons
     if (n > 0 && stamp[2 * t] != cur && stamp[2 * t + 1] == 0) atomicAdd(out, (unsigned long long)n);
 }
 
+#ifndef EPNN_CPU_EMU
 cudaError_t launch_sp_tab_build(const Workspace& w, cudaStream_t st, int* nl) {
     if (w.n_rg_large == 0 || w.n_sp_tab == 0) return cudaSuccess;
     sp_tab_init_kernel<<<div_up((int64_t)w.n_sp_tab * 32, 256), 256, 0, st>>>(w.n_sp_tab, w.sp_tab, w.sp_stamp);
@@ -401,3 +408,4 @@ template <typename R> cudaError_t launch_sp_check(const Workspace& w, cudaStream
 }
 template cudaError_t launch_sp_check<float>(const Workspace&, cudaStream_t, int*);
 template cudaError_t launch_sp_check<double>(const Workspace&, cudaStream_t, int*);
+#endif

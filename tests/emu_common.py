@@ -44,12 +44,17 @@ def build_lists_raw(offs, xyz, sp, npad, rng, equal_v_systems):
     bundles, cur0, cur_n = [], -1, 0
     for s in range(n_sys):
         ns = offs[s + 1] - offs[s]
+        if ns > BUNDLE_ATOMS:                                          # large systems take the row-group kernels
+            if cur_n:
+                bundles.append((cur0, cur_n)); cur_n = 0
+            continue
         if cur_n and cur_n + ns > BUNDLE_ATOMS:
             bundles.append((cur0, cur_n)); cur_n = 0
         if not cur_n:
             cur0 = int(offs[s])
         cur_n += int(ns)
-    bundles.append((cur0, cur_n))
+    if cur_n:
+        bundles.append((cur0, cur_n))
     atom_b0 = np.zeros(n, np.int32)
     for b0, bn in bundles:
         atom_b0[b0:b0 + bn] = b0
@@ -59,6 +64,9 @@ def build_lists_raw(offs, xyz, sp, npad, rng, equal_v_systems):
     for i in range(n):
         s = atom_sys[i]
         a0, a1 = offs[s], offs[s + 1]
+        if a1 - a0 > BUNDLE_ATOMS:                                     # far_count_kernel / far0_kernel: nothing for large systems
+            far_off.append(len(far_list)); far0_off.append(len(far0_list)); rep[i] = i
+            continue
         b0 = atom_b0[i]
         rowset = set(rows[i])
         for j in range(a0, a1):
@@ -90,7 +98,7 @@ def build_lists_raw(offs, xyz, sp, npad, rng, equal_v_systems):
     return dict(offs=offs.astype(np.int32), sp=sp, n=n, n_sys=n_sys, atom_sys=atom_sys, rows=rows, P=P,
                 pair_i=np.array(pair_i, np.int32), pair_j=np.array(pair_j, np.int32), near=np.array(near, np.uint8),
                 coef=np.ascontiguousarray(np.array(coef, np.float32).reshape(P, 16)) if P else np.zeros((1, 16), np.float32), ustart=ustart,
-                bundles=np.array(bundles, np.int32), far_off=np.array(far_off, np.int32), far_list=np.array(far_list, np.uint16),
+                bundles=np.array(bundles, np.int32).reshape(-1, 2), far_off=np.array(far_off, np.int32), far_list=np.array(far_list, np.uint16),
                 far0_off=np.array(far0_off, np.int32), far0_list=np.array(far0_list, np.uint16), far0_w=np.array(far0_w, np.uint8),
                 rep=rep, u=u, v=v, npad=np.asarray(npad, np.int32))
 
@@ -142,3 +150,17 @@ def csr(L):
     rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int32)
     col = np.array([j for r in L["rows"] for j in r] + [0], np.int32)
     return rowptr, col
+
+
+def large_system_tables(L):
+    """Row groups of the large systems (rg_fill_kernel), rgl_off (exclusive scan of the per-system counts), pair id and
+    degree per CSR entry / atom -- what gnn_pair_kernel<LARGE> reads besides the CSR."""
+    offs = L["offs"]
+    n_sys = L["n_sys"]
+    cnt = [((offs[s + 1] - offs[s] + 3) // 4) if offs[s + 1] - offs[s] > BUNDLE_ATOMS else 0 for s in range(n_sys)]
+    rgl_off = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    rg = [i for s in range(n_sys) if cnt[s] for i in range(offs[s], offs[s + 1], 4)]
+    pid_of = {(int(i), int(j)): p for p, (i, j) in enumerate(zip(L["pair_i"], L["pair_j"]))}
+    pid = np.array([pid_of[(min(i, j), max(i, j))] for i, r in enumerate(L["rows"]) for j in r] + [0], np.int32)
+    deg = np.array([len(r) for r in L["rows"]], np.int32)
+    return np.array(rg + [0], np.int32), len(rg), rgl_off, pid, deg

@@ -52,12 +52,14 @@ inline thread_local float* emu_smem = nullptr;
 #define EPNN_EMU_LANE ((int)(threadIdx.x & 31))
 
 template <typename T> inline T __shfl_sync(unsigned, T v, int src) {
-    static_assert(sizeof(T) == 4, "emulated shuffles move 32-bit values");
-    std::memcpy(&emu_warp->xbuf[EPNN_EMU_LANE], &v, 4);
-    emu_warp->bar.wait();
+    static_assert(sizeof(T) == 4 || sizeof(T) == 8, "emulated shuffles move 32- or 64-bit values");
     T r;
-    std::memcpy(&r, &emu_warp->xbuf[src & 31], 4);
-    emu_warp->bar.wait();
+    for (size_t h = 0; h < sizeof(T) / 4; ++h) {
+        std::memcpy(&emu_warp->xbuf[EPNN_EMU_LANE], reinterpret_cast<const char*>(&v) + 4 * h, 4);
+        emu_warp->bar.wait();
+        std::memcpy(reinterpret_cast<char*>(&r) + 4 * h, &emu_warp->xbuf[src & 31], 4);
+        emu_warp->bar.wait();
+    }
     return r;
 }
 template <typename T> inline T __shfl_xor_sync(unsigned m, T v, int x) { return __shfl_sync(m, v, EPNN_EMU_LANE ^ x); }
@@ -72,9 +74,33 @@ inline int __all_sync(unsigned, int pred) {
     emu_warp->bar.wait();
     return r;
 }
+inline unsigned __match_any_sync(unsigned, int key) {          // lanes holding the same key
+    emu_warp->xbuf[EPNN_EMU_LANE] = (uint32_t)key;
+    emu_warp->bar.wait();
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= (emu_warp->xbuf[l] == (uint32_t)key ? 1u : 0u) << l;
+    emu_warp->bar.wait();
+    return m;
+}
+inline unsigned __ballot_sync(unsigned, int pred) {
+    emu_warp->xbuf[EPNN_EMU_LANE] = pred ? 1u : 0u;
+    emu_warp->bar.wait();
+    unsigned m = 0;
+    for (int l = 0; l < 32; ++l) m |= emu_warp->xbuf[l] << l;
+    emu_warp->bar.wait();
+    return m;
+}
+inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline void __syncwarp() { emu_warp->bar.wait(); }
 inline void __syncthreads() { emu_cta_bar->wait(); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicMin(int* p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+    while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+    return old;
+}
 template <typename T> inline T __ldg(const T* p) { return *p; }
 using std::max;
 using std::min;
@@ -88,7 +114,8 @@ template <typename F> inline void emu_launch_simple(int grid, int block, F kerne
 }
 
 // Runs `kernel(args...)` for one CTA of `n_warps` warps (all warps concurrently, 32 host threads each).
-template <typename F> inline void emu_launch_cta(int n_warps, size_t smem_floats, F kernel) {
+// emu_launch_grid runs the CTAs of a grid one after the other.
+template <typename F> inline void emu_launch_cta(int n_warps, size_t smem_floats, F kernel, int block = 0, int grid = 1) {
     std::vector<float> smem(smem_floats, 0.f);
     std::vector<EmuWarp> warps(n_warps);
     EmuBarrier cta;
@@ -96,11 +123,14 @@ template <typename F> inline void emu_launch_cta(int n_warps, size_t smem_floats
     std::vector<std::thread> th;
     for (int t = 0; t < n_warps * 32; ++t)
         th.emplace_back([&, t] {
-            threadIdx.x = (unsigned)t; blockIdx.x = 0; gridDim.x = 1; blockDim.x = (unsigned)(n_warps * 32);
+            threadIdx.x = (unsigned)t; blockIdx.x = (unsigned)block; gridDim.x = (unsigned)grid; blockDim.x = (unsigned)(n_warps * 32);
             emu_warp = &warps[t >> 5];
             emu_cta_bar = &cta;
             emu_smem = smem.data();
             kernel();
         });
     for (auto& x : th) x.join();
+}
+template <typename F> inline void emu_launch_grid(int grid, int n_warps, size_t smem_floats, F kernel) {
+    for (int b = 0; b < grid; ++b) emu_launch_cta(n_warps, smem_floats, kernel, b, grid);
 }
