@@ -39,14 +39,22 @@ template <typename R> struct AtomArgs {
 #ifndef ATOM_PREFETCH
 #define ATOM_PREFETCH 1      // measured: per-atom kernels -5 % (tools/gpu_ab_atom.sh); keeping 4 CSR entries in flight or 14 warps: no change
 #endif
+#ifdef EPNN_CPU_EMU
+__device__ __forceinline__ void prefetch_l2(const void*) {}
+#else
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 #define ATOM_W_UPD (64 * HID + 2 * HID + HID * HID + HID + HID * HD + HD)                    // 4752
 #define ATOM_W_PROJ (HID * 64 + 64 + MAX_SPECIES * 64)                                      // 3136
 #define ATOM_TILE (32 * 64 + 32 * HID)                                                      // 3072 per warp
 
 template <typename R, int NW>
 __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
+#ifdef EPNN_CPU_EMU
+    unsigned char* smem_raw = reinterpret_cast<unsigned char*>(emu_smem);
+#else
     extern __shared__ __align__(32) unsigned char smem_raw[];
+#endif
     R* sHG = reinterpret_cast<R*>(smem_raw);   // [64][32]  [U3 U1_h ; W3 U1_M]
     R* scb = sHG + 64 * HID;                   // [32]      first-layer bias of this step
     R* sg = scb + HID;                         // [32]      U1_M^T b3
@@ -238,6 +246,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
     }
 }
 
+#ifndef EPNN_CPU_EMU
 template <typename R>
 cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd, const StepW<R>* next,
                         int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl) {
@@ -266,3 +275,4 @@ template cudaError_t launch_atom<float>(const Workspace&, int, const StepW<float
                                         int, float*, double*, cudaStream_t, int*);
 template cudaError_t launch_atom<double>(const Workspace&, int, const StepW<double>*, const UpdW<double>*, const StepW<double>*,
                                          int, float*, double*, cudaStream_t, int*);
+#endif

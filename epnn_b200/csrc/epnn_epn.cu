@@ -24,7 +24,11 @@ template <typename R> struct EpnArgs {
 
 template <typename R, int NW>
 __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) epn_pair_kernel(const EpnArgs<R> a) {
+#ifdef EPNN_CPU_EMU
+    unsigned char* smem_raw = reinterpret_cast<unsigned char*>(emu_smem);
+#else
     extern __shared__ __align__(32) unsigned char smem_raw[];
+#endif
     constexpr int EK = EKof<R>::v;
     R* sC = reinterpret_cast<R*>(smem_raw);          // [48][32]
     R* sW2 = sC + EK * HID;                          // [32][32]
@@ -146,6 +150,7 @@ __global__ void __launch_bounds__(NW * 32, sizeof(R) == 4 ? 2 : 1) epn_pair_kern
     }
 }
 
+#ifndef EPNN_CPU_EMU
 template <typename R>
 cudaError_t launch_epn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* nl) {
     if (w.P == 0 || w.n_rg_large == 0) return cudaSuccess;
@@ -171,3 +176,4 @@ cudaError_t launch_epn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t
 
 template cudaError_t launch_epn_pair<float>(const Workspace&, const StepW<float>&, cudaStream_t, int*);
 template cudaError_t launch_epn_pair<double>(const Workspace&, const StepW<double>&, cudaStream_t, int*);
+#endif

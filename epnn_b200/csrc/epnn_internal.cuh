@@ -290,6 +290,7 @@ template <typename R> cudaError_t launch_gnn_pair(const Workspace& w, const Step
 cudaError_t launch_sp_tab_build(const Workspace& w, cudaStream_t st, int* n_launch);                    // once per chunk
 template <typename R> cudaError_t launch_sp_check(const Workspace& w, cudaStream_t st, int* n_launch);  // once per step (needs w.stamp)
 template <typename R> cudaError_t launch_epn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
+#endif   // !EPNN_CPU_EMU
 // mode bits for the per-atom kernel
 #define ATOM_UPDATE  1     // h <- update_fn([h | W3^T S + npad*b3])   (finishes a message-passing step)
 #define ATOM_QUPDATE 2     // q <- q + sum_j (+/-) delta               (finishes an electron-passing pass)
@@ -297,6 +298,7 @@ template <typename R> cudaError_t launch_epn_pair(const Workspace& w, const Step
 #define ATOM_OUTPUT  8     // write q to the output buffers
 #define ATOM_FIRST   16    // first message-passing step: h = 0, there is no previous l2
 #define ATOM_WRITE_H 32    // also materialise h = U3^T l2 + c3 (last message-passing step: epnn_get_hidden)
+#ifndef EPNN_CPU_EMU
 template <typename R> cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd,
                                               const StepW<R>* next, int h_is_zero, float* q_out, double* q_out64,
                                               cudaStream_t st, int* n_launch);

@@ -92,6 +92,7 @@ inline unsigned __ballot_sync(unsigned, int pred) {
 }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0u; }
 inline void __syncwarp() { emu_warp->bar.wait(); }
 inline void __syncthreads() { emu_cta_bar->wait(); }
 inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
