@@ -17,8 +17,12 @@ __constant__ double c_mu[ED];
 
 __constant__ double c_B[ED * EDR];       // orthonormal basis of the descriptor family, [k][r]
 
+#ifdef EPNN_CPU_EMU
+void emu_set_rbf(const double* mu, const double* B) { memcpy(c_mu, mu, sizeof(c_mu)); memcpy(c_B, B, sizeof(c_B)); }
+#else
 cudaError_t upload_rbf_centers(const double* mu) { return cudaMemcpyToSymbol(c_mu, mu, sizeof(double) * ED); }
 cudaError_t upload_rbf_basis(const double* B) { return cudaMemcpyToSymbol(c_B, B, sizeof(double) * ED * EDR); }
+#endif
 
 // float64 distance exactly as scipy computes it; intrinsics forbid FMA contraction.
 __device__ __forceinline__ double dist64(float xi, float yi, float zi, float xj, float yj, float zj) {
@@ -64,12 +68,14 @@ __global__ void prep_kernel(int n_atoms, int n_sys, const int* __restrict__ sys_
     q[i] = (double)__fdiv_rn(Qsys[lo], (float)n);      // charge_gn.py:337-338
 }
 
+#ifndef EPNN_CPU_EMU
 cudaError_t launch_prep(const Workspace& w, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0) return cudaSuccess;
     prep_kernel<<<div_up(w.n_atoms, 256), 256, 0, st>>>(w.n_atoms, w.n_sys, w.sys_off, w.Qsys, w.atom_sys, w.q);
     ++*nl;
     return cudaGetLastError();
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Cell lists for big systems (n > CELL_MIN atoms).  Every such system gets its own uniform grid with cell edge
@@ -134,6 +140,7 @@ __global__ void cell_bin_kernel(int n_atoms, const int* __restrict__ atom_sys, c
     if (PASS == 1) cell_atoms[cell_start[c] + k] = i;
 }
 
+#ifndef EPNN_CPU_EMU
 cudaError_t launch_cell_build(const Workspace& w, const CellWork& cw, int* scantmp, cudaStream_t st, int* nl) {
     if (cw.n_large == 0) return cudaSuccess;
     cell_setup_kernel<<<cw.n_large, 256, 0, st>>>(cw.n_large, cw.large_sys, cw.large_base, w.sys_off, w.xyz, cw.grid);
@@ -149,6 +156,7 @@ cudaError_t launch_cell_build(const Workspace& w, const CellWork& cw, int* scant
     ++*nl;
     return cudaGetLastError();
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Neighbour search: one thread per atom row, two passes (count, fill).  Systems with n <= CELL_MIN scan their own
@@ -229,6 +237,7 @@ __global__ void nbr_kernel(int n_atoms, const int* __restrict__ atom_sys, const 
     if (!FILL) { deg[i] = c; degU[i] = cu; }
 }
 
+#ifndef EPNN_CPU_EMU
 cudaError_t launch_nbr_count(const Workspace& w, const CellWork& cw, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0) return cudaSuccess;
     nbr_kernel<false><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, w.deg, w.degU,
@@ -237,6 +246,7 @@ cudaError_t launch_nbr_count(const Workspace& w, const CellWork& cw, cudaStream_
     ++*nl;
     return cudaGetLastError();
 }
+#endif
 
 // pid of every CSR entry: upper entries (j > i) are numbered ustart[i] + rank; lower entries (j < i)
 // look the pair up in row j's upper part (binary search; rows are sorted).
@@ -325,6 +335,7 @@ __global__ void __launch_bounds__(EDGE_PAIRS) edge_desc_kernel(int64_t P, const 
     for (int f = threadIdx.x; f < rows * EKOUT; f += EDGE_PAIRS) dst[f] = tile[f / EKOUT][f % EKOUT];
 }
 
+#ifndef EPNN_CPU_EMU
 cudaError_t launch_nbr_fill(const Workspace& w, const CellWork& cw, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0) return cudaSuccess;
     nbr_kernel<true><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, nullptr, nullptr,
@@ -340,6 +351,7 @@ cudaError_t launch_nbr_fill(const Workspace& w, const CellWork& cw, cudaStream_t
     }
     return cudaGetLastError();
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Dense (n,n,48) descriptors of one system, literal layout of get_init_edges (facade / tests).
@@ -359,12 +371,14 @@ __global__ void edges_dense_kernel(int n, const float* __restrict__ xyz, float* 
     e[idx] = out;
 }
 
+#ifndef EPNN_CPU_EMU
 cudaError_t launch_edges_dense(int n, const float* xyz, float* e, cudaStream_t st) {
     const int64_t tot = (int64_t)n * n * ED;
     if (tot == 0) return cudaSuccess;
     edges_dense_kernel<<<div_up(tot, 256), 256, 0, st>>>(n, xyz, e);
     return cudaGetLastError();
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Exclusive scan of int32 (out has n+1 entries; out[n] = total).  Three small kernels:
@@ -433,6 +447,7 @@ __global__ void scan_apply(const int* __restrict__ in, int n, const int* __restr
 }
 
 // tmp needs div_up(n, 1024) ints.  out[n] receives the total.
+#ifndef EPNN_CPU_EMU
 cudaError_t launch_scan_i32(const int* in, int* out, int n, int* tmp, cudaStream_t st, int* nl) {
     if (n == 0) return cudaMemsetAsync(out, 0, sizeof(int), st);
     const int nb = div_up(n, SCAN_BLOCK);
@@ -442,3 +457,4 @@ cudaError_t launch_scan_i32(const int* in, int* out, int n, int* tmp, cudaStream
     *nl += 3;
     return cudaGetLastError();
 }
+#endif

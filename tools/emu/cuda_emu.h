@@ -25,6 +25,8 @@
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __align__(n)
+#define __constant__
+#define __shared__ static            /* statically sized shared arrays: one CTA runs at a time, its threads share the static */
 
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) int4 { int x, y, z, w; };
@@ -105,6 +107,14 @@ inline int atomicMin(int* p, int v) {
 template <typename T> inline T __ldg(const T* p) { return *p; }
 using std::max;
 using std::min;
+// round-to-nearest arithmetic intrinsics (compile the emulation with -ffp-contract=off: no fused contraction either)
+inline double __dadd_rn(double a, double b) { return a + b; }
+inline double __dsub_rn(double a, double b) { return a - b; }
+inline double __dmul_rn(double a, double b) { return a * b; }
+inline double __ddiv_rn(double a, double b) { return a / b; }
+inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+inline float __fdiv_rn(float a, float b) { return a / b; }
+inline float __double2float_rn(double a) { return (float)a; }
 
 // Runs a kernel WITHOUT warp-level primitives or shared memory (the one-thread-per-item prep kernels): every thread of
 // the grid is executed sequentially on the calling host thread.
