@@ -23,6 +23,7 @@ def emu():
                            "-o", LIB, os.path.join(ROOT, "tools", "emu", "emu_atom_epn.cpp")])
     lib = C.CDLL(LIB)
     lib.emu_atom_kernel.argtypes = [C.c_int] * 4 + [C.c_void_p] * 18
+    lib.emu_atom_const_kernel.argtypes = [C.c_int] * 4 + [C.c_void_p] * 18
     lib.emu_epn_pair_kernel.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
     return lib
 
@@ -46,7 +47,8 @@ def _lists(protein, mixed, rng):
     return L, npad
 
 
-def test_emulated_atom_kernel_modes(emu, protein, mixed):
+@pytest.mark.parametrize("kernel", ["emu_atom_kernel", "emu_atom_const_kernel"])     # default kernel; experimental atom-per-thread variant
+def test_emulated_atom_kernel_modes(emu, protein, mixed, kernel):
     rng = np.random.default_rng(21)
     L, npad = _lists(protein, mixed, rng)
     n = L["n"]
@@ -70,7 +72,7 @@ def test_emulated_atom_kernel_modes(emu, protein, mixed):
     def run(mode, h_is_zero=0, q=q0):
         l2 = l2_prev.copy(); h = np.full((n, 48), np.nan, np.float32); u = np.full((n, 32), np.nan, np.float32); v = u.copy()
         qd = q.copy(); qo = np.full(n, np.nan, np.float32); qo64 = np.full(n, np.nan)
-        assert emu.emu_atom_kernel(mode, h_is_zero, n, nsplit, _p(wu), _p(wp), _p(L["atom_sys"]), _p(L["offs"]), _p(L["npad"]), _p(L["sp"]),
+        assert getattr(emu, kernel)(mode, h_is_zero, n, nsplit, _p(wu), _p(wp), _p(L["atom_sys"]), _p(L["offs"]), _p(L["npad"]), _p(L["sp"]),
                                    _p(S), _p(h), _p(l2), _p(rowptr), _p(col), _p(pid), _p(delta), _p(qd), _p(u), _p(v), _p(qo), _p(qo64)) == 0
         return dict(l2=l2, h=h, u=u, v=v, q=qd, qo=qo, qo64=qo64)
 

@@ -4,6 +4,7 @@
 #define EPNN_CPU_EMU 1
 #include "../../epnn_b200/csrc/epnn_atom.cu"
 #include "../../epnn_b200/csrc/epnn_epn.cu"
+#include "../../epnn_b200/csrc/epnn_atom_const.cu"
 
 // wu: HG[64*32] | cb[32] | g[32] | U2[32*32] | c2[32] | U3[32*48] | c3[48]        (update side, already folded)
 // wp: Pf[32*64] | Aq64[64] | Ax[16*64]                                            (projection side of the NEXT pair kernel)
@@ -24,6 +25,27 @@ extern "C" int emu_atom_kernel(int mode, int h_is_zero, int n_atoms, int nsplit,
     constexpr int NW = 4;
     const size_t smem = sizeof(float) * (ATOM_W_UPD + ATOM_W_PROJ + (size_t)NW * ATOM_TILE + NW * 64) + sizeof(int) * NW * 64;
     emu_launch_grid(2, NW, smem / sizeof(float) + 8, [&] { atom_kernel<float, NW>(aa); });
+    return 0;
+}
+
+// the experimental atom-per-thread variant (epnn_atom_const.cu), same inputs
+extern "C" int emu_atom_const_kernel(int mode, int h_is_zero, int n_atoms, int nsplit, const float* wu, const float* wp,
+                                     const int* atom_sys, const int* sys_off, const int* npad, const int* species,
+                                     const float* Spart, float* h, float* l2, const int* rowptr, const int* col, const int* pid,
+                                     const float* delta, double* q, float* u, float* v, float* q_out, double* q_out64) {
+    AtomW W;
+    const float* p = wu;
+    memcpy(W.HG, p, sizeof(W.HG)); p += 64 * HID; memcpy(W.cb, p, sizeof(W.cb)); p += HID; memcpy(W.g, p, sizeof(W.g)); p += HID;
+    memcpy(W.U2, p, sizeof(W.U2)); p += HID * HID; memcpy(W.c2, p, sizeof(W.c2)); p += HID;
+    memcpy(W.U3, p, sizeof(W.U3)); p += HID * HD; memcpy(W.c3, p, sizeof(W.c3));
+    memcpy(W.Pf, wp, sizeof(W.Pf)); memcpy(W.Aq, wp + HID * 64, sizeof(W.Aq));
+    AtomConstArgs aa;
+    memset(&aa, 0, sizeof(aa));
+    aa.n_atoms = n_atoms; aa.mode = mode; aa.nsplit = nsplit; aa.h_is_zero = h_is_zero;
+    aa.atom_sys = atom_sys; aa.sys_off = sys_off; aa.npad = npad; aa.species = species;
+    aa.Spart = Spart; aa.h = h; aa.l2 = l2; aa.rowptr = rowptr; aa.col = col; aa.pid = pid; aa.delta = delta; aa.q = q;
+    aa.Ax = wp + HID * 64 + 64; aa.u = u; aa.v = v; aa.q_out = q_out; aa.q_out64 = q_out64;
+    emu_launch_grid(2, ACONST_NW, (size_t)ACONST_NW * 32 * ATS, [&] { atom_const_kernel(W, aa); });
     return 0;
 }
 
