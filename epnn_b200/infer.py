@@ -38,7 +38,15 @@ def main(argv=None):
                                                          "exactly like the reference loop (slow; default = packed fast path)")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
+    ap.add_argument("--option", action="append", default=[], metavar="KEY=VALUE",
+                    help="engine option (epnn_set_option), e.g. gnn_far_tensor=1, pair_tensor=1, dedup_far=0; repeatable")
     args = ap.parse_args(argv)
+    options = []
+    for kv in args.option:
+        k, sep, v = kv.partition("=")
+        if not sep:
+            raise SystemExit(f"--option expects KEY=VALUE, got {kv!r}")
+        options.append((k, float(v)))
     h_dim, e_dim, layers = 48, 48, [32, 32]                           # infer.py:38-40
     w = load_weights(args.weights)
     T, n_elems = w.T, w.n_x
@@ -49,6 +57,8 @@ def main(argv=None):
         timeB = time.time()
         model = charge_gn.make_model(layers, h_dim, T, n_elems, x.shape[1], device=args.device, precision=args.precision)
         model.load_weights(args.weights)
+        for k, v in options:
+            model.engine.set_option(k, v)
         np.save("test_names.npy", names, allow_pickle=True)
         test_preds = []
         timeC = timeD = time.time()
@@ -73,6 +83,8 @@ def main(argv=None):
         N = args.npad or int(sizes_all.max())
         model = charge_gn.make_model(layers, h_dim, T, n_elems, N, device=args.device, precision=args.precision)
         model.load_weights(args.weights)
+        for k, v in options:
+            model.engine.set_option(k, v)
         np.save("test_names.npy", names, allow_pickle=True)
         runs = []
         timeC = timeD = time.time()
