@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "epnn_internal.cuh"
+#include "epnn_pack.h"
 
 #define EPNN_VERSION_STR "epnn_b200 0.1.0 sm_100a"
 
@@ -17,13 +18,6 @@
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
-};
-
-struct PackedOffsets {           // element offsets into the packed device weight buffer (same for float/double)
-    struct Step { size_t Ah64, Aq64, Ax64, Wx64, Cw, Cw16, b1, W2, b2, W3, b3, Pf, Axf, HG, g; };
-    std::vector<Step> msg, pas;
-    size_t U1, c1, U2, c2, U3, c3, cb1;
-    size_t total;
 };
 
 struct epnn_ctx {
@@ -91,143 +85,10 @@ static int ensure(epnn_ctx* c, int which, size_t bytes, void** out) {
     return EPNN_OK;
 }
 
-// ------------------------------------------------------------------------------------------------
-static const double Z9[8] = {1, 6, 7, 8, 9, 16, 17, 35};            // infer.py:13-30
-static const double Z10[9] = {1, 6, 7, 8, 9, 15, 16, 17, 35};       // charge_gn.py:9-28
-
-static size_t expected_floats(int T, int n_x) {
-    const size_t K = 2 * (size_t)(n_x + 49) + 48;
-    const size_t msg = K * 32 + 32 + 32 * 32 + 32 + 32 * 32 + 32;
-    const size_t upd = 80 * 32 + 32 + 32 * 32 + 32 + 32 * 48 + 48;
-    const size_t pas = K * 32 + 32 + 32 * 32 + 32 + 32 + 1;
-    return T * msg + upd + T * pas;
-}
-
-static size_t take(size_t& cur, size_t n) { size_t o = cur; cur += (n + 7) & ~(size_t)7; return o; }
-
-// Split one first-layer kernel W1[K][32] (+b1) into the per-atom / per-pair blocks.
-static void pack_step(std::vector<double>& P, const PackedOffsets::Step& o, const float* W1, const float* b1, int n_x,
-                      const double* Z, int n_species, const double* basis) {
-    const int F = n_x + 49;
-    for (int r = 0; r < EDR; ++r)                 // C' = B^T C: e-rows of the first layer in the reduced descriptor basis
-        for (int c = 0; c < 32; ++c) {
-            double s = 0.0;
-            for (int k = 0; k < 48; ++k) s += basis[k * EDR + r] * (double)W1[(2 * F + k) * 32 + c];
-            P[o.Cw16 + r * 32 + c] = s;
-        }
-    for (int k = 0; k < 48; ++k)
-        for (int c = 0; c < 32; ++c) {
-            P[o.Ah64 + k * 64 + c] = W1[(n_x + k) * 32 + c];
-            P[o.Ah64 + k * 64 + 32 + c] = W1[(F + n_x + k) * 32 + c];
-            P[o.Cw + k * 32 + c] = W1[(2 * F + k) * 32 + c];
-        }
-    for (int c = 0; c < 32; ++c) {
-        P[o.Aq64 + c] = W1[(n_x + 48) * 32 + c];
-        P[o.Aq64 + 32 + c] = W1[(F + n_x + 48) * 32 + c];
-        P[o.b1 + c] = b1[c];
-    }
-    for (int f = 0; f < n_x; ++f)                 // raw x-rows (dense compatibility path: arbitrary x features)
-        for (int c = 0; c < 32; ++c) {
-            P[o.Wx64 + f * 64 + c] = W1[f * 32 + c];
-            P[o.Wx64 + f * 64 + 32 + c] = W1[(F + f) * 32 + c];
-        }
-    for (int s = 0; s < n_species; ++s)
-        for (int c = 0; c < 32; ++c) {
-            P[o.Ax64 + s * 64 + c] = Z[s] * (double)W1[c] + (double)W1[(1 + s) * 32 + c];
-            P[o.Ax64 + s * 64 + 32 + c] = Z[s] * (double)W1[F * 32 + c] + (double)W1[(F + 1 + s) * 32 + c] + (double)b1[c];
-        }
-}
-
-template <typename R> static StepW<R> step_view(const R* base, const PackedOffsets::Step& o) {
-    StepW<R> s;
-    s.Ah64 = base + o.Ah64; s.Aq64 = base + o.Aq64; s.Ax64 = base + o.Ax64; s.b1 = base + o.b1;
-    s.Cw = base + (sizeof(R) == 4 ? o.Cw16 : o.Cw);      // FP32 pair kernels work in the reduced descriptor basis
-    s.W2 = base + o.W2; s.b2 = base + o.b2; s.W3 = base + o.W3; s.b3 = base + o.b3;
-    s.Pf = base + o.Pf; s.Axf = base + o.Axf; s.HG = base + o.HG; s.g = base + o.g;
-    return s;
-}
-template <typename R> static DenseW<R> dense_view(const R* base, const PackedOffsets::Step& o) {
-    DenseW<R> d;
-    d.Wx64 = base + o.Wx64; d.Ah64 = base + o.Ah64; d.Aq64 = base + o.Aq64; d.Cw = base + o.Cw; d.b1 = base + o.b1;
-    d.W2 = base + o.W2; d.b2 = base + o.b2; d.W3 = base + o.W3; d.b3 = base + o.b3;
-    return d;
-}
-template <typename R> static UpdW<R> upd_view(const R* base, const PackedOffsets& po) {
-    UpdW<R> u;
-    u.U1 = base + po.U1; u.c1 = base + po.c1; u.U2 = base + po.U2; u.c2 = base + po.c2; u.U3 = base + po.U3; u.c3 = base + po.c3;
-    u.cb1 = base + po.cb1;
-    return u;
-}
-
 extern "C" int epnn_rbf_centers(double* mu) {
     if (!mu) return EPNN_E_INVALID;
-    // numpy.linspace(0.1, 3.0, 48): step = (stop-start)/47; y = arange(48)*step + start; y[-1] = stop
-    volatile double step = (3.0 - 0.1) / 47.0;
-    for (int k = 0; k < 48; ++k) {
-        volatile double prod = (double)k * step;      // volatile: forbid FMA contraction of k*step + start
-        mu[k] = prod + 0.1;
-    }
-    mu[47] = 3.0;
+    rbf_centers_impl(mu);
     return EPNN_OK;
-}
-
-// Orthonormal basis of the family of radial descriptors e(D) = C(D) exp(-2 (D - mu_k)^2), k < 48, D in [0, 3).
-// The 48 Gaussians (width 0.5 A, spacing 0.062 A) overlap so strongly that the family has numerical rank 16 at float32
-// precision: the best rank-16 subspace misses at most 5e-10 of any e(D) (max |e| = 1; rank 20: 1e-13, rank 24: 3e-15),
-// far below the 6e-8 float32 rounding the reference applies to e.  The FP32 kernels therefore carry the 16 coefficients
-// B^T e instead of the 48 values and use B^T C as first-layer rows.  B = leading eigenvectors of the Gram matrix of e over
-// a uniform D grid (cyclic Jacobi in float64: deterministic, no library needed).
-static void compute_rbf_basis(double* B) {
-    // One-sided (Hestenes) Jacobi SVD of the sampled family E[m][k] = e_k(D_m): rotations orthogonalise the columns of E
-    // and accumulate in V; unlike an eigen-decomposition of the Gram matrix it resolves the small singular values
-    // (sigma_16 / sigma_1 ~ 1e-9) to high relative accuracy.
-    double mu[ED];
-    epnn_rbf_centers(mu);
-    const int NG = 2048;
-    std::vector<double> A((size_t)NG * ED), V((size_t)ED * ED, 0.0);
-    for (int m = 0; m < NG; ++m) {
-        const double D = (m + 0.5) * 3.0 / NG;
-        const double C = (cos(3.141592653589793 * D / 3.0) + 1.0) / 2.0;
-        for (int k = 0; k < ED; ++k) A[(size_t)k * NG + m] = C * exp(-2.0 * (D - mu[k]) * (D - mu[k]));      // column-major
-    }
-    for (int k = 0; k < ED; ++k) V[(size_t)k * ED + k] = 1.0;
-    for (int sweep = 0; sweep < 40; ++sweep) {
-        bool rotated = false;
-        for (int p = 0; p < ED; ++p)
-            for (int q = p + 1; q < ED; ++q) {
-                double* ap = &A[(size_t)p * NG];
-                double* aq = &A[(size_t)q * NG];
-                double alpha = 0.0, beta = 0.0, gamma = 0.0;
-                for (int m = 0; m < NG; ++m) { alpha += ap[m] * ap[m]; beta += aq[m] * aq[m]; gamma += ap[m] * aq[m]; }
-                if (fabs(gamma) <= 1e-15 * sqrt(alpha * beta) || gamma == 0.0) continue;
-                rotated = true;
-                const double zeta = (beta - alpha) / (2.0 * gamma);
-                const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-                const double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
-                for (int m = 0; m < NG; ++m) { const double x = ap[m], y = aq[m]; ap[m] = cs * x - sn * y; aq[m] = sn * x + cs * y; }
-                double* vp = &V[(size_t)p * ED];
-                double* vq = &V[(size_t)q * ED];
-                for (int k = 0; k < ED; ++k) { const double x = vp[k], y = vq[k]; vp[k] = cs * x - sn * y; vq[k] = sn * x + cs * y; }
-            }
-        if (!rotated) break;
-    }
-    double norm[ED];
-    int order[ED];
-    for (int k = 0; k < ED; ++k) {
-        double s2 = 0.0;
-        for (int m = 0; m < NG; ++m) s2 += A[(size_t)k * NG + m] * A[(size_t)k * NG + m];
-        norm[k] = s2; order[k] = k;
-    }
-    for (int i = 0; i < ED; ++i)                      // selection sort by singular value, descending
-        for (int j = i + 1; j < ED; ++j)
-            if (norm[order[j]] > norm[order[i]]) { const int t = order[i]; order[i] = order[j]; order[j] = t; }
-    for (int r = 0; r < EDR; ++r) {
-        const double* v = &V[(size_t)order[r] * ED];  // right singular vector r (stored as a row of V here)
-        double sgn = 0.0;
-        for (int k = 0; k < ED; ++k) sgn += v[k];
-        sgn = sgn < 0 ? -1.0 : 1.0;                   // fixed sign convention
-        for (int k = 0; k < ED; ++k) B[k * EDR + r] = sgn * v[k];
-    }
 }
 
 extern "C" int epnn_rbf_basis(double* B) {
@@ -284,42 +145,10 @@ extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_
     epnn_rbf_basis(basis.data());
     CUC(upload_rbf_basis(basis.data()));
 
-    // ---- pack
+    // ---- pack + fold (epnn_pack.h)
     PackedOffsets& po = c->po;
-    size_t cur = 0;
-    auto step_offsets = [&](bool is_pass) {
-        PackedOffsets::Step o;
-        o.Ah64 = take(cur, 48 * 64); o.Aq64 = take(cur, 64); o.Ax64 = take(cur, MAX_SPECIES * 64); o.Wx64 = take(cur, 16 * 64);
-        o.Cw = take(cur, 48 * 32); o.Cw16 = take(cur, EDR * 32);
-        o.b1 = take(cur, 32); o.W2 = take(cur, 32 * 32); o.b2 = take(cur, 32);
-        o.W3 = take(cur, is_pass ? 32 : 32 * 32); o.b3 = take(cur, is_pass ? 1 : 32);
-        o.Pf = take(cur, 32 * 64); o.Axf = take(cur, MAX_SPECIES * 64);
-        o.HG = take(cur, is_pass ? 0 : 64 * 32); o.g = take(cur, is_pass ? 0 : 32);
-        return o;
-    };
-    for (int t = 0; t < T; ++t) po.msg.push_back(step_offsets(false));
-    po.U1 = take(cur, 80 * 32); po.c1 = take(cur, 32); po.U2 = take(cur, 32 * 32); po.c2 = take(cur, 32);
-    po.U3 = take(cur, 32 * 48); po.c3 = take(cur, 48); po.cb1 = take(cur, 32);
-    for (int t = 0; t < T; ++t) po.pas.push_back(step_offsets(true));
-    po.total = cur;
-    std::vector<double> P(po.total, 0.0);
-    const int K = 2 * (n_x + 49) + 48;
-    const double* Z = n_x == 9 ? Z9 : Z10;
-    const float* r = w;
-    auto copy = [&](size_t off, size_t n) { for (size_t i = 0; i < n; ++i) P[off + i] = r[i]; r += n; };
-    for (int t = 0; t < T; ++t) {
-        const float* W1 = r; const float* b1 = r + (size_t)K * 32;
-        pack_step(P, po.msg[t], W1, b1, n_x, Z, c->n_species, basis.data());
-        r += (size_t)K * 32 + 32;
-        copy(po.msg[t].W2, 32 * 32); copy(po.msg[t].b2, 32); copy(po.msg[t].W3, 32 * 32); copy(po.msg[t].b3, 32);
-    }
-    copy(po.U1, 80 * 32); copy(po.c1, 32); copy(po.U2, 32 * 32); copy(po.c2, 32); copy(po.U3, 32 * 48); copy(po.c3, 48);
-    for (int t = 0; t < T; ++t) {
-        const float* W1 = r; const float* b1 = r + (size_t)K * 32;
-        pack_step(P, po.pas[t], W1, b1, n_x, Z, c->n_species, basis.data());
-        r += (size_t)K * 32 + 32;
-        copy(po.pas[t].W2, 32 * 32); copy(po.pas[t].b2, 32); copy(po.pas[t].W3, 32); copy(po.pas[t].b3, 1);
-    }
+    std::vector<double> P;
+    pack_all(T, n_x, c->n_species, w, basis.data(), po, P);
     {   // 3xTF32 split of W2^T for the tensor-core far kernel: hi = W with the low 13 mantissa bits cleared, lo = W - hi
         std::vector<float> ws((size_t)T * 2 * 32 * 32);
         for (int t = 0; t < T; ++t)
@@ -333,44 +162,6 @@ extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_
                 }
         CUC(cudaMalloc(&c->w2split, ws.size() * sizeof(float)));
         CUC(cudaMemcpy(c->w2split, ws.data(), ws.size() * sizeof(float), cudaMemcpyHostToDevice));
-    }
-    {   // fold the linear layers around the update MLP (float64, exact algebra): see StepW / UpdW
-        const double* U1 = &P[po.U1]; const double* U3 = &P[po.U3]; const double* c3 = &P[po.c3]; const double* c1 = &P[po.c1];
-        for (int c = 0; c < 32; ++c) {                               // cb1 = c1 + U1_h^T c3
-            double sacc = c1[c];
-            for (int k = 0; k < 48; ++k) sacc += U1[k * 32 + c] * c3[k];
-            P[po.cb1 + c] = sacc;
-        }
-        auto fold_proj = [&](const PackedOffsets::Step& o) {        // Pf = U3 . Ah64 ; Axf = Ax64 + c3^T Ah64
-            for (int r = 0; r < 32; ++r)
-                for (int c = 0; c < 64; ++c) {
-                    double sacc = 0.0;
-                    for (int k = 0; k < 48; ++k) sacc += U3[r * 48 + k] * P[o.Ah64 + k * 64 + c];
-                    P[o.Pf + r * 64 + c] = sacc;
-                }
-            for (int c = 0; c < 64; ++c) {
-                double sacc = 0.0;
-                for (int k = 0; k < 48; ++k) sacc += c3[k] * P[o.Ah64 + k * 64 + c];
-                for (int sp = 0; sp < MAX_SPECIES; ++sp) P[o.Axf + sp * 64 + c] = P[o.Ax64 + sp * 64 + c] + sacc;
-            }
-        };
-        for (int t = 0; t < T; ++t) {
-            fold_proj(po.msg[t]); fold_proj(po.pas[t]);
-            const PackedOffsets::Step& o = po.msg[t];
-            for (int r = 0; r < 32; ++r)
-                for (int c = 0; c < 32; ++c) {
-                    double h1 = 0.0, gg = 0.0;
-                    for (int k = 0; k < 48; ++k) h1 += U3[r * 48 + k] * U1[k * 32 + c];                        // (U3 . U1_h)[r][c]
-                    for (int k = 0; k < 32; ++k) gg += P[o.W3 + r * 32 + k] * U1[(48 + k) * 32 + c];           // (W3 . U1_M)[r][c]
-                    P[o.HG + r * 32 + c] = h1;
-                    P[o.HG + (32 + r) * 32 + c] = gg;
-                }
-            for (int c = 0; c < 32; ++c) {
-                double sacc = 0.0;
-                for (int k = 0; k < 32; ++k) sacc += P[o.b3 + k] * U1[(48 + k) * 32 + c];                      // U1_M^T b3
-                P[o.g + c] = sacc;
-            }
-        }
     }
     std::vector<float> Pf(po.total);
     for (size_t i = 0; i < po.total; ++i) Pf[i] = (float)P[i];
