@@ -28,18 +28,26 @@ struct EpnMmaArgs {
     float* delta;
 };
 
+#ifdef EPNN_CPU_EMU
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) { emu_mma_m16n8k8_tf32(d, a, b); }
+#else
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
+#endif
 __device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo) {
     hi = __float_as_uint(x) & 0xFFFFE000u;
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 __global__ void __launch_bounds__(MMA_NW * 32, 1) bundle_epn_mma_kernel(const EpnMmaArgs a) {
+#ifdef EPNN_CPU_EMU
+    float* s_uv = emu_smem;
+#else
     extern __shared__ __align__(16) float s_uv[];             // [MMA_NW][BUNDLE_ATOMS * UVS]
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     float* uv = s_uv + warp * (BUNDLE_ATOMS * UVS);
     // ---- weights -> register-resident B fragments (b0 = (k position t, column g), b1 = (k position t + 4, column g))
@@ -180,6 +188,7 @@ __global__ void __launch_bounds__(MMA_NW * 32, 1) bundle_epn_mma_kernel(const Ep
     }
 }
 
+#ifndef EPNN_CPU_EMU
 cudaError_t launch_epn_bundle_mma(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* nl) {
     if (w.n_bundles == 0) return cudaSuccess;
     EpnMmaArgs ea;
@@ -199,3 +208,4 @@ cudaError_t launch_epn_bundle_mma(const Workspace& w, const StepW<float>& sw, cu
     ++*nl;
     return cudaGetLastError();
 }
+#endif

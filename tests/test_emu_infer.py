@@ -1,8 +1,9 @@
 """A WHOLE charge inference on the CPU through the product's own code: weights packed and folded by epnn_pack.h (what
 epnn_create runs), then every kernel of the FP32 path -- neighbour list, descriptors, far lists, bundle kernels, row-group
 kernels, per-atom kernel -- executed by the warp emulation (tools/emu/emu_infer.cpp) in run_chunk's launch order.
-Compared with the float64 oracle and with the reference's own shipped predictions.  Also run with pair_const = 1: the
-experimental pair-per-thread kernels (epnn_bundle_const.cu, epnn_atom_const.cu), which have not been on a GPU yet.
+Compared with the float64 oracle and with the reference's own shipped predictions.  Also run with the experimental
+pair-per-thread kernels (epnn_bundle_const.cu, epnn_atom_const.cu), which have not been on a GPU yet, and with the
+mma.sync electron-passing kernel (epnn_bundle_mma.cu; its fragment layout is emulated lane by lane).
 This is test infrastructure, not a fallback: nothing in epnn_b200/ can reach it."""
 import ctypes as C
 import os
@@ -46,7 +47,7 @@ def _infer(emu, w, offs, xyz, sp, Q, npad, pair_const=0, dedup=1):
     return q32, q64, h, int(rows[0])
 
 
-@pytest.mark.parametrize("pair_const", [0, 1])
+@pytest.mark.parametrize("pair_const", [0, 1, 2])      # 0 default kernels, 1 experimental pair_const, 2 pair_tensor (mma.sync EPN kernel)
 def test_emulated_inference_reproduces_shipped_predictions(emu, weights, mixed, val871, pair_const):
     """decay_model_weights, pad 41: the reference's own predictions (models/model_systems/test_pred_charges.npy)."""
     w = weights["decay_model_weights"]
@@ -63,7 +64,7 @@ def test_emulated_inference_reproduces_shipped_predictions(emu, weights, mixed, 
 
 
 @pytest.mark.parametrize("name", ["model2_weights", "model_weights"])
-@pytest.mark.parametrize("pair_const", [0, 1])
+@pytest.mark.parametrize("pair_const", [0, 1, 2])
 def test_emulated_inference_live_checkpoints(emu, weights, mixed, name, pair_const):
     """Checkpoints whose hidden state is live: charges AND the GNN-layer output against the oracle (only step 0 collapses)."""
     w = weights[name]

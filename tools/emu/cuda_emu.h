@@ -30,6 +30,9 @@
 
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 struct alignas(16) ulonglong2 { unsigned long long x, y; };
 struct int2 { int x, y; };
 inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
@@ -91,6 +94,32 @@ inline unsigned __ballot_sync(unsigned, int pred) {
     for (int l = 0; l < 32; ++l) m |= emu_warp->xbuf[l] << l;
     emu_warp->bar.wait();
     return m;
+}
+inline void emu_allgather32(unsigned v, unsigned (&out)[32]) {     // every lane's 32-bit value, seen by every lane
+    emu_warp->xbuf[EPNN_EMU_LANE] = v;
+    emu_warp->bar.wait();
+    for (int l = 0; l < 32; ++l) out[l] = emu_warp->xbuf[l];
+    emu_warp->bar.wait();
+}
+// mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 (D = A B + D) with the PTX fragment layout: g = lane >> 2, t = lane & 3,
+// a0 (g, t) a1 (g + 8, t) a2 (g, t + 4) a3 (g + 8, t + 4); b0 (k = t, n = g) b1 (k = t + 4, n = g);
+// d0 (g, 2t) d1 (g, 2t + 1) d2 (g + 8, 2t) d3 (g + 8, 2t + 1).  TF32 inputs: the low 13 mantissa bits are ignored.
+inline void emu_mma_m16n8k8_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    unsigned A[4][32], B[2][32];
+    for (int r = 0; r < 4; ++r) emu_allgather32(a[r] & 0xFFFFE000u, A[r]);
+    for (int r = 0; r < 2; ++r) emu_allgather32(b[r] & 0xFFFFE000u, B[r]);
+    const int g = EPNN_EMU_LANE >> 2, t = EPNN_EMU_LANE & 3;
+    for (int i = 0; i < 4; ++i) {
+        const int row = g + 8 * (i >> 1), col = 2 * t + (i & 1);
+        float acc = d[i];
+        for (int k = 0; k < 8; ++k) {
+            float av, bv;
+            std::memcpy(&av, &A[(row >= 8) + 2 * (k >= 4)][4 * (row & 7) + (k & 3)], 4);
+            std::memcpy(&bv, &B[k >= 4][4 * col + (k & 3)], 4);
+            acc = std::fmaf(av, bv, acc);
+        }
+        d[i] = acc;
+    }
 }
 inline int __ffs(unsigned x) { return __builtin_ffs((int)x); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }

@@ -1,9 +1,9 @@
 // CPU emulation of a WHOLE charge inference through the product's own kernels (test infrastructure; see cuda_emu.h).
 //
 // Weights are packed / folded by the product's own host code (epnn_pack.h, the code epnn_create runs); then the kernels
-// of epnn_neighbor / epnn_bundle / epnn_gnn / epnn_epn / epnn_atom (and, with pair_const = 1, epnn_bundle_const /
-// epnn_atom_const) run in the launch order of run_chunk (epnn_api.cu), FP32, one chunk.  The only code that is not the
-// product's is this orchestration (a restatement of run_chunk without streams and workspaces) and two host-side scans.
+// of epnn_neighbor / epnn_bundle / epnn_gnn / epnn_epn / epnn_atom (and, with variant = 1, epnn_bundle_const /
+// epnn_atom_const; with variant = 2, the mma.sync electron-passing kernel epnn_bundle_mma) run in the launch order of
+// run_chunk (epnn_api.cu), FP32, one chunk.  The only code that is not the product's is this orchestration (a restatement of run_chunk without streams and workspaces) and two host-side scans.
 // tests/test_emu_infer.py compares the result with the oracle and with the reference's shipped predictions.
 // Build: g++ -O1 -std=c++17 -ffp-contract=off -shared -fPIC -pthread -DEPNN_CPU_EMU -o build/libemu_infer.so tools/emu/emu_infer.cpp
 #define EPNN_CPU_EMU 1
@@ -30,13 +30,17 @@ namespace k_bconst {
 namespace k_aconst {
 #include "../../epnn_b200/csrc/epnn_atom_const.cu"
 }
+namespace k_mma {
+#include "../../epnn_b200/csrc/epnn_bundle_mma.cu"
+}
 
 static void exclusive_scan(const int* in, int* out, int n) { int s = 0; for (int i = 0; i < n; ++i) { out[i] = s; s += in[i]; } out[n] = s; }
 
 extern "C" int emu_infer(int T, int n_x, const float* w_packed, size_t n_w, int n_sys, const int* off, const float* xyz,
-                         const int* species, const float* Q, const int* npad_in, int pair_const, int dedup,
+                         const int* species, const float* Q, const int* npad_in, int variant, int dedup,
                          float* q_out, double* q_out64, float* h_out, long long* dedup_rows_out) {
     if (n_w != expected_floats(T, n_x)) return -1;
+    const int pair_const = variant == 1, pair_tensor = variant == 2;
     const int n = off[n_sys];
     const int n_species = n_x - 1;
     // ---------------------------------------------------------------- weights: the product's own packing and folding
@@ -188,6 +192,14 @@ extern "C" int emu_infer(int T, int n_x, const float* w_packed, size_t n_w, int 
     auto bundle = [&](bool epn, const StepW<float>& sw) {
         if (!n_bundles) return;
         work_counter = 0;
+        if (pair_tensor && epn) {
+            k_mma::EpnMmaArgs a;
+            a.n_bundles = n_bundles; a.bundle = bundles.data(); a.work_counter = &work_counter;
+            a.ustart = ustart.data(); a.pair_i = pair_i.data(); a.pair_j = pair_j.data(); a.near = near.data(); a.e = e.data();
+            a.u = u.data(); a.v = v.data(); a.Cw = sw.Cw; a.W2 = sw.W2; a.b2 = sw.b2; a.w3 = sw.W3; a.delta = delta.data();
+            emu_launch_cta(MMA_NW, (size_t)MMA_NW * BUNDLE_ATOMS * UVS, [&] { k_mma::bundle_epn_mma_kernel(a); });
+            return;
+        }
         if (pair_const) {
             k_bconst::PairW W;
             memcpy(W.Cw, sw.Cw, sizeof(W.Cw)); memcpy(W.W2, sw.W2, sizeof(W.W2)); memcpy(W.b2, sw.b2, sizeof(W.b2));
