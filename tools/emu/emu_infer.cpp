@@ -3,7 +3,8 @@
 // Weights are packed / folded by the product's own host code (epnn_pack.h, the code epnn_create runs); then the kernels
 // of epnn_neighbor / epnn_bundle / epnn_gnn / epnn_epn / epnn_atom (and, with variant = 1, epnn_bundle_const /
 // epnn_atom_const; with variant = 2, the mma.sync electron-passing kernel epnn_bundle_mma) run in the launch order of
-// run_chunk (epnn_api.cu), FP32, one chunk.  The only code that is not the product's is this orchestration (a restatement of run_chunk without streams and workspaces) and two host-side scans.
+// run_chunk (epnn_api.cu), FP32, one chunk.  The only code that is not the product's is this orchestration (a
+// restatement of run_chunk without streams and workspaces) and two host-side scans.
 // tests/test_emu_infer.py compares the result with the oracle and with the reference's shipped predictions.
 // Build: g++ -O1 -std=c++17 -ffp-contract=off -shared -fPIC -pthread -DEPNN_CPU_EMU -o build/libemu_infer.so tools/emu/emu_infer.cpp
 #define EPNN_CPU_EMU 1
