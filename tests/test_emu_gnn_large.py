@@ -61,14 +61,14 @@ def test_emulated_large_gnn_kernel_with_and_without_dedup(emu, protein, mixed, n
     large = np.concatenate([np.arange(offs[s], offs[s + 1]) for s in (0, 2, 3)])
     n_tab = n_rg // 8 + 2
     emu.emu_gnn_large_step.argtypes = ([C.c_void_p] + [C.c_int] * 3 + [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 12 +
-                                       [C.c_int] * 3 + [C.c_void_p] * 4)
+                                       [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_int] * 2)
     for stamp in (0, 2):
         S = np.zeros((nsplit, L["n"], 32), np.float32)
         tab = np.zeros(n_tab * 32, np.int32); st = np.zeros(n_tab * 2, np.int32); rows = np.zeros(1, np.uint64)
         rc = emu.emu_gnn_large_step(_p(wts), L["n"], L["n_sys"], n_rg, _p(rg), nsplit, 0,
                                     _p(L["atom_sys"]), _p(L["offs"]), _p(L["npad"]), _p(L["sp"]), _p(rgl_off),
                                     _p(rowptr), _p(col), _p(pid), _p(deg), _p(L["coef"]), _p(L["u"]), _p(L["v"]),
-                                    stamp, n_x - 1, n_tab, _p(tab), _p(st), _p(rows), _p(S))
+                                    stamp, n_x - 1, n_tab, _p(tab), _p(st), _p(rows), _p(S), 0, 1)
         assert rc == 0
         tot = S.astype(np.float64).sum(axis=0)                          # the per-atom kernel adds the planes in this order
         err = np.abs(tot[large] - ref[large]).max() / np.abs(ref[large]).max()
@@ -80,3 +80,35 @@ def test_emulated_large_gnn_kernel_with_and_without_dedup(emu, protein, mixed, n
             assert all(t0[16 + k] == np.nonzero(sp[:150] == k)[0][0] for k in range(16) if t0[k])   # first atom per species
             if nsplit > 1:                                              # collapsed systems leave the other planes at zero
                 assert np.abs(S[1:, :150]).max() == 0.0
+
+
+def test_emulated_sharded_large_gnn_is_bit_identical(emu, protein, mixed):
+    """epnn_set_shard splits the row-group x plane units of this kernel into contiguous ranges, zero-fills the rest and
+    all-reduces: the partial buffers of the ranks must add up to the single-rank buffer BIT FOR BIT (each element is
+    written by exactly one rank), with the de-duplication on."""
+    rng = np.random.default_rng(14)
+    offs, xyz, sp = _system(protein, mixed, 9, rng, False)
+    sizes = np.diff(offs)
+    npad = np.array([sizes[0] + 6, 41, sizes[2], sizes[3] + 1], np.int32)
+    L = build_lists_raw(offs, xyz, sp, npad, rng, equal_v_systems=[0])
+    rowptr, col = csr(L)
+    rg, n_rg, rgl_off, pid, deg = large_system_tables(L)
+    W = weights(rng)
+    wts = np.concatenate([W["Cw"].ravel(), W["W2"].ravel(), W["b2"], W["x32"]]).astype(np.float32)
+    n_tab, nsplit = n_rg // 8 + 2, 3
+    emu.emu_gnn_large_step.argtypes = ([C.c_void_p] + [C.c_int] * 3 + [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 12 +
+                                       [C.c_int] * 3 + [C.c_void_p] * 4 + [C.c_int] * 2)
+
+    def run(rank, world):
+        S = np.zeros((nsplit, L["n"], 32), np.float32)
+        tab = np.zeros(n_tab * 32, np.int32); st = np.zeros(n_tab * 2, np.int32); rows = np.zeros(1, np.uint64)
+        assert emu.emu_gnn_large_step(_p(wts), L["n"], L["n_sys"], n_rg, _p(rg), nsplit, 0, _p(L["atom_sys"]), _p(L["offs"]), _p(L["npad"]),
+                                      _p(L["sp"]), _p(rgl_off), _p(rowptr), _p(col), _p(pid), _p(deg), _p(L["coef"]), _p(L["u"]), _p(L["v"]),
+                                      1, 8, n_tab, _p(tab), _p(st), _p(rows), _p(S), rank, world) == 0
+        return S
+
+    single = run(0, 1)
+    for world in (2, 3):
+        parts = [run(r, world) for r in range(world)]
+        assert sum((p != 0).astype(int) for p in parts).max() <= 1          # disjoint support
+        assert np.array_equal(sum(parts), single)

@@ -11,7 +11,7 @@ extern "C" int emu_gnn_large_step(const float* weights, int n_atoms, int n_sys, 
                                   const int* atom_sys, const int* sys_off, const int* npad, const int* species, const int* rgl_off,
                                   const int* rowptr, const int* col, const int* pid, const int* deg, const float* e,
                                   const float* u, const float* v, int stamp, int n_species, int n_sp_tab, int* sp_tab, int* sp_stamp,
-                                  unsigned long long* dedup_rows, float* S) {
+                                  unsigned long long* dedup_rows, float* S, int shard_rank, int shard_world) {
     if (stamp) {                      // species tables + this step's equality check, exactly as launch_sp_tab_build / launch_sp_check
         emu_launch_simple(div_up((int64_t)n_sp_tab * 32, 256), 256, [&] { sp_tab_init_kernel(n_sp_tab, sp_tab, sp_stamp); });
         emu_launch_grid(div_up(n_atoms, 256), 8, 0, [&] { sp_tab_fill_kernel(n_atoms, atom_sys, sys_off, species, rgl_off, deg, sp_tab, sp_stamp); });
@@ -20,7 +20,10 @@ extern "C" int emu_gnn_large_step(const float* weights, int n_atoms, int n_sys, 
         emu_launch_simple(div_up(n_sp_tab, 256), 256, [&] { sp_tally_kernel(n_sp_tab, sp_tab, sp_stamp, stamp, dedup_rows); });
     }
     GnnArgs<float> ga;
-    ga.rg_atom = rg_atom; ga.unit_begin = 0; ga.n_units = n_rg * nsplit; ga.nsplit = nsplit; ga.n_atoms = n_atoms;
+    // this rank's contiguous slice of the work units, as launch_gnn_pair computes it (world 1: everything)
+    const int64_t total = (int64_t)n_rg * nsplit;
+    ga.rg_atom = rg_atom; ga.unit_begin = (int)(total * shard_rank / shard_world); ga.n_units = (int)(total * (shard_rank + 1) / shard_world);
+    ga.nsplit = nsplit; ga.n_atoms = n_atoms;
     ga.skip_far = skip_far; ga.plane = 0;
     ga.atom_sys = atom_sys; ga.sys_off = sys_off; ga.npad = npad; ga.rowptr = rowptr; ga.col = col; ga.pid = pid; ga.e = e;
     ga.u = u; ga.v = v;
