@@ -99,3 +99,29 @@ def test_emulated_inference_with_a_large_system(emu, weights, mixed, protein, pa
     assert np.abs(q64 - ref).max() < 1e-5, np.abs(q64 - ref).max()
     assert np.abs(np.add.reduceat(q64, offs[:-1]) - Q).max() < 1e-6
     assert rows == (3 * 90 if dedup else 0)                              # 3 of the 5 steps collapse for this checkpoint
+
+
+@pytest.mark.parametrize("seed,pair_const", [(1, 0), (2, 0), (3, 1)])
+def test_emulated_inference_random_systems(emu, weights, seed, pair_const):
+    """Randomly sized synthetic systems (1 .. 48 atoms and a few larger ones, jittered-lattice geometries, random species
+    and net charges, padded and unpadded) -- tile and bundle boundaries fall wherever they fall."""
+    w = weights["model2_weights"]                     # T = 3, live hidden state
+    rng = np.random.default_rng(seed)
+    sizes = list(rng.integers(1, 49, size=7)) + [int(rng.integers(49, 80))] + list(rng.integers(1, 30, size=3))
+    rng.shuffle(sizes)
+    offs, xyz, sp = [0], [], []
+    for n in sizes:
+        side = int(np.ceil(n ** (1 / 3))) + 1
+        grid = np.stack(np.meshgrid(*[np.arange(side)] * 3, indexing="ij"), -1).reshape(-1, 3)
+        pts = grid[rng.permutation(len(grid))[:n]] * 1.3 + rng.normal(scale=0.12, size=(n, 3))
+        xyz.append(pts); sp.append(rng.integers(0, 8, size=n)); offs.append(offs[-1] + n)
+    offs = np.array(offs, np.int32)
+    xyz = np.concatenate(xyz).astype(np.float32)
+    sp = np.concatenate(sp).astype(np.int32)
+    Q = rng.integers(-2, 3, size=len(sizes)).astype(np.float32)
+    npad = np.array([n if k % 2 else n + int(rng.integers(1, 12)) for k, n in enumerate(sizes)], np.int32)
+    q32, q64, _, _ = _infer(emu, w, offs, xyz, sp, Q, npad, pair_const=pair_const)
+    ref = O.predict_batch(w, offs, xyz, sp, Q, npad)
+    scale = max(1.0, np.abs(ref).max())
+    assert np.abs(q64 - ref).max() < 5e-5 * scale, (seed, np.abs(q64 - ref).max(), scale)
+    assert np.abs(np.add.reduceat(q64, offs[:-1]) - Q).max() < 1e-6 * scale
