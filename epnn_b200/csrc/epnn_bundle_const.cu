@@ -232,15 +232,22 @@ __global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kerne
             const unsigned short* flist = use0 ? a.far0_list : a.far_list;
             const int f0 = use0 ? a.far0_off[atom0] : a.far_off[atom0], f1 = use0 ? a.far0_off[atom0 + nat] : a.far_off[atom0 + nat];
             const float zero_ce[HID] = {};
+            // the next tile's slot codes / weights are requested one tile ahead (two registers)
+            int n_code = f0 + lane < f1 ? (int)flist[f0 + lane] : -1;
+            int n_cnt = (use0 && f0 + lane < f1) ? (int)a.far0_w[f0 + lane] : 1;
             for (int fb = f0; fb < f1; fb += 32) {
-                const bool ok = fb + lane < f1;
+                const bool ok = n_code >= 0;
                 int li = 0, lj = 0;
                 float wv = 0.f;
                 if (ok) {
-                    const int code = (int)flist[fb + lane];
-                    li = code >> 8; lj = code & 0xFF;
+                    li = n_code >> 8; lj = n_code & 0xFF;
                     if (lj == 0xFF) { lj = PAD_ROW; wv = padw[li]; }        // pad pseudo-pair: weight npad - n, v = b1
-                    else wv = use0 ? (float)a.far0_w[fb + lane] : 1.f;      // species slot: number of far columns of that species
+                    else wv = (float)n_cnt;                                 // species slot: number of far columns of that species (1: plain column)
+                }
+                {
+                    const int k = fb + 32 + lane;
+                    n_code = k < f1 ? (int)flist[k] : -1;
+                    n_cnt = (use0 && k < f1) ? (int)a.far0_w[k] : 1;
                 }
                 f2_t acc2[HID / 2];
                 second_layer<false>(W, zero_ce, uv + li * CUVS, uv + lj * CUVS + HID, acc2);
