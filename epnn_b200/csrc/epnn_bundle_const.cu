@@ -59,6 +59,12 @@ __device__ __forceinline__ void cfma2(f2_t& d, f2_t wpair, float a) {
 }
 #endif
 
+#ifdef EPNN_CPU_EMU
+__device__ __forceinline__ void cprefetch_l2(const void*) {}
+#else
+__device__ __forceinline__ void cprefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
+
 // acc[c] = b2[c] + sum_k relu(ce[k] + urow[k] + vrow[k]) * W2[k][c]   (ce == nullptr-like: pass zeros for far slots)
 template <bool WITH_CE>
 __device__ __forceinline__ void second_layer(const PairW& W, const float (&ce)[HID], const float* urow, const float* vrow, f2_t (&acc2)[HID / 2]) {
@@ -131,10 +137,21 @@ __global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kerne
         if (lane == 0) x = atomicAdd(a.work_counter, 1);
         return __shfl_sync(0xffffffffu, x, 0);
     };
-    for (int b = grab(); b < a.n_bundles; b = grab()) {
+    // every warp already holds the index of its NEXT bundle, to pull that bundle's u / v rows into L2 while it works
+    int b = grab();
+    int b_next = grab();
+    for (; b < a.n_bundles; b = b_next, b_next = grab()) {
         const int2 bd = a.bundle[b];
         const int atom0 = bd.x, nat = bd.y;
         const int p0 = a.ustart[atom0], p1 = a.ustart[atom0 + nat];
+        if (b_next < a.n_bundles) {
+            const int2 nd = a.bundle[b_next];
+            const int nbytes = nd.y * HID * (int)sizeof(float);
+            for (int o = lane * 128; o < nbytes; o += 32 * 128) {
+                cprefetch_l2(reinterpret_cast<const char*>(a.u + (int64_t)nd.x * HID) + o);
+                cprefetch_l2(reinterpret_cast<const char*>(a.v + (int64_t)nd.x * HID) + o);
+            }
+        }
         __syncwarp();
         for (int f = lane; f < nat * 16; f += 32) {                // stage u | v (coalesced 16-byte loads)
             const int row = f >> 4, c4 = f & 15;
