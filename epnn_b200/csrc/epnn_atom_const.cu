@@ -48,7 +48,9 @@ __device__ __forceinline__ void afma2(a2_t& d, a2_t wpair, float a) {
 }
 #endif
 
-// out[0 .. 2*NP) += x[0 .. K) . Wm[K][ld] (columns col0 .. col0 + 2*NP), weights uniform
+// out[0 .. 2*NP) += x[0 .. K) . Wm[K][ld] (columns col0 .. col0 + 2*NP), weights uniform.  Fully unrolled on purpose: the
+// activations x[] live in registers, and a rolled k loop would index them dynamically (ptxas then moves them to local
+// memory: tried, 256-byte stack frame).  The price is code size -- 4 864 FFMA2, about 120 KB of SASS for the kernel.
 template <int K, int NP>
 __device__ __forceinline__ void uniform_product(const float* __restrict__ Wm, int ld, int col0, const float (&x)[K], a2_t (&acc)[NP]) {
 #pragma unroll
