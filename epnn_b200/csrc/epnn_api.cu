@@ -52,7 +52,7 @@ static thread_local std::string g_create_err;
 enum {
     B_XYZ, B_SPECIES, B_OFF, B_Q, B_NPAD, B_ATOMSYS, B_DEG, B_DEGU, B_ROWPTR, B_USTART, B_COL, B_PID, B_PI, B_PJ, B_PD,
     B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_FAR0CNT, B_FAR0OFF, B_FAR0LIST, B_FAR0W, B_REP, B_ATOMB0, B_BNAT, B_PERM, B_LARGESYS, B_GRID, B_CELLCNT, B_CELLSTART, B_CELLATOMS, B_DTMP, B_H, B_L2, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
-    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_COUNT
+    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_ROWBLK, B_COUNT
 };
 
 static int fail(epnn_ctx* c, int code, const char* fmt, ...) {
@@ -399,6 +399,21 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
             ns = ns < 1 ? 1 : (ns > 15 ? 15 : ns);
             w.far_tc = 1;
             w.nsplit = ns + 1;                       // + the SIMT kernel's plane (near pairs, pad pair)
+        } else if (c->pair_const && sizeof(R) == 4) {   // experimental row-per-thread far kernel: warp units = 32-row block x column range
+            std::vector<int2> hb;
+            for (int s = 0; s < n_sys; ++s) {
+                const int a0 = h_off[s] - base, ns_ = h_off[s + 1] - h_off[s];
+                if (ns_ > SMALL_MAX) for (int i = 0; i < ns_; i += 32) hb.push_back(make_int2(a0 + i, s));
+            }
+            w.n_rowblk = (int)hb.size();
+            int2* d_blk;
+            ENS(B_ROWBLK, sizeof(int2) * (hb.size() + 1), d_blk, int2*);
+            CU(c, cudaMemcpy(d_blk, hb.data(), sizeof(int2) * hb.size(), cudaMemcpyHostToDevice));
+            w.rowblk = d_blk;
+            int ns = div_up((int64_t)c->sm_count * 32, w.n_rowblk);
+            ns = ns < 1 ? 1 : (ns > 15 ? 15 : ns);
+            w.far_tc = 2;
+            w.nsplit = ns + 1;                       // + gnn_pair_kernel's plane (near pairs, pad pair, species slots)
         } else {
             int ns = div_up((int64_t)c->sm_count * 64, w.n_rg_large);
             w.nsplit = ns < 1 ? 1 : (ns > 32 ? 32 : ns);
@@ -468,9 +483,12 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
         if (!sharded || c->shard_rank == 0) CU(c, launch_gnn_bundle<R>(w, msg[t], st, n_launch));
         w.stamp = w.sp_tab ? t + 1 : 0;             // large systems: are this step's v rows equal species by species?
         CU(c, launch_sp_check<R>(w, st, n_launch));
-        if (w.far_tc)
+        if (w.far_tc == 1)
             CU(c, launch_gnn_far_tc(w, c->w2split + (size_t)t * 2048, c->w2split + (size_t)t * 2048 + 1024, (const float*)msg[t].b2,
                                     w.nsplit - 1, st, n_launch));
+        if constexpr (sizeof(R) == 4) {
+            if (w.far_tc == 2) CU(c, launch_gnn_far_const(w, msg[t], w.nsplit - 1, st, n_launch));
+        }
         CU(c, launch_gnn_pair<R>(w, msg[t], st, n_launch));
         if (sharded && c->allreduce(c->allreduce_user, w.S, (size_t)HID * n_atoms * w.nsplit, sizeof(R) == 8, (void*)st) != 0)
             return fail(c, EPNN_E_CUDA, "allreduce callback failed (GNN step %d)", t);

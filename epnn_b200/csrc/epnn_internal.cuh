@@ -235,7 +235,9 @@ struct Workspace {
     int* far_off; unsigned short* far_list; int64_t n_far;
     int* far0_off; unsigned short* far0_list; unsigned char* far0_w; int* rep; int64_t n_far0; int dedup_far;   // species-compressed far list   // per-bundle list of the GNN's e == 0 ("far") ordered pairs
     int* rg_large; int n_rg_large; int nsplit;    // 4-row groups of the large systems
-    int far_tc;                                   // 1: the far part of the big-system message sum runs on the tensor cores;
+    const int2* rowblk; int n_rowblk;             // 32-row blocks of the large systems (first atom, system): units of gnn_far_const_kernel
+    int far_tc;                                   // 1: the far part of the big-system message sum runs on the tensor cores (2: on the
+                                                  //    experimental row-per-thread FP32 kernel, epnn_gnn_far_const.cu);
                                                   //    planes [0, nsplit-1) of S are theirs, the SIMT kernel (near only) owns the last
     int shard_rank, shard_world;                  // this rank's slice of the large-system pair kernels (world 1 = everything)
     // species tables of the large systems (exact de-duplication of their far columns, epnn_gnn.cu): entry
@@ -284,6 +286,7 @@ template <typename R> cudaError_t launch_epn_bundle(const Workspace& w, const St
 cudaError_t launch_epn_bundle_mma(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* n_launch);   // option pair_tensor
 cudaError_t launch_gnn_bundle_const(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* n_launch); // option pair_const
 cudaError_t launch_epn_bundle_const(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* n_launch);
+cudaError_t launch_gnn_far_const(const Workspace& w, const StepW<float>& sw, int nsplit_far, cudaStream_t st, int* n_launch);   // option pair_const
 cudaError_t launch_gnn_far_tc(const Workspace& w, const float* Whi, const float* Wlo, const float* b2, int nsplit_tc,
                               cudaStream_t st, int* n_launch);
 template <typename R> cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);

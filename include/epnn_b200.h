@@ -95,8 +95,9 @@ const char* epnn_last_error(const epnn_ctx* ctx);
  * tensor path (mma.sync m16n8k8 TF32 inputs, 3xTF32 split, FP32 accumulation, operands chained through registers)
  * instead of FP32 SIMT (precision 32 only; per-pair transfers differ from the SIMT path by about 1e-6 relative);
  * "pair_const" 0 (default) / 1: EXPERIMENTAL, not yet validated on a GPU (see epnn_bundle_const.cu): plain-FP32
- * variant of both small-system pair kernels (one thread owns one pair) and of the per-atom kernel (one thread owns one
- * atom) in which the weights are uniform operands passed as kernel parameters (precision 32 only). */
+ * variant of both small-system pair kernels (one thread owns one pair), of the per-atom kernel (one thread owns one
+ * atom) and of the far part of the big-system message sum (one thread owns one row) in which the weights are uniform
+ * operands passed as kernel parameters (precision 32 only). */
 int epnn_set_option(epnn_ctx* ctx, const char* key, double value);
 
 /* Charge inference for a packed batch of systems, host buffers.

@@ -31,6 +31,9 @@ namespace k_bconst {
 namespace k_aconst {
 #include "../../epnn_b200/csrc/epnn_atom_const.cu"
 }
+namespace k_farc {
+#include "../../epnn_b200/csrc/epnn_gnn_far_const.cu"
+}
 namespace k_mma {
 #include "../../epnn_b200/csrc/epnn_bundle_mma.cu"
 }
@@ -237,8 +240,24 @@ extern "C" int emu_infer(int T, int n_x, const float* w_packed, size_t n_w, int 
                     k_gnn::sp_check_kernel<float>(n, atom_sys.data(), off, species, rgl_off.data(), sp_tab.data(), v.data(), sp_stamp.data(), stamp); });
                 emu_launch_simple(div_up(n_sp_tab, 256), 256, [&] { k_gnn::sp_tally_kernel(n_sp_tab, sp_tab.data(), sp_stamp.data(), stamp, &dedup_rows); });
             }
+            // variant 1: the far columns of the live steps go to the row-per-thread kernel (planes 0 .. nsplit - 2), gnn_pair_kernel keeps
+            // the near pairs, the pad pair and the species slots on the last plane -- the far_tc == 2 arrangement of run_chunk
+            const bool far_const = pair_const;
+            if (far_const) {
+                std::vector<int2> blk;
+                for (int s = 0; s < n_sys; ++s)
+                    if (off[s + 1] - off[s] > SMALL_MAX) for (int i = off[s]; i < off[s + 1]; i += 32) blk.push_back(make_int2(i, s));
+                k_farc::FarW FW;
+                memcpy(FW.W2, msg[t].W2, sizeof(FW.W2)); memcpy(FW.b2, msg[t].b2, sizeof(FW.b2));
+                k_farc::FarConstArgs fa;
+                fa.blk = blk.data(); fa.nsplit = nsplit - 1; fa.n_atoms = n; fa.unit_begin = 0; fa.unit_end = (int)blk.size() * (nsplit - 1);
+                fa.sys_off = off; fa.rowptr = rowptr.data(); fa.col = col.data(); fa.u = u.data(); fa.v = v.data(); fa.S = S.data();
+                fa.rgl_off = rgl_off.data(); fa.sp_stamp = sp_stamp.data(); fa.stamp = stamp;
+                emu_launch_grid(2, FARC_NW, (size_t)FARC_NW * FARC_PW_BYTES / sizeof(float) + 8, [&] { k_farc::gnn_far_const_kernel(FW, fa); });
+            }
             k_gnn::GnnArgs<float> ga;
-            ga.rg_atom = rg.data(); ga.unit_begin = 0; ga.n_units = n_rg * nsplit; ga.nsplit = nsplit; ga.n_atoms = n; ga.skip_far = 0; ga.plane = 0;
+            ga.rg_atom = rg.data(); ga.unit_begin = 0; ga.n_units = far_const ? n_rg : n_rg * nsplit; ga.nsplit = far_const ? 1 : nsplit; ga.n_atoms = n;
+            ga.skip_far = far_const ? 1 : 0; ga.plane = far_const ? nsplit - 1 : 0;
             ga.atom_sys = atom_sys.data(); ga.sys_off = off; ga.npad = npad.data(); ga.rowptr = rowptr.data(); ga.col = col.data(); ga.pid = pid.data();
             ga.e = e.data(); ga.u = u.data(); ga.v = v.data(); ga.Cw = msg[t].Cw; ga.W2 = msg[t].W2; ga.b2 = msg[t].b2; ga.b1 = msg[t].b1; ga.S = S.data();
             ga.species = species; ga.rgl_off = rgl_off.data(); ga.sp_tab = sp_tab.data(); ga.sp_stamp = sp_stamp.data(); ga.stamp = stamp; ga.n_species = n_species;
