@@ -85,3 +85,40 @@ def test_pair_const_golden_871(weights, mixed, val871):
         eng.close()
     worst = max(float(np.abs(q[offs[k]:offs[k + 1]] - val871["pred"][k][:offs[k + 1] - offs[k]]).max()) for k in range(len(idx)))
     assert worst < 1e-5, worst
+
+
+def test_pair_const_protein_golden(weights, protein):
+    """Galectin-3C through pair_const: per-atom variant, row-per-thread far kernel (epnn_gnn_far_const.cu) for the two
+    live steps, species slots for the three collapsed ones."""
+    eng = _engine(weights, "decay_model_weights")
+    try:
+        n = len(protein["Z"])
+        offs = np.array([0, n], np.int32)
+        sp = O.species_from_Z(protein["Z"], 9)
+        q, q64 = eng.infer_batch(offs, protein["xyz"], sp, np.array([protein["Q"]], np.float32), None, want_f64=True)
+        assert eng.last_stats["n_far_dedup_rows"] == 3 * n
+    finally:
+        eng.close()
+    assert np.abs(q - protein["preds"]).max() < 1e-5
+    assert abs(q64.sum() - 2.0) < 1e-6
+
+
+@pytest.mark.parametrize("name,rtol", [("model2_weights", 2e-4), ("model_weights", 2e-2)])
+def test_pair_const_large_live_gnn(engines, weights, protein, name, rtol):
+    w = weights[name]
+    n = 600
+    xyz = protein["xyz"][:n]
+    sp = O.species_from_Z(protein["Z"][:n], w.n_x)
+    offs = np.array([0, n], np.int32)
+    Q = np.array([1.0], np.float32)
+    eng = _engine(weights, name)
+    try:
+        for npad in (None, 640):
+            q64 = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
+            h = eng.hidden(n).copy()
+            tr = {}
+            ref = O.forward_factorised(w, xyz, sp, Q[0], npad, trace=tr)
+            assert np.abs(q64 - ref).max() / np.abs(ref).max() < rtol, (name, npad)
+            assert np.abs(h - tr["h"]).max() / np.abs(tr["h"]).max() < 2e-4, (name, npad)
+    finally:
+        eng.close()
