@@ -9,3 +9,5 @@ echo "== --pair-const 1 (FP32 SIMT, pair per thread, uniform weights)"; run --pa
 echo "== --pair-tensor 1 (EPN on mma.sync 3xTF32)"; run --pair-tensor 1
 echo "== --pair-const 1, model_weights (live hidden state: 4 of 5 steps walk the full far list)"; run --pair-const 1 --checkpoint model_weights
 echo "== default, model_weights"; run --checkpoint model_weights
+echo "== protein-like 40k atoms, default FP32 (row-group kernels)"; run --workload protein --atoms 40000 --steps 3
+echo "== protein-like 40k atoms, --pair-const 1 (row-per-thread far kernel for the live steps)"; run --workload protein --atoms 40000 --steps 3 --pair-const 1
