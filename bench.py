@@ -68,7 +68,7 @@ def parse_args():
                     help="big systems: far part of the message sum on tcgen05 tensor cores (3xTF32) instead of FP32 SIMT")
     ap.add_argument("--pair-tensor", type=int, default=0, choices=[0, 1],
                     help="small systems: electron-passing pair MLP on mma.sync 3xTF32 instead of FP32 SIMT (opt-in)")
-    ap.add_argument("--pair-const", type=int, default=0, choices=[0, 1],
+    ap.add_argument("--pair-const", type=int, default=2, choices=[0, 1, 2],
                     help="EXPERIMENTAL (unvalidated): pair-per-thread FP32 bundle kernels with weights as uniform operands")
     ap.add_argument("--dedup-far", type=int, default=1, choices=[0, 1], help="collapse species-equivalent far columns (exact; 0 = ablation)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -333,8 +333,7 @@ def run_b200(args):
         eng.set_option("dedup_far", 0)
     if args.pair_tensor:
         eng.set_option("pair_tensor", 1)
-    if args.pair_const:
-        eng.set_option("pair_const", 1)
+    eng.set_option("pair_const", args.pair_const)
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
     sharded_system = args.workload == "protein" and world > 1
     if sharded_system:                       # one big system: pair kernels split over the ranks, all-reduce per step / pass

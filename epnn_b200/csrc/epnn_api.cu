@@ -27,7 +27,7 @@ struct epnn_ctx {
     int far_tensor = 0;          // option "gnn_far_tensor"
     int dedup_far = 1;           // option "dedup_far": collapse species-equivalent far columns (exact)
     int pair_tensor = 0;         // option "pair_tensor": EPN bundle kernel on mma.sync 3xTF32 (precision 32 only)
-    int pair_const = 0;          // option "pair_const": EXPERIMENTAL pair-per-thread bundle kernels (precision 32 only)
+    int pair_const = 2;          // option "pair_const": FP32 kernel set (0 warp-tile, 1 pair-per-thread everywhere, 2 default mix; see epnn_internal.cuh)
     std::vector<float> wf_host;  // host mirror of wf (pair_const passes a step's weights as kernel parameters)
     float* w2split = nullptr;    // [T][2][32][32]: hi / lo parts of W2^T of every message MLP (tensor-core far kernel)
     int shard_rank = 0, shard_world = 1;
@@ -52,7 +52,7 @@ static thread_local std::string g_create_err;
 enum {
     B_XYZ, B_SPECIES, B_OFF, B_Q, B_NPAD, B_ATOMSYS, B_DEG, B_DEGU, B_ROWPTR, B_USTART, B_COL, B_PID, B_PI, B_PJ, B_PD,
     B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_FAR0CNT, B_FAR0OFF, B_FAR0LIST, B_FAR0W, B_REP, B_ATOMB0, B_BNAT, B_PERM, B_LARGESYS, B_GRID, B_CELLCNT, B_CELLSTART, B_CELLATOMS, B_DTMP, B_H, B_L2, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
-    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_ROWBLK, B_COUNT
+    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_ROWBLK, B_ROWL, B_COUNT
 };
 
 static int fail(epnn_ctx* c, int code, const char* fmt, ...) {
@@ -200,7 +200,10 @@ extern "C" int epnn_set_option(epnn_ctx* c, const char* key, double value) {
     else if (k == "gnn_far_tensor") c->far_tensor = value != 0;
     else if (k == "dedup_far") c->dedup_far = value != 0;
     else if (k == "pair_tensor") c->pair_tensor = value != 0;
-    else if (k == "pair_const") c->pair_const = value != 0;
+    else if (k == "pair_const") {
+        if (value != 0 && value != 1 && value != 2) return fail(c, EPNN_E_INVALID, "pair_const must be 0, 1 or 2");
+        c->pair_const = (int)value;
+    }
     else if (k == "chunk_atoms") {
         if (value < 64) return fail(c, EPNN_E_INVALID, "chunk_atoms must be >= 64");
         c->chunk_atoms = (int64_t)value;
@@ -286,7 +289,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     w.ek = EKof<R>::v;
     w.n_species = c->n_species;
     w.pair_tensor = c->pair_tensor && sizeof(R) == 4;
-    w.pair_const = c->pair_const && sizeof(R) == 4;
+    w.pair_const = sizeof(R) == 4 ? c->pair_const : 0;
     w.wf_host = c->wf_host.data(); w.wf_dev = c->wf;
     w.work_counter = c->d_flags + 7;
     w.xyz = d_xyz; w.species = d_species; w.Qsys = d_Q;
@@ -408,7 +411,8 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
             w.n_rowblk = (int)hb.size();
             int2* d_blk;
             ENS(B_ROWBLK, sizeof(int2) * (hb.size() + 1), d_blk, int2*);
-            CU(c, cudaMemcpy(d_blk, hb.data(), sizeof(int2) * hb.size(), cudaMemcpyHostToDevice));
+            CU(c, cudaMemcpyAsync(d_blk, hb.data(), sizeof(int2) * hb.size(), cudaMemcpyHostToDevice, st));
+            CU(c, cudaStreamSynchronize(st));      // hb is a local
             w.rowblk = d_blk;
             int ns = div_up((int64_t)c->sm_count * 32, w.n_rowblk);
             ns = ns < 1 ? 1 : (ns > 15 ? 15 : ns);
@@ -422,6 +426,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
 
     ENS(B_COL, sizeof(int) * (size_t)(w.nnz + 1), w.col, int*);
     ENS(B_PID, sizeof(int) * (size_t)(w.nnz + 1), w.pid, int*);
+    ENS(B_ROWL, (size_t)(w.nnz + 16), w.rowl, unsigned char*);
     ENS(B_PI, sizeof(int) * (size_t)(w.P + 1), w.pair_i, int*);
     ENS(B_PJ, sizeof(int) * (size_t)(w.P + 1), w.pair_j, int*);
     ENS(B_PD, sizeof(double) * (size_t)(w.P + 1), w.pair_D, double*);
@@ -446,6 +451,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     if (cw.n_large) ENS(B_DTMP, sizeof(double) * (size_t)(w.nnz + 1), cw.Dtmp, double*);
     CU(c, launch_nbr_fill(w, cw, st, n_launch));
     CU(c, launch_far_fill(w, atom_b0, st, n_launch));
+    if (w.pair_const == 2) CU(c, launch_csr_rowl(w, atom_b0, st, n_launch));
     // species-compressed far list (needs the filled CSR): counts -> offsets -> slots; its size is bounded, no host sync
     CU(c, launch_far0_count(w, far0_cnt, st, n_launch));
     CU(c, launch_scan_i32(far0_cnt, w.far0_off, n_atoms, scantmp, st, n_launch));

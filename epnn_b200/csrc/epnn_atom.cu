@@ -252,7 +252,7 @@ cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, cons
                         int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0) return cudaSuccess;
     if constexpr (sizeof(R) == 4) {
-        if (w.pair_const) return launch_atom_const(w, mode, prev, upd, next, h_is_zero, q_out, q_out64, st, nl);   // experimental (epnn_atom_const.cu)
+        if (w.pair_const == 1) return launch_atom_const(w, mode, prev, upd, next, h_is_zero, q_out, q_out64, st, nl);   // experimental (epnn_atom_const.cu)
     }
     constexpr int NW = sizeof(R) == 4 ? ATOM_NW : 4;
     AtomArgs<R> aa;

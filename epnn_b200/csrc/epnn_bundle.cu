@@ -440,14 +440,15 @@ static cudaError_t launch_bundle(const Workspace& w, const StepW<R>& sw, cudaStr
 #ifndef EPNN_CPU_EMU
 template <typename R> cudaError_t launch_gnn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* nl) {
     if constexpr (sizeof(R) == 4) {
-        if (w.pair_const) return launch_gnn_bundle_const(w, sw, st, nl);    // experimental pair-per-thread variant (epnn_bundle_const.cu)
+        if (w.pair_const == 2) return launch_gnn_bundle_run(w, sw, st, nl);    // row-run mapping (epnn_bundle_run.cu): FP32 default
+        if (w.pair_const == 1) return launch_gnn_bundle_const(w, sw, st, nl);  // pair-per-thread variant with transpose (epnn_bundle_const.cu)
     }
     return launch_bundle<R, false>(w, sw, st, nl);
 }
 template <typename R> cudaError_t launch_epn_bundle(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* nl) {
     if constexpr (sizeof(R) == 4) {
-        if (w.pair_const) return launch_epn_bundle_const(w, sw, st, nl);     // experimental pair-per-thread variant (epnn_bundle_const.cu)
         if (w.pair_tensor) return launch_epn_bundle_mma(w, sw, st, nl);      // optional 3xTF32 mma.sync variant (epnn_bundle_mma.cu)
+        if (w.pair_const) return launch_epn_bundle_const(w, sw, st, nl);     // pair-per-thread variant (epnn_bundle_const.cu): FP32 default
     }
     return launch_bundle<R, true>(w, sw, st, nl);
 }

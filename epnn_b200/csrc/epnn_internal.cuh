@@ -231,6 +231,7 @@ struct Workspace {
     int ek;                            // floats per row of `e`: ED (48 descriptor values) or EDR (16 basis coefficients)
     int* work_counter;                 // device int: dynamic work queue of the bundle kernels
     int2* bundle; int n_bundles;       // (first atom, atom count) of every bundle of small systems (n <= SMALL_MAX)
+    unsigned char* rowl;               // local row (atom - first atom of its bundle) of every CSR entry (small systems)
     int* bundle_nat; unsigned char* perm_j;   // atoms of the bundle (at its first atom); rank of a pair's j inside its tile
     int* far_off; unsigned short* far_list; int64_t n_far;
     int* far0_off; unsigned short* far0_list; unsigned char* far0_w; int* rep; int64_t n_far0; int dedup_far;   // species-compressed far list   // per-bundle list of the GNN's e == 0 ("far") ordered pairs
@@ -248,7 +249,8 @@ struct Workspace {
     int stamp;                                    // stamp of the current message-passing step (t + 1); 0 = de-duplication off
     int n_species;                                // species of the element table in use (8 or 9)
     int pair_tensor;                              // 1: electron-passing bundle kernel on the warp-level tensor path (3xTF32, FP32 only)
-    int pair_const;                               // 1: EXPERIMENTAL pair-per-thread bundle kernels, weights as uniform operands (FP32 only)
+    int pair_const;                               // FP32 kernel set: 0 warp-tile kernels (round 1), 1 pair-per-thread kernels everywhere,
+                                                  // 2 (default) row-run GNN bundle kernel + pair-per-thread EPN bundle kernel + row-per-thread far kernel
     const float* wf_host; const float* wf_dev;    // packed FP32 weights: host mirror and device base (pair_const passes weights as kernel parameters)
     unsigned long long* dedup_rows;               // device counter (statistics): rows whose far part was collapsed, summed over steps
     void* h; void* S; void* u; void* v; void* delta;   // precision-dependent (float or double)
@@ -286,6 +288,8 @@ template <typename R> cudaError_t launch_epn_bundle(const Workspace& w, const St
 cudaError_t launch_epn_bundle_mma(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* n_launch);   // option pair_tensor
 cudaError_t launch_gnn_bundle_const(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* n_launch); // option pair_const
 cudaError_t launch_epn_bundle_const(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* n_launch);
+cudaError_t launch_gnn_bundle_run(const Workspace& w, const StepW<float>& sw, cudaStream_t st, int* n_launch);   // row-run mapping (FP32 default)
+cudaError_t launch_csr_rowl(const Workspace& w, const int* atom_b0, cudaStream_t st, int* n_launch);
 cudaError_t launch_gnn_far_const(const Workspace& w, const StepW<float>& sw, int nsplit_far, cudaStream_t st, int* n_launch);   // option pair_const
 cudaError_t launch_gnn_far_tc(const Workspace& w, const float* Whi, const float* Wlo, const float* b2, int nsplit_tc,
                               cudaStream_t st, int* n_launch);

@@ -1,42 +1,43 @@
-"""EXPERIMENTAL pair-per-thread bundle kernels ("pair_const" = 1; epnn_bundle_const.cu) -- written after round 1's GPU
-budget was spent, so these tests only run with EPNN_TEST_EXPERIMENTAL=1 until the kernels have been validated on a B200
-(first GPU call of round 2: `EPNN_TEST_EXPERIMENTAL=1 python -m pytest tests/test_gpu_pair_const.py -m gpu`).
+"""The FP32 kernel sets ("pair_const" option) against the oracle and against each other.
 
-Plain FP32 like the default kernels, only the mapping of the work onto the warp differs, so the bar is the default
-path's: FP32 tolerances against the float64 oracle, 871 shipped predictions within 1e-5, hidden state against the oracle
-for the live checkpoints, charge conservation, bitwise reproducibility, and agreement with the default kernels to FP32
-round-off (the additions into S happen in another -- equally fixed -- order)."""
-import os
+  2 (default since round 2): row-run GNN bundle kernel (epnn_bundle_run.cu) + pair-per-thread EPN bundle kernel
+     (epnn_bundle_const.cu) + row-per-thread far kernel for large systems (epnn_gnn_far_const.cu) + warp-tile per-atom kernel
+  1: pair-per-thread kernels everywhere (GNN bundle kernel with the 32 x 33 transpose, per-atom variant)
+  0: the round-1 warp-tile kernels
 
+All three are plain FP32 and evaluate the same formulas; only the mapping of the work onto the warp (and therefore the --
+fixed -- order of the additions into S) differs, so the bar is the same for each: FP32 tolerances against the float64
+oracle, 871 shipped predictions within 1e-5, hidden state against the oracle for the live checkpoints, charge
+conservation, bitwise reproducibility, agreement with the default set to FP32 round-off.  First validated on a B200 in
+round 2 (profiles/r02/call01_pair_const_tests_and_ab.log)."""
 import numpy as np
 import pytest
 
 from oracle import epnn_oracle as O
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("EPNN_TEST_EXPERIMENTAL") != "1",
-                                 reason="pair_const kernels not yet validated on a GPU (set EPNN_TEST_EXPERIMENTAL=1)")]
+pytestmark = [pytest.mark.gpu]
 
 TOL_FP32 = {"decay_model_weights": 1e-5, "model2_weights": 5e-5, "model_weights": 1e-3}
 
 
-def _engine(weights, name):
+def _engine(weights, name, kset=1):
     from epnn_b200.engine import Engine
     eng = Engine(weights[name], device=0)
-    eng.set_option("pair_const", 1)
+    eng.set_option("pair_const", kset)
     eng.set_option("keep_hidden", 1)
     return eng
 
 
 @pytest.mark.parametrize("name", ["decay_model_weights", "model2_weights", "model_weights"])
 @pytest.mark.parametrize("dedup", [1, 0])
-def test_pair_const_vs_oracle_and_default(engines, weights, mixed, name, dedup):
+@pytest.mark.parametrize("kset", [0, 1, 2])
+def test_pair_const_vs_oracle_and_default(engines, weights, mixed, name, dedup, kset):
     w = weights[name]
     rng = np.random.default_rng(44)
     idx = sorted(rng.choice(mixed.usable(w.n_x), 300, replace=False).tolist())
     offs, xyz, sp, Q = mixed.batch(idx, w.n_x)
     npad = np.where(np.arange(len(Q)) % 3 == 0, np.diff(offs), 41).astype(np.int32)      # some systems without padding
-    eng = _engine(weights, name)
+    eng = _engine(weights, name, kset)
     eng.set_option("dedup_far", dedup)
     try:
         q64 = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
@@ -57,11 +58,12 @@ def test_pair_const_vs_oracle_and_default(engines, weights, mixed, name, dedup):
 
 
 @pytest.mark.parametrize("name", ["model_weights", "model2_weights"])
-def test_pair_const_hidden_state_vs_oracle(weights, mixed, name):
+@pytest.mark.parametrize("kset", [0, 1, 2])
+def test_pair_const_hidden_state_vs_oracle(weights, mixed, name, kset):
     w = weights[name]
     idx = mixed.usable(w.n_x)[:40].tolist()
     offs, xyz, sp, Q = mixed.batch(idx, w.n_x)
-    eng = _engine(weights, name)
+    eng = _engine(weights, name, kset)
     try:
         eng.infer_batch(offs, xyz, sp, Q, 41)
         h = eng.hidden(int(offs[-1])).copy()
@@ -74,11 +76,12 @@ def test_pair_const_hidden_state_vs_oracle(weights, mixed, name):
         assert np.abs(h[a0:a1] - tr["h"]).max() < 2e-4 * max(1.0, np.abs(tr["h"]).max()), (name, k)
 
 
-def test_pair_const_golden_871(weights, mixed, val871):
+@pytest.mark.parametrize("kset", [0, 1, 2])
+def test_pair_const_golden_871(weights, mixed, val871, kset):
     w = weights["decay_model_weights"]
     idx = [mixed.index[n] for n in val871["names"]]
     offs, xyz, sp, Q = mixed.batch(idx, 9)
-    eng = _engine(weights, "decay_model_weights")
+    eng = _engine(weights, "decay_model_weights", kset)
     try:
         q = eng.infer_batch(offs, xyz, sp, Q, 41)
     finally:
@@ -87,10 +90,11 @@ def test_pair_const_golden_871(weights, mixed, val871):
     assert worst < 1e-5, worst
 
 
-def test_pair_const_protein_golden(weights, protein):
+@pytest.mark.parametrize("kset", [1, 2])
+def test_pair_const_protein_golden(weights, protein, kset):
     """Galectin-3C through pair_const: per-atom variant, row-per-thread far kernel (epnn_gnn_far_const.cu) for the two
     live steps, species slots for the three collapsed ones."""
-    eng = _engine(weights, "decay_model_weights")
+    eng = _engine(weights, "decay_model_weights", kset)
     try:
         n = len(protein["Z"])
         offs = np.array([0, n], np.int32)
