@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libepnn_b200.so")
+# EPNN_B200_LIB: development override (A/B of kernel variants built by tools/build_variant.sh); the product is the in-tree library
+LIB_PATH = os.environ.get("EPNN_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libepnn_b200.so")
 
 EPNN_OK = 0
 ERRORS = {-1: "EPNN_E_INVALID", -2: "EPNN_E_CUDA", -3: "EPNN_E_NOMEM", -4: "EPNN_E_CAPACITY", -5: "EPNN_E_UNSUPPORTED"}

@@ -52,7 +52,7 @@ static thread_local std::string g_create_err;
 enum {
     B_XYZ, B_SPECIES, B_OFF, B_Q, B_NPAD, B_ATOMSYS, B_DEG, B_DEGU, B_ROWPTR, B_USTART, B_COL, B_PID, B_PI, B_PJ, B_PD,
     B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_FAR0CNT, B_FAR0OFF, B_FAR0LIST, B_FAR0W, B_REP, B_ATOMB0, B_BNAT, B_PERM, B_LARGESYS, B_GRID, B_CELLCNT, B_CELLSTART, B_CELLATOMS, B_DTMP, B_H, B_L2, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
-    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_ROWBLK, B_ROWL, B_COUNT
+    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_ROWBLK, B_ROWL, B_ARGS, B_COUNT
 };
 
 static int fail(epnn_ctx* c, int code, const char* fmt, ...) {
@@ -292,6 +292,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     w.pair_const = sizeof(R) == 4 ? c->pair_const : 0;
     w.wf_host = c->wf_host.data(); w.wf_dev = c->wf;
     w.work_counter = c->d_flags + 7;
+    { void* pa; int rca = ensure(c, B_ARGS, 1024, &pa); if (rca != EPNN_OK) return rca; w.args_dev = pa; }
     w.xyz = d_xyz; w.species = d_species; w.Qsys = d_Q;
     void* p;
     int rc;

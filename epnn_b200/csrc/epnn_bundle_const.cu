@@ -29,7 +29,11 @@
 #define CUVS 68                         // row stride of the staged u | v rows (64 + 4: rows start in different bank groups)
 #define PAD_ROW BUNDLE_ATOMS            // extra row: v = b1 (a_j = 0, e = 0), the pad pseudo-atom of the GNN's far tiles
 
-struct PairW { float Cw[EDR * HID]; float W2[HID * HID]; float b2[HID]; float x32[HID]; };      // x32 = b1 (GNN) / w3 (EPN)
+// The only constants the tile loop walks: W2, exactly 4 KB = the level-0 constant cache (tools/ubench_uniform.cu: the
+// uniform-operand path drops from 64.7 to 41 TFLOP/s as soon as a loop's constants exceed it).  C rows, b2 and x32 (b1 for
+// the GNN variant, w3 for the EPN variant) are staged in shared memory, the kernel arguments come through global memory
+// (as parameters ptxas re-reads them from the constant bank inside the loop).
+struct PairW { float W2[HID * HID]; };
 
 struct ConstArgs {
     int n_bundles; const int2* bundle; int* work_counter;
@@ -38,6 +42,7 @@ struct ConstArgs {
     const int* far0_off; const unsigned short* far0_list; const unsigned char* far0_w; const int* rep; int dedup;
     const int* atom_sys; const int* sys_off; const int* npad;
     const float* u; const float* v;
+    const float* Cw; const float* b2; const float* x32;      // device pointers into the packed weights
     float* S; float* delta;
 };
 
@@ -67,9 +72,12 @@ __device__ __forceinline__ void cprefetch_l2(const void* p) { asm volatile("pref
 
 // acc[c] = b2[c] + sum_k relu(ce[k] + urow[k] + vrow[k]) * W2[k][c]   (ce == nullptr-like: pass zeros for far slots)
 template <bool WITH_CE>
-__device__ __forceinline__ void second_layer(const PairW& W, const float (&ce)[HID], const float* urow, const float* vrow, f2_t (&acc2)[HID / 2]) {
+__device__ __forceinline__ void second_layer(const PairW& W, const float* __restrict__ sb2, const float (&ce)[HID], const float* urow, const float* vrow, f2_t (&acc2)[HID / 2]) {
 #pragma unroll
-    for (int o = 0; o < HID / 2; ++o) acc2[o] = cpack2(W.b2[2 * o], W.b2[2 * o + 1]);
+    for (int o = 0; o < HID / 2; o += 2) {
+        const ulonglong2 b = *reinterpret_cast<const ulonglong2*>(sb2 + 2 * o);
+        acc2[o] = b.x; acc2[o + 1] = b.y;
+    }
 #pragma unroll
     for (int k4 = 0; k4 < HID / 4; ++k4) {
         const float4 u4 = *reinterpret_cast<const float4*>(urow + 4 * k4);
@@ -115,22 +123,30 @@ __device__ __forceinline__ void add_messages(const f2_t (&acc2)[HID / 2], float 
 
 template <bool EPN> struct ConstSmem {
     static constexpr int PW = (BUNDLE_ATOMS + 1) * CUVS + (EPN ? 0 : BUNDLE_ATOMS * HID + 32 * 33 + BUNDLE_ATOMS);   // floats per warp
-    static size_t bytes() { return sizeof(float) * (size_t)CONST_NW * PW; }
+    static constexpr int SHARED = EDR * HID + 2 * HID;                    // C rows, b2, x32 (per CTA)
+    static size_t bytes() { return sizeof(float) * ((size_t)CONST_NW * PW + SHARED); }
 };
 
 template <bool EPN>
-__global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kernel(const __grid_constant__ PairW W, const ConstArgs a) {
+__global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kernel(const __grid_constant__ PairW W, const ConstArgs* __restrict__ ap) {
+    const ConstArgs a = *ap;
 #ifdef EPNN_CPU_EMU
     float* csm = emu_smem;
 #else
     extern __shared__ __align__(16) float csm[];
 #endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* uv = csm + warp * ConstSmem<EPN>::PW;                   // [BUNDLE_ATOMS + 1][CUVS]
+    float* sCw = csm;                                              // [EDR][32]
+    float* sb2 = csm + EDR * HID;                                  // [32]
+    float* sx = sb2 + HID;                                         // [32]  b1 (GNN) / w3 (EPN)
+    for (int t = threadIdx.x; t < EDR * HID; t += blockDim.x) sCw[t] = a.Cw[t];
+    if (threadIdx.x < HID) { sb2[threadIdx.x] = a.b2[threadIdx.x]; sx[threadIdx.x] = a.x32[threadIdx.x]; }
+    __syncthreads();
+    float* uv = csm + ConstSmem<EPN>::SHARED + warp * ConstSmem<EPN>::PW;   // [BUNDLE_ATOMS + 1][CUVS]
     float* S = uv + (BUNDLE_ATOMS + 1) * CUVS;                     // [BUNDLE_ATOMS][32]   (GNN)
     float* Mt = S + BUNDLE_ATOMS * HID;                            // [32][33]             (GNN)
     float* padw = Mt + 32 * 33;                                    // [BUNDLE_ATOMS]       (GNN)
-    if (!EPN) uv[PAD_ROW * CUVS + HID + lane] = W.x32[lane];       // v of the pad pseudo-atom = b1 (written once per warp)
+    if (!EPN) uv[PAD_ROW * CUVS + HID + lane] = sx[lane];       // v of the pad pseudo-atom = b1 (written once per warp)
 
     auto grab = [&]() {
         int x = 0;
@@ -200,7 +216,10 @@ __global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kerne
 #pragma unroll
                 for (int k = 0; k < EDR; ++k)
 #pragma unroll
-                    for (int o = 0; o < HID / 2; ++o) cfma2(ce2[o], *reinterpret_cast<const f2_t*>(&W.Cw[k * HID + 2 * o]), cf[k]);
+                    for (int o = 0; o < HID / 2; o += 2) {
+                        const ulonglong2 w4 = *reinterpret_cast<const ulonglong2*>(sCw + k * HID + 2 * o);
+                        cfma2(ce2[o], w4.x, cf[k]); cfma2(ce2[o + 1], w4.y, cf[k]);
+                    }
 #pragma unroll
                 for (int o = 0; o < HID / 2; ++o) cunpack2(ce2[o], ce[2 * o], ce[2 * o + 1]);
             }
@@ -210,15 +229,16 @@ __global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kerne
             for (int dir = 0; dir < 2; ++dir) {                    // dir 0: i receives from j;  dir 1: j receives from i
                 const int ir = dir ? lj : li, is = dir ? li : lj;
                 f2_t acc2[HID / 2];
-                second_layer<true>(W, ce, uv + ir * CUVS, uv + is * CUVS + HID, acc2);
+                second_layer<true>(W, sb2, ce, uv + ir * CUVS, uv + is * CUVS + HID, acc2);
                 if (EPN) {
                     float f = 0.f;
 #pragma unroll
                     for (int o = 0; o < HID / 2; ++o) {
                         float x, y;
                         cunpack2(acc2[o], x, y);
-                        f = fmaf(fmaxf(x, 0.f), W.x32[2 * o], f);
-                        f = fmaf(fmaxf(y, 0.f), W.x32[2 * o + 1], f);
+                        const float2 w3 = *reinterpret_cast<const float2*>(sx + 2 * o);
+                        f = fmaf(fmaxf(x, 0.f), w3.x, f);
+                        f = fmaf(fmaxf(y, 0.f), w3.y, f);
                     }
                     fd = dir ? fd - f : f;
                 } else {
@@ -267,7 +287,7 @@ __global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kerne
                     n_cnt = (use0 && k < f1) ? (int)a.far0_w[k] : 1;
                 }
                 f2_t acc2[HID / 2];
-                second_layer<false>(W, zero_ce, uv + li * CUVS, uv + lj * CUVS + HID, acc2);
+                second_layer<false>(W, sb2, zero_ce, uv + li * CUVS, uv + lj * CUVS + HID, acc2);
                 add_messages(acc2, wv, ok ? li : -1, Mt, S, lane);
             }
             // ---- S -> global (plane 0 of the partial-sum planes the per-atom kernel reads)
@@ -284,10 +304,7 @@ static cudaError_t launch_const(const Workspace& w, const StepW<float>& sw, cuda
     if (!w.wf_host || !w.wf_dev) return cudaErrorInvalidValue;
     PairW W;                                                       // this launch's weights; copied into the launch's parameter buffer
     auto host = [&](const float* dev) { return w.wf_host + (dev - w.wf_dev); };
-    memcpy(W.Cw, host(sw.Cw), sizeof(W.Cw));
     memcpy(W.W2, host(sw.W2), sizeof(W.W2));
-    memcpy(W.b2, host(sw.b2), sizeof(W.b2));
-    memcpy(W.x32, host(EPN ? sw.W3 : sw.b1), sizeof(W.x32));
     ConstArgs ca;
     ca.n_bundles = w.n_bundles; ca.bundle = w.bundle; ca.work_counter = w.work_counter;
     cudaError_t e = cudaMemsetAsync(w.work_counter, 0, sizeof(int), st);
@@ -297,13 +314,16 @@ static cudaError_t launch_const(const Workspace& w, const StepW<float>& sw, cuda
     ca.far0_off = w.far0_off; ca.far0_list = w.far0_list; ca.far0_w = w.far0_w; ca.rep = w.rep; ca.dedup = w.dedup_far;
     ca.atom_sys = w.atom_sys; ca.sys_off = w.sys_off; ca.npad = w.npad;
     ca.u = (const float*)w.u; ca.v = (const float*)w.v; ca.S = (float*)w.S; ca.delta = (float*)w.delta;
+    ca.Cw = sw.Cw; ca.b2 = sw.b2; ca.x32 = EPN ? sw.W3 : sw.b1;
     const size_t smem = ConstSmem<EPN>::bytes();
     e = cudaFuncSetAttribute(bundle_const_kernel<EPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int per_sm = EPN ? 2 : 1;
     int grid = div_up(w.n_bundles, CONST_NW);
     if (grid > w.sm_count * per_sm) grid = w.sm_count * per_sm;
-    bundle_const_kernel<EPN><<<grid, CONST_NW * 32, smem, st>>>(W, ca);
+    e = cudaMemcpyAsync(w.args_dev, &ca, sizeof(ca), cudaMemcpyHostToDevice, st);      // pageable source: staged before the call returns
+    if (e != cudaSuccess) return e;
+    bundle_const_kernel<EPN><<<grid, CONST_NW * 32, smem, st>>>(W, (const ConstArgs*)w.args_dev);
     ++*nl;
     return cudaGetLastError();
 }

@@ -251,6 +251,7 @@ struct Workspace {
     int pair_tensor;                              // 1: electron-passing bundle kernel on the warp-level tensor path (3xTF32, FP32 only)
     int pair_const;                               // FP32 kernel set: 0 warp-tile kernels (round 1), 1 pair-per-thread kernels everywhere,
                                                   // 2 (default) row-run GNN bundle kernel + pair-per-thread EPN bundle kernel + row-per-thread far kernel
+    void* args_dev;                               // 1 KB device scratch: argument block of the kernels that take theirs through global memory
     const float* wf_host; const float* wf_dev;    // packed FP32 weights: host mirror and device base (pair_const passes weights as kernel parameters)
     unsigned long long* dedup_rows;               // device counter (statistics): rows whose far part was collapsed, summed over steps
     void* h; void* S; void* u; void* v; void* delta;   // precision-dependent (float or double)

@@ -12,10 +12,7 @@ extern "C" int emu_bundle_const(int epn, int n_warps, const float* weights,
                                 const int* atom_sys, const int* sys_off, const int* npad,
                                 const float* u, const float* v, float* S, float* delta) {
     PairW W;
-    memcpy(W.Cw, weights, sizeof(W.Cw));
     memcpy(W.W2, weights + EDR * HID, sizeof(W.W2));
-    memcpy(W.b2, weights + EDR * HID + HID * HID, sizeof(W.b2));
-    memcpy(W.x32, weights + EDR * HID + HID * HID + HID, sizeof(W.x32));
     ConstArgs a;
     a.n_bundles = n_bundles; a.bundle = reinterpret_cast<const int2*>(bundle_xy); a.work_counter = work_counter;
     a.ustart = ustart; a.pair_i = pair_i; a.pair_j = pair_j; a.near = near; a.e = e;
@@ -23,9 +20,10 @@ extern "C" int emu_bundle_const(int epn, int n_warps, const float* weights,
     a.far0_off = far0_off; a.far0_list = far0_list; a.far0_w = far0_w; a.rep = rep; a.dedup = dedup;
     a.atom_sys = atom_sys; a.sys_off = sys_off; a.npad = npad;
     a.u = u; a.v = v; a.S = S; a.delta = delta;
+    a.Cw = weights; a.b2 = weights + EDR * HID + HID * HID; a.x32 = weights + EDR * HID + HID * HID + HID;
     *work_counter = 0;
     if (n_warps < 1 || n_warps > CONST_NW) return -1;
-    if (epn) emu_launch_cta(n_warps, (size_t)CONST_NW * ConstSmem<true>::PW, [&] { bundle_const_kernel<true>(W, a); });
-    else     emu_launch_cta(n_warps, (size_t)CONST_NW * ConstSmem<false>::PW, [&] { bundle_const_kernel<false>(W, a); });
+    if (epn) emu_launch_cta(n_warps, (size_t)CONST_NW * ConstSmem<true>::PW + ConstSmem<true>::SHARED, [&] { bundle_const_kernel<true>(W, &a); });
+    else     emu_launch_cta(n_warps, (size_t)CONST_NW * ConstSmem<false>::PW + ConstSmem<false>::SHARED, [&] { bundle_const_kernel<false>(W, &a); });
     return 0;
 }

@@ -206,16 +206,16 @@ extern "C" int emu_infer(int T, int n_x, const float* w_packed, size_t n_w, int 
         }
         if (pair_const) {
             k_bconst::PairW W;
-            memcpy(W.Cw, sw.Cw, sizeof(W.Cw)); memcpy(W.W2, sw.W2, sizeof(W.W2)); memcpy(W.b2, sw.b2, sizeof(W.b2));
-            memcpy(W.x32, epn ? sw.W3 : sw.b1, sizeof(W.x32));
+            memcpy(W.W2, sw.W2, sizeof(W.W2));
             k_bconst::ConstArgs a;
             a.n_bundles = n_bundles; a.bundle = bundles.data(); a.work_counter = &work_counter;
             a.ustart = ustart.data(); a.pair_i = pair_i.data(); a.pair_j = pair_j.data(); a.near = near.data(); a.e = e.data();
             a.far_off = far_off.data(); a.far_list = far_list.data();
             a.far0_off = far0_off.data(); a.far0_list = far0_list.data(); a.far0_w = far0_w.data(); a.rep = rep.data(); a.dedup = dedup;
             a.atom_sys = atom_sys.data(); a.sys_off = off; a.npad = npad.data(); a.u = u.data(); a.v = v.data(); a.S = S.data(); a.delta = delta.data();
-            if (epn) emu_launch_cta(CONST_NW, (size_t)CONST_NW * k_bconst::ConstSmem<true>::PW, [&] { k_bconst::bundle_const_kernel<true>(W, a); });
-            else     emu_launch_cta(CONST_NW, (size_t)CONST_NW * k_bconst::ConstSmem<false>::PW, [&] { k_bconst::bundle_const_kernel<false>(W, a); });
+            a.Cw = sw.Cw; a.b2 = sw.b2; a.x32 = epn ? sw.W3 : sw.b1;
+            if (epn) emu_launch_cta(CONST_NW, (size_t)CONST_NW * k_bconst::ConstSmem<true>::PW + k_bconst::ConstSmem<true>::SHARED, [&] { k_bconst::bundle_const_kernel<true>(W, &a); });
+            else     emu_launch_cta(CONST_NW, (size_t)CONST_NW * k_bconst::ConstSmem<false>::PW + k_bconst::ConstSmem<false>::SHARED, [&] { k_bconst::bundle_const_kernel<false>(W, &a); });
             return;
         }
         k_bundle::BundleArgs<float> a;
