@@ -25,7 +25,12 @@
 #include "epnn_internal.cuh"
 #endif
 
+#ifndef CONST_NW
 #define CONST_NW 8
+#endif
+#ifndef CONST_CTAS_EPN
+#define CONST_CTAS_EPN 2
+#endif
 #define CUVS 68                         // row stride of the staged u | v rows (64 + 4: rows start in different bank groups)
 #define PAD_ROW BUNDLE_ATOMS            // extra row: v = b1 (a_j = 0, e = 0), the pad pseudo-atom of the GNN's far tiles
 
@@ -128,7 +133,7 @@ template <bool EPN> struct ConstSmem {
 };
 
 template <bool EPN>
-__global__ void __launch_bounds__(CONST_NW * 32, EPN ? 2 : 1) bundle_const_kernel(const __grid_constant__ PairW W, const ConstArgs* __restrict__ ap) {
+__global__ void __launch_bounds__(CONST_NW * 32, EPN ? CONST_CTAS_EPN : 1) bundle_const_kernel(const __grid_constant__ PairW W, const ConstArgs* __restrict__ ap) {
     const ConstArgs a = *ap;
 #ifdef EPNN_CPU_EMU
     float* csm = emu_smem;
@@ -318,7 +323,7 @@ static cudaError_t launch_const(const Workspace& w, const StepW<float>& sw, cuda
     const size_t smem = ConstSmem<EPN>::bytes();
     e = cudaFuncSetAttribute(bundle_const_kernel<EPN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const int per_sm = EPN ? 2 : 1;
+    const int per_sm = EPN ? CONST_CTAS_EPN : 1;
     int grid = div_up(w.n_bundles, CONST_NW);
     if (grid > w.sm_count * per_sm) grid = w.sm_count * per_sm;
     e = cudaMemcpyAsync(w.args_dev, &ca, sizeof(ca), cudaMemcpyHostToDevice, st);      // pageable source: staged before the call returns
