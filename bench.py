@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("--atoms", type=int, default=2220, help="atoms of the protein-like system (workload protein)")
     ap.add_argument("--npad", type=int, default=29, help="pad size N of the reference's dense model (qm9 workload)")
     ap.add_argument("--checkpoint", default=None, help="default: decay_model_weights (qm9, protein), model_weights (qm9_test), model2_weights (ssi)")
-    ap.add_argument("--precision", type=int, default=32, choices=[32, 64])
+    ap.add_argument("--precision", type=int, default=32, choices=[0, 32, 48, 64], help="0 auto (probe), 32 FP32, 48 mixed (FP64 per-atom kernel), 64 all FP64")
     ap.add_argument("--chunk-atoms", type=int, default=0, help="override the library's internal batch size")
     ap.add_argument("--ref-molecules", type=int, default=2048, help="molecules per step of the CPU reference arm")
     ap.add_argument("--gnn-far-tensor", type=int, default=0, choices=[0, 1],

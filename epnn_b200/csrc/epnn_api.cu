@@ -23,7 +23,11 @@ struct DevBuf {
 struct epnn_ctx {
     int device = 0, T = 0, n_x = 0, n_species = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
-    int precision = 32, timing = 0, keep_hidden = 0;
+    int precision = 32, timing = 0, keep_hidden = 0;      // precision: 32, 48 (mixed), 64, 0 (auto: probe on the first call)
+    int eff_precision = 32;      // precision of the call in flight (32 / 48 / 64)
+    int auto_choice = 0;         // precision chosen by the probe (0 = not probed yet)
+    double auto_tol = 2.5e-6;    // a cheaper precision is accepted if its probe charges are within this of the FP64 kernels
+    double probe_err32 = -1, probe_err48 = -1;
     int far_tensor = 0;          // option "gnn_far_tensor"
     int dedup_far = 1;           // option "dedup_far": collapse species-equivalent far columns (exact)
     int pair_tensor = 0;         // option "pair_tensor": EPN bundle kernel on mma.sync 3xTF32 (precision 32 only)
@@ -193,8 +197,13 @@ extern "C" int epnn_set_option(epnn_ctx* c, const char* key, double value) {
     if (!c || !key) return EPNN_E_INVALID;
     const std::string k(key);
     if (k == "precision") {
-        if (value != 32 && value != 64) return fail(c, EPNN_E_INVALID, "precision must be 32 or 64");
+        if (value != 32 && value != 64 && value != 48 && value != 0)
+            return fail(c, EPNN_E_INVALID, "precision must be 32, 48 (mixed), 64 or 0 (auto)");
         c->precision = (int)value;
+        c->auto_choice = 0;
+    } else if (k == "auto_tol") {
+        if (!(value > 0)) return fail(c, EPNN_E_INVALID, "auto_tol must be positive");
+        c->auto_tol = value; c->auto_choice = 0;
     } else if (k == "timing") c->timing = value != 0;
     else if (k == "keep_hidden") c->keep_hidden = value != 0;
     else if (k == "gnn_far_tensor") c->far_tensor = value != 0;
@@ -282,6 +291,8 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
                      const int* d_species, const float* d_Q, const int* d_npad_in, float* d_out32, double* d_out64,
                      epnn_stats* stats, Timer& tm, int* n_launch, bool neighbors_only, Workspace* ws_out) {
     cudaStream_t st = c->stream;
+    // mixed precision (48): FP32 pair kernels around an FP64 per-atom kernel (state l2 / h in FP64, S / u / v / delta in FP32)
+    const bool mixed = sizeof(R) == 4 && c->eff_precision == 48;
     Workspace w;
     memset(&w, 0, sizeof(w));
     w.n_atoms = n_atoms; w.n_sys = n_sys; w.sm_count = c->sm_count;
@@ -465,25 +476,35 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     if (ws_out) *ws_out = w;
     if (neighbors_only) return EPNN_OK;
 
-    ENS(B_H, sizeof(R) * HD * (size_t)n_atoms, w.h, void*);
-    ENS(B_L2, sizeof(R) * HID * (size_t)n_atoms, w.l2, void*);
+    const size_t state_sz = mixed ? sizeof(double) : sizeof(R);
+    ENS(B_H, state_sz * HD * (size_t)n_atoms, w.h, void*);
+    ENS(B_L2, state_sz * HID * (size_t)n_atoms, w.l2, void*);
     ENS(B_S, sizeof(R) * HID * (size_t)n_atoms * w.nsplit, w.S, void*);
     ENS(B_U, sizeof(R) * HID * (size_t)n_atoms, w.u, void*);
     ENS(B_V, sizeof(R) * HID * (size_t)n_atoms, w.v, void*);
     ENS(B_DELTA, sizeof(R) * (size_t)(w.P + 1), w.delta, void*);
 #undef ENS
-    CU(c, cudaMemsetAsync(w.h, 0, sizeof(R) * HD * (size_t)n_atoms, st));
+    CU(c, cudaMemsetAsync(w.h, 0, state_sz * HD * (size_t)n_atoms, st));
 
     const R* wb = sizeof(R) == 4 ? (const R*)c->wf : (const R*)c->wd;
     const UpdW<R> upd = upd_view<R>(wb, c->po);
     std::vector<StepW<R>> msg(c->T), pas(c->T);
     for (int t = 0; t < c->T; ++t) { msg[t] = step_view<R>(wb, c->po.msg[t]); pas[t] = step_view<R>(wb, c->po.pas[t]); }
+    const UpdW<double> updd = upd_view<double>(c->wd, c->po);
+    std::vector<StepW<double>> msgd(mixed ? c->T : 0), pasd(mixed ? c->T : 0);
+    for (int t = 0; t < (int)msgd.size(); ++t) { msgd[t] = step_view<double>(c->wd, c->po.msg[t]); pasd[t] = step_view<double>(c->wd, c->po.pas[t]); }
+    // per-atom kernel in the precision of the call; prev / next index the message (0 .. T-1) and pass (T .. 2T-1) MLPs, -1 = none
+    auto atom = [&](int mode, int prev, int next, int h_is_zero, float* o32, double* o64) -> cudaError_t {
+        auto pick = [&](auto& ms, auto& ps, int i) { return i < 0 ? nullptr : (i < c->T ? &ms[i] : &ps[i - c->T]); };
+        if (mixed) return launch_atom_mixed(w, mode, pick(msgd, pasd, prev), &updd, pick(msgd, pasd, next), h_is_zero, o32, o64, st, n_launch);
+        return launch_atom<R>(w, mode, pick(msg, pas, prev), &upd, pick(msg, pas, next), h_is_zero, o32, o64, st, n_launch);
+    };
 
     // Sharding only concerns the large-system pair kernels; a chunk without large systems runs replicated.
     const bool sharded = c->shard_world > 1 && w.n_rg_large > 0;
     if (!sharded) { w.shard_rank = 0; w.shard_world = 1; }
     // ---- GNN layer: T message-passing steps (charge_gn.py:60-74)
-    CU(c, launch_atom<R>(w, ATOM_PROJECT, nullptr, nullptr, &msg[0], 1, nullptr, nullptr, st, n_launch));
+    CU(c, atom(ATOM_PROJECT, -1, 0, 1, nullptr, nullptr));
     tm.mark(4);
     for (int t = 0; t < c->T; ++t) {
         if (sharded) CU(c, cudaMemsetAsync(w.S, 0, sizeof(R) * HID * (size_t)n_atoms * w.nsplit, st));
@@ -500,9 +521,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
         if (sharded && c->allreduce(c->allreduce_user, w.S, (size_t)HID * n_atoms * w.nsplit, sizeof(R) == 8, (void*)st) != 0)
             return fail(c, EPNN_E_CUDA, "allreduce callback failed (GNN step %d)", t);
         tm.mark(3);
-        const StepW<R>* next = t + 1 < c->T ? &msg[t + 1] : &pas[0];
-        CU(c, launch_atom<R>(w, ATOM_UPDATE | ATOM_PROJECT | (t == 0 ? ATOM_FIRST : 0) | (t + 1 == c->T ? ATOM_WRITE_H : 0),
-                             &msg[t], &upd, next, 0, nullptr, nullptr, st, n_launch));
+        CU(c, atom(ATOM_UPDATE | ATOM_PROJECT | (t == 0 ? ATOM_FIRST : 0) | (t + 1 == c->T ? ATOM_WRITE_H : 0), t, t + 1, 0, nullptr, nullptr));
         tm.mark(t + 1 < c->T ? 4 : 6);
     }
     // ---- EPN layer: T electron-passing passes (charge_gn.py:98-118)
@@ -514,13 +533,13 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
             return fail(c, EPNN_E_CUDA, "allreduce callback failed (EPN pass %d)", t);
         tm.mark(5);
         if (t + 1 < c->T)
-            CU(c, launch_atom<R>(w, ATOM_QUPDATE | ATOM_PROJECT, nullptr, nullptr, &pas[t + 1], 0, nullptr, nullptr, st, n_launch));
+            CU(c, atom(ATOM_QUPDATE | ATOM_PROJECT, -1, c->T + t + 1, 0, nullptr, nullptr));
         else
-            CU(c, launch_atom<R>(w, ATOM_QUPDATE | ATOM_OUTPUT, nullptr, nullptr, nullptr, 0, d_out32, d_out64, st, n_launch));
+            CU(c, atom(ATOM_QUPDATE | ATOM_OUTPUT, -1, -1, 0, d_out32, d_out64));
         tm.mark(6);
     }
     c->hidden_atoms = n_atoms;
-    c->hidden_precision = sizeof(R) == 4 ? 32 : 64;
+    c->hidden_precision = (sizeof(R) == 4 && !mixed) ? 32 : 64;
     return EPNN_OK;
 }
 
@@ -553,6 +572,51 @@ static int validate_offsets(epnn_ctx* c, int64_t n_sys, const int32_t* off) {
     return EPNN_OK;
 }
 
+
+static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_io, const float* xyz, const int32_t* species,
+                      const float* Q, const int32_t* npad_host, float* q_out, double* q_out64, epnn_stats* stats);
+
+// "precision" 0 (auto): run a bounded prefix of the first call through the FP32, mixed and FP64 kernels and keep the cheapest
+// precision whose charges stay within auto_tol of the FP64 kernels (which agree with the float64 oracle to 1e-9).  The
+// conditioning of the model is a property of checkpoint AND data (|h| reaches 150 for model_weights on QM9), so it is
+// measured on the caller's own systems, not assumed.  Sticky for the ctx until "precision" / "auto_tol" is set again.
+static int probe_precision(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_io, const float* xyz, const int32_t* species,
+                           const float* Q, const int32_t* npad_host) {
+    int64_t ns = n_sys < 64 ? n_sys : 64;
+    while (ns > 1 && off[ns] > 8192) --ns;
+    const int64_t na = off[ns];
+    c->probe_err32 = c->probe_err48 = -1;
+    if (na > 8192) { c->auto_choice = 32; return EPNN_OK; }       // one big system: three extra inferences would not be a probe
+    std::vector<float> hx, hQ, tmp((size_t)na);
+    std::vector<int32_t> hs;
+    const float* px = xyz; const int32_t* ps = species; const float* pq = Q;
+    if (!host_io) {
+        hx.resize(3 * (size_t)na); hs.resize((size_t)na); hQ.resize((size_t)ns);
+        CU(c, cudaSetDevice(c->device));
+        CU(c, cudaMemcpy(hx.data(), xyz, sizeof(float) * 3 * (size_t)na, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(hs.data(), species, sizeof(int32_t) * (size_t)na, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(hQ.data(), Q, sizeof(float) * (size_t)ns, cudaMemcpyDeviceToHost));
+        px = hx.data(); ps = hs.data(); pq = hQ.data();
+    }
+    std::vector<double> q[3];
+    const int prec[3] = {64, 32, 48};
+    const int64_t hidden_atoms = c->hidden_atoms;
+    int rc = EPNN_OK;
+    for (int k = 0; k < 3 && rc == EPNN_OK; ++k) {
+        q[k].resize((size_t)na);
+        c->precision = prec[k];
+        rc = infer_impl(c, ns, off, true, px, ps, pq, npad_host, tmp.data(), q[k].data(), nullptr);
+    }
+    c->precision = 0;
+    c->hidden_atoms = hidden_atoms;
+    if (rc != EPNN_OK) return rc;
+    double e32 = 0, e48 = 0;
+    for (int64_t i = 0; i < na; ++i) { e32 = fmax(e32, fabs(q[1][i] - q[0][i])); e48 = fmax(e48, fabs(q[2][i] - q[0][i])); }
+    c->probe_err32 = e32; c->probe_err48 = e48;
+    c->auto_choice = e32 <= c->auto_tol ? 32 : (e48 <= c->auto_tol ? 48 : 64);
+    return EPNN_OK;
+}
+
 static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_io, const float* xyz, const int32_t* species,
                       const float* Q, const int32_t* npad_host, float* q_out, double* q_out64, epnn_stats* stats) {
     if (!c) return EPNN_E_INVALID;
@@ -561,6 +625,11 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
     if (stats) memset(stats, 0, sizeof(*stats));
     if (n_sys == 0) return EPNN_OK;
     if (!xyz || !species || !Q || (!q_out && !q_out64)) return fail(c, EPNN_E_INVALID, "NULL input/output pointer");
+    if (c->precision == 0 && c->auto_choice == 0) {
+        rc = probe_precision(c, n_sys, off, host_io, xyz, species, Q, npad_host);
+        if (rc != EPNN_OK) return rc;
+    }
+    c->eff_precision = c->precision == 0 ? c->auto_choice : c->precision;
     CU(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     std::vector<int64_t> bounds;
@@ -605,7 +674,7 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
         }
         tm.mark(1);
         Workspace w;
-        if (c->precision == 64)
+        if (c->eff_precision == 64)
             rc = run_chunk<double>(c, ns, na, off + s0, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
         else
             rc = run_chunk<float>(c, ns, na, off + s0, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
@@ -630,6 +699,8 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
         stats->n_far_dedup_rows = (int64_t)nn[1];
         stats->n_systems = n_sys; stats->n_atoms = off[n_sys]; stats->n_chunks = (int64_t)bounds.size() - 1;
         stats->n_launches = n_launch;
+        stats->precision_used = c->eff_precision;
+        stats->probe_err32 = (float)c->probe_err32; stats->probe_err48 = (float)c->probe_err48;
     }
     tm.finish(stats);
     if (bounds.size() != 2) c->hidden_atoms = 0;       // hidden state only meaningful for single-chunk calls

@@ -21,14 +21,23 @@
 // Work unit = one warp on a tile of 32 consecutive atoms; the dense layers run through tile_gemm.
 #include "epnn_internal.cuh"
 
-template <typename R> struct AtomArgs {
+// R = arithmetic and state type (weights, l2, h); IO = type of the buffers shared with the pair kernels (S planes in, u / v out,
+// delta in).  IO = float with R = double is the "mixed" precision: FP32 pair kernels around an FP64 per-atom kernel.
+template <typename R, typename IO> struct AtomArgs {
     int n_atoms, mode, nsplit, h_is_zero;
     const int* atom_sys; const int* sys_off; const int* npad; const int* species;
-    const R* Spart; R* h; R* l2; const R* HG; const R* g; const R* cb; UpdW<R> upd;
-    const int* rowptr; const int* col; const int* pid; const R* delta; double* q;
-    const R* Pf; const R* Aq64; const R* Ax; R* u; R* v;
+    const IO* Spart; R* h; R* l2; const R* HG; const R* g; const R* cb; UpdW<R> upd;
+    const int* rowptr; const int* col; const int* pid; const IO* delta; double* q;
+    const R* Pf; const R* Aq64; const R* Ax; IO* u; IO* v;
     float* q_out; double* q_out64;
 };
+template <typename R, typename IO> __device__ __forceinline__ Vec4<R> ld_io(const IO* p) {
+    const Vec4<IO> t = ldv(p);
+    Vec4<R> r; r.x = (R)t.x; r.y = (R)t.y; r.z = (R)t.z; r.w = (R)t.w; return r;
+}
+template <typename R, typename IO> __device__ __forceinline__ void st_io(IO* p, Vec4<R> v) {
+    Vec4<IO> t; t.x = (IO)v.x; t.y = (IO)v.y; t.z = (IO)v.z; t.w = (IO)v.w; stv(p, t);
+}
 
 #ifndef ATOM_NW
 #define ATOM_NW 12
@@ -48,8 +57,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #define ATOM_W_PROJ (HID * 64 + 64 + MAX_SPECIES * 64)                                      // 3136
 #define ATOM_TILE (32 * 64 + 32 * HID)                                                      // 3072 per warp
 
-template <typename R, int NW>
-__global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
+template <typename R, int NW, typename IO>
+__global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) {
 #ifdef EPNN_CPU_EMU
     unsigned char* smem_raw = reinterpret_cast<unsigned char*>(emu_smem);
 #else
@@ -148,7 +157,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
                     if (!first) lv = ldv(a.l2 + (int64_t)at * HID + ch * 4);
                     const int ns = slot_ns[sl];
                     for (int sp = 0; sp < ns; ++sp)
-                        sv = vadd(sv, ldv(a.Spart + ((int64_t)sp * a.n_atoms + at) * HID + ch * 4));
+                        sv = vadd(sv, ld_io<R, IO>(a.Spart + ((int64_t)sp * a.n_atoms + at) * HID + ch * 4));
                 }
                 stv(T64 + tile_off(sl, ch, 64), lv);
                 stv(T64 + tile_off(sl, 8 + ch, 64), sv);
@@ -227,7 +236,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
                 zero_acc(acc);
                 if (!a.h_is_zero) tile_gemm_unr<R, HID, 64, ATOM_UNR>(T32b, sP, half * HID + og * 4, acc, pg);
                 const Vec4<R> aq = ldv(sAq + half * HID + og * 4);
-                R* dst = half == 0 ? a.u : a.v;
+                IO* dst = half == 0 ? a.u : a.v;
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     const int at = base + pg * 8 + s;
@@ -237,7 +246,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
                         Vec4<R> o;
                         o.x = acc[s][0] + fma(qv, aq.x, ax.x); o.y = acc[s][1] + fma(qv, aq.y, ax.y);
                         o.z = acc[s][2] + fma(qv, aq.z, ax.z); o.w = acc[s][3] + fma(qv, aq.w, ax.w);
-                        stv(dst + (int64_t)at * HID + og * 4, o);
+                        st_io<R, IO>(dst + (int64_t)at * HID + og * 4, o);
                     }
                 }
             }
@@ -247,31 +256,42 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R> a) {
 }
 
 #ifndef EPNN_CPU_EMU
-template <typename R>
-cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd, const StepW<R>* next,
-                        int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl) {
+template <typename R, typename IO>
+cudaError_t launch_atom_io(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd, const StepW<R>* next,
+                           int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0) return cudaSuccess;
     if constexpr (sizeof(R) == 4) {
         if (w.pair_const == 1) return launch_atom_const(w, mode, prev, upd, next, h_is_zero, q_out, q_out64, st, nl);   // experimental (epnn_atom_const.cu)
     }
     constexpr int NW = sizeof(R) == 4 ? ATOM_NW : 4;
-    AtomArgs<R> aa;
+    AtomArgs<R, IO> aa;
     memset(&aa, 0, sizeof(aa));
     aa.n_atoms = w.n_atoms; aa.mode = mode; aa.nsplit = w.nsplit; aa.h_is_zero = h_is_zero;
     aa.atom_sys = w.atom_sys; aa.sys_off = w.sys_off; aa.npad = w.npad; aa.species = w.species;
-    aa.Spart = (const R*)w.S; aa.h = (R*)w.h; aa.l2 = (R*)w.l2;
+    aa.Spart = (const IO*)w.S; aa.h = (R*)w.h; aa.l2 = (R*)w.l2;
     if (mode & ATOM_UPDATE) { aa.HG = prev->HG; aa.g = prev->g; aa.upd = *upd; aa.cb = (mode & ATOM_FIRST) ? upd->c1 : upd->cb1; }
-    aa.rowptr = w.rowptr; aa.col = w.col; aa.pid = w.pid; aa.delta = (const R*)w.delta; aa.q = w.q;
+    aa.rowptr = w.rowptr; aa.col = w.col; aa.pid = w.pid; aa.delta = (const IO*)w.delta; aa.q = w.q;
     if (mode & ATOM_PROJECT) { aa.Pf = next->Pf; aa.Aq64 = next->Aq64; aa.Ax = h_is_zero ? next->Ax64 : next->Axf; }
-    aa.u = (R*)w.u; aa.v = (R*)w.v; aa.q_out = q_out; aa.q_out64 = q_out64;
+    aa.u = (IO*)w.u; aa.v = (IO*)w.v; aa.q_out = q_out; aa.q_out64 = q_out64;
     const size_t smem = sizeof(R) * (ATOM_W_UPD + ATOM_W_PROJ + (size_t)NW * ATOM_TILE + NW * 64) + sizeof(int) * NW * 64;
-    cudaError_t e = cudaFuncSetAttribute(atom_kernel<R, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(atom_kernel<R, NW, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int grid = div_up(div_up(w.n_atoms, 32), NW);
     if (grid > w.sm_count) grid = w.sm_count;
-    atom_kernel<R, NW><<<grid, NW * 32, smem, st>>>(aa);
+    atom_kernel<R, NW, IO><<<grid, NW * 32, smem, st>>>(aa);
     ++*nl;
     return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd, const StepW<R>* next,
+                        int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl) {
+    return launch_atom_io<R, R>(w, mode, prev, upd, next, h_is_zero, q_out, q_out64, st, nl);
+}
+// "mixed" precision: FP64 per-atom arithmetic and state, FP32 buffers towards the pair kernels
+cudaError_t launch_atom_mixed(const Workspace& w, int mode, const StepW<double>* prev, const UpdW<double>* upd, const StepW<double>* next,
+                              int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl) {
+    return launch_atom_io<double, float>(w, mode, prev, upd, next, h_is_zero, q_out, q_out64, st, nl);
 }
 
 template cudaError_t launch_atom<float>(const Workspace&, int, const StepW<float>*, const UpdW<float>*, const StepW<float>*,

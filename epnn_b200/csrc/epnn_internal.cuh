@@ -310,6 +310,8 @@ template <typename R> cudaError_t launch_epn_pair(const Workspace& w, const Step
 template <typename R> cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd,
                                               const StepW<R>* next, int h_is_zero, float* q_out, double* q_out64,
                                               cudaStream_t st, int* n_launch);
+cudaError_t launch_atom_mixed(const Workspace& w, int mode, const StepW<double>* prev, const UpdW<double>* upd, const StepW<double>* next,
+                              int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* n_launch);   // precision 48
 cudaError_t launch_atom_const(const Workspace& w, int mode, const StepW<float>* prev, const UpdW<float>* upd, const StepW<float>* next,
                               int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* n_launch);   // option pair_const
 

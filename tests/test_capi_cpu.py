@@ -74,10 +74,12 @@ def test_stats_struct_matches_the_header():
     text = open(os.path.join(ROOT, "include", "epnn_b200.h")).read()
     body = re.search(r"typedef struct epnn_stats \{(.*?)\} epnn_stats;", text, flags=re.S).group(1)
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    fields = re.findall(r"\b(int64_t|float)\s+([a-z0-9_]+)\s*;", body)
-    ctype = {"int64_t": C.c_int64, "float": C.c_float}
+    fields = re.findall(r"\b(int64_t|int32_t|float)\s+([a-z0-9_]+)\s*;", body)
+    ctype = {"int64_t": C.c_int64, "int32_t": C.c_int32, "float": C.c_float}
+    size = {"int64_t": 8, "int32_t": 4, "float": 4}
     assert [(n, ctype[t]) for t, n in fields] == list(_capi.Stats._fields_)
-    assert C.sizeof(_capi.Stats) == 8 * sum(t == "int64_t" for t, _ in fields) + 4 * sum(t == "float" for t, _ in fields)
+    packed = sum(size[t] for t, _ in fields)
+    assert C.sizeof(_capi.Stats) == (packed + 7) // 8 * 8          # no internal padding; tail padded to the int64 alignment
 
 
 def test_bench_real_data_workloads_are_the_reference_sets():

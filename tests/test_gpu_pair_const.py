@@ -17,7 +17,7 @@ from oracle import epnn_oracle as O
 
 pytestmark = [pytest.mark.gpu]
 
-TOL_FP32 = {"decay_model_weights": 1e-5, "model2_weights": 5e-5, "model_weights": 1e-3}
+TOL_FP32 = {"decay_model_weights": 2e-6, "model2_weights": 1e-5, "model_weights": 2e-4}     # tests/test_gpu_parity.py: measured floors
 
 
 def _engine(weights, name, kset=1):
@@ -53,7 +53,7 @@ def test_pair_const_vs_oracle_and_default(engines, weights, mixed, name, dedup, 
     simt.set_option("keep_hidden", 1)
     q_simt = simt.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1]
     h_simt = simt.hidden(int(offs[-1]))
-    assert np.abs(q64 - q_simt).max() < 0.5 * TOL_FP32[name]
+    assert np.abs(q64 - q_simt).max() < TOL_FP32[name]
     assert np.abs(h - h_simt).max() <= 2e-5 * max(1.0, np.abs(h_simt).max())
 
 

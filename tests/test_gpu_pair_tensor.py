@@ -9,7 +9,7 @@ from oracle import epnn_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-TOL_FP32 = {"decay_model_weights": 1e-5, "model2_weights": 5e-5, "model_weights": 1e-3}
+TOL_FP32 = {"decay_model_weights": 3e-6, "model2_weights": 1e-5, "model_weights": 2e-4}     # FP32 floors of tests/test_gpu_parity.py (+ the 3xTF32 split for decay)
 
 
 @pytest.mark.parametrize("name", ["decay_model_weights", "model2_weights", "model_weights"])
@@ -33,7 +33,7 @@ def test_pair_tensor_vs_oracle_and_simt(engines, weights, mixed, name):
     sums = np.add.reduceat(q64, offs[:-1])
     assert np.abs(sums - Q).max() < 1e-6                                    # antisymmetric transfers: conserved by construction
     simt = engines(name, 32).infer_batch(offs, xyz, sp, Q, 41, want_f64=True)[1]
-    assert 0 < np.abs(q64 - simt).max() < 0.5 * TOL_FP32[name], (name, np.abs(q64 - simt).max())   # another kernel really ran
+    assert 0 < np.abs(q64 - simt).max() < TOL_FP32[name], (name, np.abs(q64 - simt).max())   # another kernel really ran
 
 
 def test_pair_tensor_golden_871(weights, mixed, val871):

@@ -12,7 +12,7 @@ extern "C" int emu_atom_kernel(int mode, int h_is_zero, int n_atoms, int nsplit,
                                const int* atom_sys, const int* sys_off, const int* npad, const int* species,
                                const float* Spart, float* h, float* l2, const int* rowptr, const int* col, const int* pid,
                                const float* delta, double* q, float* u, float* v, float* q_out, double* q_out64) {
-    AtomArgs<float> aa;
+    AtomArgs<float, float> aa;
     memset(&aa, 0, sizeof(aa));
     aa.n_atoms = n_atoms; aa.mode = mode; aa.nsplit = nsplit; aa.h_is_zero = h_is_zero;
     aa.atom_sys = atom_sys; aa.sys_off = sys_off; aa.npad = npad; aa.species = species;
@@ -24,7 +24,7 @@ extern "C" int emu_atom_kernel(int mode, int h_is_zero, int n_atoms, int nsplit,
     aa.u = u; aa.v = v; aa.q_out = q_out; aa.q_out64 = q_out64;
     constexpr int NW = 4;
     const size_t smem = sizeof(float) * (ATOM_W_UPD + ATOM_W_PROJ + (size_t)NW * ATOM_TILE + NW * 64) + sizeof(int) * NW * 64;
-    emu_launch_grid(2, NW, smem / sizeof(float) + 8, [&] { atom_kernel<float, NW>(aa); });
+    emu_launch_grid(2, NW, smem / sizeof(float) + 8, [&] { atom_kernel<float, NW, float>(aa); });
     return 0;
 }
 
