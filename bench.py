@@ -69,8 +69,10 @@ def parse_args():
     ap.add_argument("--pair-tensor", type=int, default=0, choices=[0, 1],
                     help="small systems: electron-passing pair MLP on mma.sync 3xTF32 instead of FP32 SIMT (opt-in)")
     ap.add_argument("--pair-const", type=int, default=2, choices=[0, 1, 2],
-                    help="EXPERIMENTAL (unvalidated): pair-per-thread FP32 bundle kernels with weights as uniform operands")
+                    help="FP32 kernel set: 2 default (row-run GNN bundle kernel + pair-per-thread EPN kernel), 1 pair-per-thread everywhere, 0 round-1 warp-tile kernels")
     ap.add_argument("--dedup-far", type=int, default=1, choices=[0, 1], help="collapse species-equivalent far columns (exact; 0 = ablation)")
+    ap.add_argument("--secondary", type=int, default=1, choices=[0, 1], help="append the secondary blocks (strong scaling, live-GNN checkpoints, the reference's own configs) to the JSON line")
+    ap.add_argument("--strong-atoms", type=int, default=100_000, help="atoms of the large system of the strong-scaling block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
@@ -83,10 +85,26 @@ def parse_args():
 
 
 # ------------------------------------------------------------------------------------------------ workloads
+_QM9_CACHE = {}
+
+
+def qm9_stream(n_mol, n_x, seed, first):
+    """synth.qm9_shaped, memoised: the secondary blocks reuse the headline stream (generation is host work, outside every timed region)."""
+    from epnn_b200 import synth
+    key = (n_mol, seed, first)
+    if key not in _QM9_CACHE:
+        _QM9_CACHE.clear()
+        offs, xyz, sp9, Q = synth.qm9_shaped(n_mol, 9, seed=seed, first=first)
+        _QM9_CACHE[key] = (offs, np.ascontiguousarray(xyz, np.float32), sp9, Q)
+    offs, xyz, sp9, Q = _QM9_CACHE[key]
+    sp = sp9 if n_x == 9 else np.where(sp9 >= 5, sp9 + 1, sp9).astype(np.int32)      # the 10-wide table inserts P at index 5
+    return offs, xyz, sp, Q
+
+
 def make_workload(args, w, rank):
     from epnn_b200 import synth
     if args.workload == "qm9":
-        offs, xyz, sp, Q = synth.qm9_shaped(args.molecules, w.n_x, seed=args.seed, first=rank * args.molecules)
+        offs, xyz, sp, Q = qm9_stream(args.molecules, w.n_x, args.seed, rank * args.molecules)
         npad = np.full(args.molecules, args.npad, np.int32)
         desc = {"workload": f"synthetic QM9-shaped molecules (<=29 atoms), {args.molecules} per GPU per step, pad N={args.npad}",
                 "molecules_per_gpu": args.molecules}
@@ -296,35 +314,53 @@ def cpu_baseline_subprocess(args):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-def run_b200(args):
-    import torch
-    import torch.distributed as dist
+class Box:
+    """torch / torch.distributed plumbing of one rank (device memory, streams, barriers) -- not the product."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={self.world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: epnn_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize(self.dev)
+
+    def max_over_ranks(self, x):
+        if self.world == 1:
+            return float(x)
+        t = self.torch.tensor([x], device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, xs):
+        if self.world == 1:
+            return [float(x) for x in xs]
+        t = self.torch.tensor(list(xs), device=self.dev, dtype=self.torch.float64)
+        self.dist.all_reduce(t)
+        return [float(x) for x in t.tolist()]
+
+
+def make_engine(box, args, ckpt, precision=None, timing=True):
     from epnn_b200.checkpoint import load_weights
     from epnn_b200.engine import Engine
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: epnn_b200 has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    # CPU baseline first (rank 0, N = 1 only), before this process owns a CUDA context
-    cpu_base = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_baseline_subprocess(args)
-
-    w = load_weights(os.path.join(GOLDEN, "checkpoints", args.checkpoint))
-    offs, xyz, sp, Q, npad, desc = make_workload(args, w, rank)
-    n_atoms = int(offs[-1])
-    eng = Engine(w, device=local, precision=args.precision)
-    eng.set_option("timing", 1)
+    w = load_weights(os.path.join(GOLDEN, "checkpoints", ckpt))
+    eng = Engine(w, device=box.local, precision=args.precision if precision is None else precision)
+    if timing:
+        eng.set_option("timing", 1)
     if args.chunk_atoms:
         eng.set_option("chunk_atoms", args.chunk_atoms)
     if args.gnn_far_tensor:
@@ -334,60 +370,54 @@ def run_b200(args):
     if args.pair_tensor:
         eng.set_option("pair_tensor", 1)
     eng.set_option("pair_const", args.pair_const)
-    stream = torch.cuda.ExternalStream(eng.stream, device=dev)
-    sharded_system = args.workload == "protein" and world > 1
-    if sharded_system:                       # one big system: pair kernels split over the ranks, all-reduce per step / pass
-        eng.set_shard(rank, world)
+    return w, eng
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
+
+def time_case(box, eng, offs, xyz, sp, Q, npad, steps, warmup, host_too=True, clocks=False):
+    """W warm-up + K timed steps of one workload on this rank's engine.  Device-resident arm (inputs already in HBM, CUDA
+    events on the ctx stream, max over ranks) and, if asked, the end-to-end arm through the host API (pinned host buffers,
+    H2D + D2H inside the timed region).  Returns a dict; q64 = the FP64 copy of the charges of the device arm."""
+    torch = box.torch
+    n_atoms = int(offs[-1])
+    stream = torch.cuda.ExternalStream(eng.stream, device=box.dev)
 
     def timed(step_fn):
-        """W warm-up + K timed steps; CUDA events on the ctx stream; returns (ms, per-phase stats sum, clocks)."""
-        for _ in range(args.warmup):
+        for _ in range(warmup):
             step_fn()
-        barrier()
-        clk = ClockSampler(local)
-        if rank == 0:
+        box.barrier()
+        clk = ClockSampler(box.local)
+        if clocks and box.rank == 0:
             clk.start()
             time.sleep(0.25)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         acc = {}
-        barrier()
+        box.barrier()
         e0.record(stream)
-        for _ in range(args.steps):
+        for _ in range(steps):
             step_fn()
             for k, v in eng.last_stats.items():
                 acc[k] = acc.get(k, 0) + v
         e1.record(stream)
         e1.synchronize()
-        barrier()
-        ms = e0.elapsed_time(e1)
-        clocks = clk.stop() if rank == 0 else None
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, acc, clocks
+        box.barrier()
+        ms = box.max_over_ranks(e0.elapsed_time(e1))
+        return ms, acc, (clk.stop() if clocks and box.rank == 0 else None)
 
-    # ---- (1) device-resident: inputs already in HBM when the timed region starts
-    d_xyz = torch.from_numpy(xyz).to(dev)
-    d_sp = torch.from_numpy(sp).to(dev)
-    d_Q = torch.from_numpy(Q).to(dev)
-    d_out = torch.empty(n_atoms, dtype=torch.float32, device=dev)
-    torch.cuda.synchronize(dev)
+    d_xyz = torch.from_numpy(xyz).to(box.dev)
+    d_sp = torch.from_numpy(sp).to(box.dev)
+    d_Q = torch.from_numpy(Q).to(box.dev)
+    d_out = torch.empty(n_atoms, dtype=torch.float32, device=box.dev)
+    d_out64 = torch.empty(n_atoms, dtype=torch.float64, device=box.dev)
+    torch.cuda.synchronize(box.dev)
 
     def step_dev():
-        eng.infer_batch_dev(offs, d_xyz.data_ptr(), d_sp.data_ptr(), d_Q.data_ptr(), npad, d_out.data_ptr())
+        eng.infer_batch_dev(offs, d_xyz.data_ptr(), d_sp.data_ptr(), d_Q.data_ptr(), npad, d_out.data_ptr(), d_out64.data_ptr())
 
-    ms_dev, acc, clocks = timed(step_dev)
-    q_dev = d_out.cpu().numpy()
-
-    # ---- (2) end to end through the public host API: pinned host buffers, H2D + D2H inside the timed region
-    e2e = None
-    if not args.no_e2e:
+    ms_dev, acc, clk = timed(step_dev)
+    res = {"ms_dev": ms_dev, "acc": acc, "clocks": clk, "q32": d_out.cpu().numpy(), "q64": d_out64.cpu().numpy(), "n_atoms": n_atoms,
+           "e2e_ms": None}
+    del d_xyz, d_sp, d_Q, d_out, d_out64
+    if host_too:
         h_xyz = eng.pinned_empty(xyz.shape, np.float32); h_xyz[...] = xyz
         h_sp = eng.pinned_empty(sp.shape, np.int32); h_sp[...] = sp
         h_Q = eng.pinned_empty(Q.shape, np.float32); h_Q[...] = Q
@@ -397,28 +427,151 @@ def run_b200(args):
             eng.infer_batch(offs, h_xyz, h_sp, h_Q, npad, out=h_out)
 
         ms_e2e, _, _ = timed(step_host)
-        if not np.array_equal(h_out, q_dev):
+        if not np.array_equal(h_out, res["q32"]):
             raise SystemExit("host-API and device-API results differ")
-        h2d = xyz.nbytes + sp.nbytes + Q.nbytes + offs.nbytes + npad.nbytes
-        e2e = {"value": (1 if sharded_system else world) * n_atoms * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_out.nbytes), "ms_per_step": ms_e2e / args.steps}
+        res["e2e_ms"] = ms_e2e
+        res["h2d"] = int(xyz.nbytes + sp.nbytes + Q.nbytes + offs.nbytes + npad.nbytes)
+        res["d2h"] = int(h_out.nbytes)
+        eng.free_pinned()
+    return res
 
-    # ---- sanity on the result of the timed path (cheap, outside the timed region)
-    sums = np.add.reduceat(q_dev.astype(np.float64), offs[:-1])
-    max_dQ = float(np.abs(sums - Q.astype(np.float64)).max())
+
+def conservation(q64, offs, Q):
+    """max |sum_i q_i - Q| per system from the FP64 charges, next to the floor the reference's own initial state imposes:
+    q0 = fl32(fl32(Q)/n) on every atom (charge_gn.py:337-338) already misses Q by up to n * ulp(Q/n)/2."""
+    n = np.diff(offs).astype(np.float64)
+    sums = np.add.reduceat(q64, offs[:-1])
+    q0 = (Q.astype(np.float32) / n.astype(np.float32)).astype(np.float32).astype(np.float64)
+    return {"max_abs_sum_q_minus_Q": float(np.abs(sums - Q.astype(np.float64)).max()),
+            "q0_floor_max_abs_n_q0_minus_Q": float(np.abs(q0 * n - Q.astype(np.float64)).max()),
+            "from": "FP64 copy of the charges (q_out_f64); the float32 output rounds each charge by up to 6e-8 |q| on top"}
+
+
+def secondary_blocks(box, args, main_res, main_value):
+    """Driver-visible evidence beyond the headline line: strong scaling of both multi-GPU configs,
+    a live-GNN checkpoint on the headline workload, and the reference's own three configurations.  Short runs (3 steps)."""
+    from epnn_b200 import synth
+    out = {}
+    world, rank = box.world, box.rank
+    K, W = 3, 3
+    # ---- strong scaling, many small molecules: --molecules in TOTAL, a contiguous 1/N of the stream per rank, no collective
+    if world > 1:
+        w, eng = make_engine(box, args, "decay_model_weights")
+        per = args.molecules // world
+        offs, xyz, sp, Q = synth.qm9_shaped(per, w.n_x, seed=args.seed, first=rank * per)      # another slice of the stream: not cached
+        r = time_case(box, eng, offs, np.ascontiguousarray(xyz, np.float32), sp, Q, np.full(per, args.npad, np.int32), K, W, host_too=False)
+        tot = box.sum_over_ranks([r["n_atoms"]])[0]
+        out["strong_qm9"] = {"workload": f"{per * world} QM9-shaped molecules in total, {per} per GPU, no collective", "scaling": "strong",
+                             "value": tot * K / (r["ms_dev"] * 1e-3), "unit": UNIT, "ms_per_step": r["ms_dev"] / K, "steps": K, "warmup": W,
+                             "limiter": "per-chunk fixed cost (one host sync after the neighbour count, ~60 launches) over 1/N of the atoms"}
+        eng.close()
+    else:
+        out["strong_qm9"] = {"workload": f"{args.molecules} QM9-shaped molecules in total on 1 GPU (= the headline line)", "scaling": "strong",
+                             "value": main_value, "unit": UNIT, "ms_per_step": main_res["ms_dev"] / args.steps, "steps": args.steps, "warmup": args.warmup}
+    # ---- strong scaling, one large system sharded over the ranks (BASELINE config 5 at a size that steps in about a second)
+    w, eng = make_engine(box, args, "decay_model_weights")
+    offs, xyz, sp, Q = synth.protein_like(args.strong_atoms, w.n_x, seed=1)
+    xyz = np.ascontiguousarray(xyz, np.float32)
+    npad = np.array([args.strong_atoms], np.int32)
+    ident = None
+    if world > 1:
+        single = None
+        if rank == 0:                                        # rank 0's single-GPU result: the sharded run must reproduce it bit for bit
+            single = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
+        eng.set_shard(rank, world)
+    r = time_case(box, eng, offs, xyz, sp, Q, npad, K, 1, host_too=False)
+    if world > 1 and rank == 0:
+        ident = bool(np.array_equal(single, r["q64"]))
+    ph = {k: r["acc"][k] / K for k in r["acc"] if k.startswith("ms_")}
+    out["strong_protein"] = {"workload": f"protein-like single system, {args.strong_atoms} atoms, exact all-pairs GNN, sharded over {world} GPU(s)",
+                             "scaling": "strong", "value": args.strong_atoms * K / (r["ms_dev"] * 1e-3), "unit": UNIT,
+                             "ms_per_step": r["ms_dev"] / K, "steps": K, "warmup": 1, "phases_ms_per_step": ph,
+                             "bit_identical_to_single_gpu": ident, "exchange": getattr(eng, "shard_state", None) and
+                             {k: v for k, v in eng.shard_state.items() if k in ("calls", "bytes")},
+                             "checks": conservation(r["q64"], offs, Q)}
+    eng.set_shard(0, 1)
+    eng.close()
+    # ---- the headline workload with a checkpoint whose GNN is live at every step but the first (the default checkpoint's update
+    #      MLP is dead at 3 of 5 steps, which the exact far-column de-duplication exploits)
+    for ck in ("model2_weights", "model_weights"):
+        w, eng = make_engine(box, args, ck, precision=32)
+        n_mol = args.molecules
+        offs, xyz, sp, Q = qm9_stream(n_mol, w.n_x, args.seed, rank * n_mol)
+        r = time_case(box, eng, offs, np.ascontiguousarray(xyz, np.float32), sp, Q, np.full(n_mol, args.npad, np.int32), K, W, host_too=False)
+        tot = box.sum_over_ranks([r["n_atoms"]])[0]
+        out["live_gnn_" + ck] = {"workload": f"{n_mol} QM9-shaped molecules per GPU, {ck} (T={w.T}), FP32 kernels", "scaling": "weak",
+                                 "value": tot * K / (r["ms_dev"] * 1e-3), "unit": UNIT, "ms_per_step": r["ms_dev"] / K, "steps": K, "warmup": W,
+                                 "fp32_distance_to_oracle": {"model2_weights": "<= 3.9e-6 e", "model_weights": "<= 1.0e-4 e (needs the FP64 kernels for 1e-5)"}[ck] +
+                                                            " on data/mixed (profiles/r02/call15_noise_floor.log)"}
+        eng.close()
+    # ---- the reference's own configurations (BASELINE.json configs[0..2]), rank 0 only: replicas, no sharding
+    if rank == 0:
+        for wl, ck in (("qm9_test", "model_weights"), ("ssi", "model2_weights")):
+            w, eng = make_engine(box, args, ck, precision=0)          # auto: the probe picks the precision that holds 1e-5
+            offs, xyz, sp, Q, n_sel = real_set(wl, w.n_x)
+            sub = Box.__new__(Box); sub.__dict__.update(box.__dict__); sub.world = 1
+            r = time_case(sub, eng, offs, xyz, sp, Q, np.full(n_sel, 41, np.int32), 10, W, host_too=True)
+            st = eng.last_stats
+            out["config_" + wl] = {"workload": f"{n_sel} {'QM9 molecules' if wl == 'qm9_test' else 'SSI dimers'} of data/mixed, {ck}, pad N=41",
+                                   "value": r["n_atoms"] * 10 / (r["ms_dev"] * 1e-3), "unit": UNIT, "ms_per_step": r["ms_dev"] / 10,
+                                   "e2e": r["n_atoms"] * 10 / (r["e2e_ms"] * 1e-3), "precision_used": st["precision_used"],
+                                   "probe_max_abs_dq_fp32_vs_fp64_kernels": st["probe_err32"], "probe_max_abs_dq_mixed_vs_fp64_kernels": st["probe_err48"],
+                                   "note": "precision 0 (auto): cheapest kernel precision whose probe charges are within 2.5e-6 e of the FP64 kernels "
+                                           "(which agree with the float64 oracle to 1e-9, tests/test_gpu_parity.py)",
+                                   "checks": conservation(r["q64"], offs, Q)}
+            eng.close()
+        w, eng = make_engine(box, args, "decay_model_weights", precision=32)
+        d = np.load(os.path.join(GOLDEN, "protein.npz"))
+        n = len(d["Z"])
+        offs = np.array([0, n], np.int32)
+        xyz = np.ascontiguousarray(d["xyz"], np.float32)
+        sp = synth.species_from_Z(d["Z"], 9).astype(np.int32)
+        Q = np.array([d["Q"]], np.float32)
+        sub = Box.__new__(Box); sub.__dict__.update(box.__dict__); sub.world = 1
+        r = time_case(sub, eng, offs, xyz, sp, Q, np.array([n], np.int32), 20, 5, host_too=True)
+        out["config_galectin3c"] = {"workload": "Galectin-3C, 2220 atoms, Q=+2, decay_model_weights, pad N=n", "value": n * 20 / (r["ms_dev"] * 1e-3),
+                                    "unit": UNIT, "ms_per_step": r["ms_dev"] / 20, "e2e": n * 20 / (r["e2e_ms"] * 1e-3),
+                                    "max_abs_dq_vs_reference_preds_npy": float(np.abs(r["q32"] - d["preds"].reshape(-1)).max()),
+                                    "checks": conservation(r["q64"], offs, Q)}
+        eng.close()
+    box.barrier()
+    return out
+
+
+def run_b200(args):
+    box = Box(args)
+    torch, dist = box.torch, box.dist
+    rank, world, local, dev = box.rank, box.world, box.local, box.dev
+
+    # CPU baseline first (rank 0, N = 1 only), before this process owns a CUDA context
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_baseline_subprocess(args)
+
+    w, eng = make_engine(box, args, args.checkpoint)
+    offs, xyz, sp, Q, npad, desc = make_workload(args, w, rank)
+    n_atoms = int(offs[-1])
+    sharded_system = args.workload == "protein" and world > 1
+    if sharded_system:                       # one big system: sharded over the ranks
+        eng.set_shard(rank, world)
+    res = time_case(box, eng, offs, xyz, sp, Q, npad, args.steps, args.warmup, host_too=not args.no_e2e, clocks=True)
+    ms_dev, acc, clocks = res["ms_dev"], res["acc"], res["clocks"]
+    e2e = None
+    if res["e2e_ms"] is not None:
+        e2e = {"value": (1 if sharded_system else world) * n_atoms * args.steps / (res["e2e_ms"] * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": res["h2d"], "d2h_bytes_per_step": res["d2h"], "ms_per_step": res["e2e_ms"] / args.steps}
+    checks = conservation(res["q64"], offs, Q)
 
     # ---- totals over ranks
-    tot_atoms = n_atoms
-    launches = int(acc["n_launches"])
-    if world > 1:
-        t = torch.tensor([n_atoms, launches], device=dev, dtype=torch.float64)
-        dist.all_reduce(t)
-        tot_atoms, launches = int(t[0].item()), int(t[1].item())
-        if sharded_system:
-            tot_atoms = n_atoms              # every rank worked on the same atoms (strong scaling)
+    tot_atoms, launches = box.sum_over_ranks([n_atoms, acc["n_launches"]])
+    tot_atoms, launches = int(tot_atoms), int(launches)
+    if sharded_system:
+        tot_atoms = n_atoms              # every rank worked on the same atoms (strong scaling)
+    value = tot_atoms * args.steps / (ms_dev * 1e-3)
 
+    line = None
     if rank == 0:
-        # roofline of the dominant kernel (gnn_pair_kernel): algorithmic FLOPs / CUDA-event time of its launches
+        # roofline of the dominant kernel (message-passing pair MLP): FLOPs / CUDA-event time of its launches
         n_sys_sizes = np.diff(offs).astype(np.float64)
         ordered_pairs = float((n_sys_sizes ** 2).sum() + (n_sys_sizes * (npad > np.diff(offs))).sum())
         nnz = 2.0 * acc["n_pairs_e"] / args.steps
@@ -446,19 +599,28 @@ def run_b200(args):
                     traffic = tj["gnn_pair_dram_bytes_per_atom_per_launch"] * n_atoms / n_chunks
             except Exception:   # noqa: BLE001
                 traffic = None
-        achieved = gnn_flops_step / (ms_gnn * 1e-3) * 1e-12
-        if sharded_system:
-            achieved /= world                # every rank ran 1/world of the launch's work: quote the per-GPU rate
+        algorithmic = gnn_flops_step / (ms_gnn * 1e-3) * 1e-12 / (world if sharded_system else 1)
+        # what the small-system kernel really evaluated (device counters): every slot = one 32x32 second-layer product + glue,
+        # every near slot additionally the rank-16 descriptor product -- the exact de-duplication of species-equivalent far columns
+        # and the rank-16 basis make this smaller than the algorithmic count
+        slots_near = acc.get("n_gnn_near_slots", 0) / args.steps
+        slots_far = acc.get("n_gnn_far_slots", 0) / args.steps
+        executed = None
+        if slots_near + slots_far > 0 and args.workload != "protein":
+            executed = (FLOP_PAIR * (slots_near + slots_far) + 2 * 16 * 32 * slots_near) / (ms_gnn * 1e-3) * 1e-12
+        headline = executed if executed is not None else algorithmic
         roofline = {
-            "kernel": "bundle_kernel<float,8,GNN> / gnn_pair_kernel (message-passing pair MLP, FP32 SIMT, FFMA2)", "bound": "fp32",
-            "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak if fp32_peak else None,
+            "kernel": "bundle_run_kernel (message-passing pair MLP of the small systems, FP32 SIMT, FFMA2 with uniform weight operands)"
+                      if args.workload != "protein" else "gnn_pair_kernel + gnn_far_const_kernel (message-passing pair MLP of large systems, FP32 SIMT)",
+            "bound": "fp32", "achieved": headline, "peak": fp32_peak, "unit": "TFLOP/s", "frac": headline / fp32_peak if fp32_peak else None,
+            "achieved_is": "EXECUTED FLOPs (slots the kernel evaluated, device counters) / CUDA-event time" if executed is not None
+                           else "ALGORITHMIC FLOPs (SURVEY 8d) / CUDA-event time",
+            "algorithmic": {"achieved": algorithmic, "frac": algorithmic / fp32_peak if fp32_peak else None,
+                            "note": "SURVEY 8d count of the reference's unmasked n^2 sum: 2144 FLOP per ordered pair + 3072 per e != 0 pair, per step; "
+                                    "not a utilisation figure -- the exact far-column de-duplication and the rank-16 descriptor basis skip part of it"},
             "peak_source": "FP32 FMA micro-benchmark measured in this run (epnn_measure_fp32_peak); MEASURED_PEAKS.json "
                            "holds no SIMT peak. north_star: pair MLP defaults to FP32 SIMT, tensor pipe unused",
             "traffic": traffic,
-            "note": "achieved = ALGORITHMIC FLOPs (SURVEY 8d: 2144 per ordered pair + 3072 per e != 0 pair, per step) / CUDA-event time. "
-                    "The kernels execute fewer FLOPs than that count: C^T e once per unordered pair and in the rank-16 descriptor "
-                    "basis, and (dedup_far) one far slot per species instead of one per column when the v rows coincide. "
-                    "Hardware utilisation from ncu (profiles/): FMA pipe ~46 % of cycles active, shared-memory wavefronts ~58 % of peak.",
             "launches_per_step": w.T * n_chunks, "avg_launch_ms": ms_gnn / (w.T * n_chunks),
             "algorithmic_flops_per_launch": gnn_flops_step / (w.T * n_chunks),
             "share_of_step": ms_gnn / phases["ms_total"],
@@ -479,51 +641,45 @@ def run_b200(args):
             dd_rows = acc.get("n_far_dedup_rows", 0) / args.steps
             n_slots = len(np.unique(sp)) + (1 if int(npad[0]) > n_atoms else 0)
             far_exec = dd_rows * n_slots + (row_steps - dd_rows) * max(n_atoms - nnz / n_atoms, 0.0)
-            exec_flops = FLOP_PAIR * (w.T * nnz + far_exec) + 2 * (16 if args.precision == 32 else 48) * 32 * w.T * nnz
+            exec_flops = FLOP_PAIR * (w.T * nnz + far_exec) + 2 * (16 if args.precision != 64 else 48) * 32 * w.T * nnz
             executed = exec_flops / (ms_gnn * 1e-3) * 1e-12 / (world if sharded_system else 1)
-            roofline["far_dedup"] = {
-                "row_steps_collapsed": dd_rows, "row_steps": row_steps, "slots_per_collapsed_row": n_slots,
-                "executed": executed, "executed_frac": executed / fp32_peak if fp32_peak else None, "unit": "TFLOP/s",
-                "note": "executed = FLOPs the message kernels really ran (near pairs + species slots + any column-by-column far "
-                        "rows) / CUDA-event time; `achieved` above stays the ALGORITHMIC count of the reference's unmasked n^2 sum, "
-                        "which the exact de-duplication no longer executes term by term -- it can exceed the FP32 peak by orders "
-                        "of magnitude and says nothing about pipe utilisation when row_steps_collapsed > 0"}
+            roofline["far_dedup"] = {"row_steps_collapsed": dd_rows, "row_steps": row_steps, "slots_per_collapsed_row": n_slots}
+            if dd_rows > 0:          # the algorithmic count is meaningless once rows collapse: quote what really ran
+                roofline.update({"achieved": executed, "frac": executed / fp32_peak if fp32_peak else None,
+                                 "achieved_is": "EXECUTED FLOPs (near pairs + species slots + column-by-column far rows) / CUDA-event time"})
         if args.gnn_far_tensor and args.workload == "protein":
             # the O(n^2) far part runs on tcgen05 (3xTF32): executed tensor FLOPs = 3 x (2*32*32) per far ordered pair per step
-            # far pairs that really went through the tensor kernel: the row-steps the de-duplication did not collapse
             far_pair_steps = (row_steps - dd_rows) * max(n_atoms - nnz / n_atoms, 0.0)
             tf32_exec = 3.0 * 2 * 32 * 32 * far_pair_steps / (ms_gnn * 1e-3) * 1e-12 / (world if sharded_system else 1)
             tf32_peak = peaks.get("bf16_tflops", 1590.0) / 2.0
-            fp32_view = {k: roofline[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "peak_source")}
-            fp32_view["note"] = "algorithmic FP32-equivalent rate of the whole message step; can exceed the SIMT peak because the far part ran on the tensor pipe"
-            roofline["fp32_equivalent"] = fp32_view
             roofline["tensor_far"] = {
                 "kernel": "gnn_far_tc_kernel (tcgen05.mma kind::tf32, M128 N32 K8, A in tensor memory, 3xTF32 split)",
                 "bound": "tensor", "achieved": tf32_exec, "peak": tf32_peak, "unit": "TFLOP/s", "frac": tf32_exec / tf32_peak,
                 "peak_source": "half of MEASURED_PEAKS.json bf16_tflops (TF32 dense = half the bf16 rate)" if "bf16_tflops" in peaks
-                               else "half of the fallback 1590 (B200_PROFILING.md)",
-                "note": "achieved counts the three TF32 MMAs of the error-compensated split; the kernel is bound by the SIMT "
-                        "producer/epilogue around the MMAs (ncu: tensor pipe ~19 % active), not by the tensor pipe"}
+                               else "half of the fallback 1590 (B200_PROFILING.md)"}
             if far_pair_steps > 0.5 * row_steps * n_atoms:       # the dominant kernel of this configuration is the tcgen05 one
                 for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "peak_source"):
                     roofline[k] = roofline["tensor_far"][k]
         for k in ("neighbor_build", "charge_reduction"):
             roofline["hbm_side"][k]["frac"] = roofline["hbm_side"][k]["achieved"] / hbm_peak
-        par = (f"one system, large-system pair kernels sharded x{world}, all-reduce of S / delta per step / pass (NCCL)"
-               if sharded_system else f"molecule-shards x{world}, no collective")
+        par = (f"one system sharded x{world}" if sharded_system else f"molecule-shards x{world}, no collective")
         desc.update({"checkpoint": args.checkpoint, "parallelism": par,
                      "l2": "inputs larger than L2 (no flush needed)" if n_atoms * 16 > 126e6 else "inputs smaller than L2",
-                     "atoms_per_gpu_per_step": n_atoms, "T": w.T, "precision": args.precision,
+                     "atoms_per_gpu_per_step": n_atoms, "T": w.T, "precision": args.precision, "precision_used": int(acc["precision_used"] / args.steps),
                      "gnn_far_tensor": args.gnn_far_tensor, "dedup_far": args.dedup_far, "pair_tensor": args.pair_tensor, "pair_const": args.pair_const})
-        line = {"metric": METRIC, "value": tot_atoms * args.steps / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world,
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
                 "scaling": "strong" if sharded_system else "weak", "vs_baseline": None,
-                "dtype": "f32" if args.precision == 32 else "f64", "data": data_kind(args), "config": desc, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
-                "cpu_baseline": cpu_base, "phases_ms_per_step": phases,
-                "checks": {"max_abs_sum_q_minus_Q": max_dQ}}
-        print(json.dumps(line), flush=True)
-    eng.free_pinned()
+                "dtype": "f64" if int(acc["precision_used"] / args.steps) == 64 else "f32", "data": data_kind(args), "config": desc, "clocks": clocks,
+                "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+                "cpu_baseline": cpu_base, "phases_ms_per_step": phases, "checks": checks}
     eng.close()
+    if args.secondary and args.workload == "qm9":
+        sec = secondary_blocks(box, args, res, value)
+        if rank == 0:
+            line["secondary"] = sec
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

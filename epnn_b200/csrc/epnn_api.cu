@@ -303,6 +303,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     w.pair_const = sizeof(R) == 4 ? c->pair_const : 0;
     w.wf_host = c->wf_host.data(); w.wf_dev = c->wf;
     w.work_counter = c->d_flags + 7;
+    w.slot_counter = stats && c->bufs[B_MISC].p ? (unsigned long long*)c->bufs[B_MISC].p + 2 : nullptr;
     { void* pa; int rca = ensure(c, B_ARGS, 1024, &pa); if (rca != EPNN_OK) return rca; w.args_dev = pa; }
     w.xyz = d_xyz; w.species = d_species; w.Qsys = d_Q;
     void* p;
@@ -640,7 +641,7 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
     void* p;
     if ((rc = ensure(c, B_MISC, 64, &p)) != EPNN_OK) return rc;
     d_near_count = (unsigned long long*)p;
-    CU(c, cudaMemsetAsync(d_near_count, 0, 2 * sizeof(unsigned long long), st));      // [0] near pairs, [1] de-duplicated rows
+    CU(c, cudaMemsetAsync(d_near_count, 0, 4 * sizeof(unsigned long long), st));      // [0] near pairs, [1] de-duplicated rows, [2] near / [3] far slots run by the bundle GNN kernel
     tm.mark(0);
     for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
         const int64_t s0 = bounds[ci], s1 = bounds[ci + 1];
@@ -693,10 +694,11 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
     }
     CU(c, cudaStreamSynchronize(st));
     if (stats) {
-        unsigned long long nn[2] = {0, 0};
+        unsigned long long nn[4] = {0, 0, 0, 0};
         CU(c, cudaMemcpy(nn, d_near_count, sizeof(nn), cudaMemcpyDeviceToHost));
         stats->n_pairs_near = (int64_t)nn[0];
         stats->n_far_dedup_rows = (int64_t)nn[1];
+        stats->n_gnn_near_slots = (int64_t)nn[2]; stats->n_gnn_far_slots = (int64_t)nn[3];
         stats->n_systems = n_sys; stats->n_atoms = off[n_sys]; stats->n_chunks = (int64_t)bounds.size() - 1;
         stats->n_launches = n_launch;
         stats->precision_used = c->eff_precision;

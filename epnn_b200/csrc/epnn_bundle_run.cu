@@ -49,6 +49,7 @@ struct RunArgs {
     const int* atom_sys; const int* sys_off; const int* npad;
     const float* u; const float* v;
     const float* Cw; const float* b2; const float* b1;      // device pointers into the packed weights (staged into shared memory)
+    unsigned long long* slot_counter;                       // statistics (may be NULL): [0] near slots, [1] far slots evaluated
     float* S;
 };
 
@@ -201,6 +202,7 @@ __global__ void __launch_bounds__(RUN_NW * 32, RUN_CTAS) bundle_run_kernel(const
             else { s0 = use0 ? a.far0_off[atom0] : a.far_off[atom0]; s1 = use0 ? a.far0_off[atom0 + nat] : a.far_off[atom0 + nat]; }
             const int len = s1 - s0;
             if (len <= 0) continue;
+            if (a.slot_counter && lane == 0) atomicAdd(a.slot_counter + phase, (unsigned long long)len);
             const int J = (len + 31) >> 5;
             const int k0 = s0 + lane * J;
             int cur = -1;
@@ -350,7 +352,7 @@ cudaError_t launch_gnn_bundle_run(const Workspace& w, const StepW<float>& sw, cu
     ra.far0_off = w.far0_off; ra.far0_list = w.far0_list; ra.far0_w = w.far0_w; ra.rep = w.rep; ra.dedup = w.dedup_far;
     ra.atom_sys = w.atom_sys; ra.sys_off = w.sys_off; ra.npad = w.npad;
     ra.u = (const float*)w.u; ra.v = (const float*)w.v; ra.S = (float*)w.S;
-    ra.Cw = sw.Cw; ra.b2 = sw.b2; ra.b1 = sw.b1;
+    ra.Cw = sw.Cw; ra.b2 = sw.b2; ra.b1 = sw.b1; ra.slot_counter = w.slot_counter;
     const size_t smem = RunSmem::bytes();
     e = cudaFuncSetAttribute(bundle_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

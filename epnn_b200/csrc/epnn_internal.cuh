@@ -253,6 +253,7 @@ struct Workspace {
                                                   // 2 (default) row-run GNN bundle kernel + pair-per-thread EPN bundle kernel + row-per-thread far kernel
     void* args_dev;                               // 1 KB device scratch: argument block of the kernels that take theirs through global memory
     const float* wf_host; const float* wf_dev;    // packed FP32 weights: host mirror and device base (pair_const passes weights as kernel parameters)
+    unsigned long long* slot_counter;             // device counters (statistics): [0] near, [1] far slots evaluated by the row-run GNN kernel
     unsigned long long* dedup_rows;               // device counter (statistics): rows whose far part was collapsed, summed over steps
     void* h; void* S; void* u; void* v; void* delta;   // precision-dependent (float or double)
     void* l2;                          // [n][32] last hidden layer of the update MLP: the state carried between steps

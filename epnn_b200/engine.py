@@ -92,6 +92,8 @@ class Engine:
         return a
 
     def free_pinned(self):
+        """Frees every buffer handed out by ``pinned_empty``.  The numpy views of those buffers must not be used afterwards
+        (they are plain views of the page-locked memory, not owners)."""
         for p in getattr(self, "_pinned", []):
             self.lib.epnn_host_free(p)
         self._pinned = []
@@ -108,6 +110,9 @@ class Engine:
         if xyz.size != 3 * n_atoms or species.size != n_atoms or Q.size != n_sys:
             raise ValueError("array sizes are inconsistent with atom_offsets")
         npad_a = None if npad is None else _as(np.broadcast_to(npad, (n_sys,)), np.int32)
+        if out is not None and (not isinstance(out, np.ndarray) or out.dtype != np.float32 or out.size != n_atoms
+                                or not out.flags.c_contiguous or not out.flags.writeable):
+            raise ValueError("out must be a writeable C-contiguous float32 array with one entry per atom")
         q32 = out if out is not None else np.empty(n_atoms, np.float32)
         q64 = np.empty(n_atoms, np.float64) if want_f64 else None
         st = _capi.Stats()

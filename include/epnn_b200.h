@@ -59,6 +59,8 @@ typedef struct epnn_stats {
     float ms_d2h;
     int64_t n_far_dedup_rows; /* rows of systems with more than 48 atoms whose far (e == 0) columns were collapsed to one
                                  weighted slot per species, summed over the T message-passing steps ("dedup_far") */
+    int64_t n_gnn_near_slots; /* ordered near (e != 0) slots and far slots (far columns, or one weighted slot per species where the */
+    int64_t n_gnn_far_slots;  /*   exact de-duplication applied, + pad slots) the small-system GNN kernel evaluated, summed over the T steps */
     int32_t precision_used;   /* 32, 48 (mixed) or 64: what "precision" resolved to for this call */
     float probe_err32;        /* "precision" 0 (auto): max |dq| of the FP32 / mixed kernels against the FP64 kernels on the */
     float probe_err48;        /*   probe sample of the first call (e); -1 if no probe ran */
