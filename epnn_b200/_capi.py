@@ -33,7 +33,6 @@ class Stats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
-ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p)
 
 # name -> (restype, argtypes); mirrors include/epnn_b200.h one to one
 SIGNATURES = {
@@ -53,7 +52,10 @@ SIGNATURES = {
     "epnn_get_hidden": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
     "epnn_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "epnn_host_free": (C.c_int, [C.c_void_p]),
-    "epnn_set_shard": (C.c_int, [C.c_void_p, C.c_int, C.c_int, ALLREDUCE_FN, C.c_void_p]),
+    "epnn_shard_unique_id": (C.c_int, [C.c_void_p]),
+    "epnn_shard_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "epnn_shard_slice": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "epnn_shard_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "epnn_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "epnn_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "epnn_xyz_load": (C.c_int, [C.POINTER(C.c_char_p), C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),

@@ -1,5 +1,6 @@
 // C-ABI of libepnn_b200.so: context, weight upload, workspace management and the launch sequence.
 // See include/epnn_b200.h for the contract of every entry point and the reference code it replaces.
+#include <dlfcn.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -20,6 +21,43 @@ struct DevBuf {
     size_t cap = 0;
 };
 
+// ------------------------------------------------------------------------------------------------
+// NCCL, bound at run time (dlopen of libnccl.so.2: the copy the process already holds -- e.g. torch's -- or the system one).
+// Only four entry points are used; all exchanges are in-place all-gathers of equal slices on the ctx stream.
+typedef struct ncclComm* ncclComm_t;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, /* ncclUniqueId by value: 128 bytes */ struct NcclId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+struct NcclId { char bytes[128]; };
+static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
+static const char* load_nccl() {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.handle) return nullptr;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return "libnccl.so.2 not found (needed for epnn_shard_init with world > 1)";
+    NcclApi a;
+    a.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    a.CommInitRank = (int (*)(ncclComm_t*, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+    a.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclAllGather");
+    a.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+    a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy) { dlclose(h); return "libnccl.so.2 lacks a required symbol"; }
+    a.handle = h;
+    g_nccl = a;
+    return nullptr;
+}
+
+// Equal slices of the atom index space of a batch: rank r owns rows [r * slice, (r + 1) * slice) clipped to n;
+// slice = ceil(n / world) rounded up to 32 rows (all-gathers need equal counts; 32 = the row block of the far kernels).
+static inline int64_t shard_slice_rows(int64_t n, int world) { const int64_t s = (n + world - 1) / world; return (s + 31) / 32 * 32; }
+
 struct epnn_ctx {
     int device = 0, T = 0, n_x = 0, n_species = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -34,9 +72,9 @@ struct epnn_ctx {
     int pair_const = 2;          // option "pair_const": FP32 kernel set (0 warp-tile, 1 pair-per-thread everywhere, 2 default mix; see epnn_internal.cuh)
     std::vector<float> wf_host;  // host mirror of wf (pair_const passes a step's weights as kernel parameters)
     float* w2split = nullptr;    // [T][2][32][32]: hi / lo parts of W2^T of every message MLP (tensor-core far kernel)
-    int shard_rank = 0, shard_world = 1;
-    epnn_allreduce_fn allreduce = nullptr;
-    void* allreduce_user = nullptr;
+    int shard_rank = 0, shard_world = 1;      // large systems of a call are split over shard_world ranks (epnn_shard_init)
+    ncclComm_t comm = nullptr;
+    int64_t xchg_calls = 0, xchg_bytes = 0;   // all-gathers issued / bytes received by this rank since epnn_shard_init
     int64_t chunk_atoms = 4 * 1024 * 1024;
     PackedOffsets po;
     float* wf = nullptr;         // packed weights, float
@@ -56,7 +94,7 @@ static thread_local std::string g_create_err;
 enum {
     B_XYZ, B_SPECIES, B_OFF, B_Q, B_NPAD, B_ATOMSYS, B_DEG, B_DEGU, B_ROWPTR, B_USTART, B_COL, B_PID, B_PI, B_PJ, B_PD,
     B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_FAR0CNT, B_FAR0OFF, B_FAR0LIST, B_FAR0W, B_REP, B_ATOMB0, B_BNAT, B_PERM, B_LARGESYS, B_GRID, B_CELLCNT, B_CELLSTART, B_CELLATOMS, B_DTMP, B_H, B_L2, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
-    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_ROWBLK, B_ROWL, B_ARGS, B_COUNT
+    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_ROWBLK, B_ROWL, B_ARGS, B_DEGALL, B_ACTIVE, B_COUNT
 };
 
 static int fail(epnn_ctx* c, int code, const char* fmt, ...) {
@@ -183,6 +221,7 @@ extern "C" void epnn_destroy(epnn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
     for (DevBuf& b : c->bufs) if (b.p) cudaFree(b.p);
     if (c->wf) cudaFree(c->wf);
     if (c->wd) cudaFree(c->wd);
@@ -263,6 +302,17 @@ __global__ void collect_totals_kernel(const int* rowptr, const int* ustart, cons
     flags[1] = rowptr[n_atoms]; flags[2] = ustart[n_atoms]; flags[3] = far_off[n_atoms]; flags[4] = rgl_off[n_sys];
 }
 
+// Sharded calls: active[i] = 1 for the rows of this rank's slice (PASS 0) and for every column of one of those rows (PASS 1).
+template <int PASS>
+__global__ void active_mark_kernel(int n_atoms, int row_lo, int row_hi, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                   unsigned char* __restrict__ active) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_atoms) return;
+    const bool mine = i >= row_lo && i < row_hi;
+    if (PASS == 0) { active[i] = mine ? 1 : 0; return; }
+    if (mine) for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) active[col[k]] = 1;
+}
+
 struct Timer {
     bool on; cudaStream_t st; std::vector<cudaEvent_t> ev; std::vector<int> tag;
     void mark(int t) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); tag.push_back(t); }
@@ -296,13 +346,30 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     Workspace w;
     memset(&w, 0, sizeof(w));
     w.n_atoms = n_atoms; w.n_sys = n_sys; w.sm_count = c->sm_count;
-    w.shard_rank = c->shard_rank; w.shard_world = c->shard_world;
+    // ---- sharded call (epnn_shard_init, world > 1): the rows of the chunk's LARGE systems are split into equal slices of the
+    // atom index space, one per rank; small systems are replicated.  Decided on the host: the offsets are host data.
+    bool has_large = false;
+    for (int s = 0; s < n_sys && !has_large; ++s) has_large = h_off[s + 1] - h_off[s] > SMALL_MAX;
+    const bool sharded = c->shard_world > 1 && c->comm && has_large && !neighbors_only;
+    const int64_t slice = sharded ? shard_slice_rows(n_atoms, c->shard_world) : n_atoms;
+    const int64_t rows_pad = sharded ? slice * c->shard_world : n_atoms;       // exchanged arrays hold world equal slices
+    w.shard_rank = sharded ? c->shard_rank : 0; w.shard_world = sharded ? c->shard_world : 1;
+    w.row_lo = (int)(slice * w.shard_rank < n_atoms ? slice * w.shard_rank : n_atoms);
+    w.row_hi = (int)(slice * (w.shard_rank + 1) < n_atoms ? slice * (w.shard_rank + 1) : n_atoms);
+    // in-place all-gather of an array of rows_pad rows: every rank contributes its slice (NCCL on the ctx stream)
+    auto gather_rows = [&](void* buf, size_t row_bytes) -> int {
+        const int rcn = g_nccl.AllGather((char*)buf + (size_t)slice * w.shard_rank * row_bytes, buf, (size_t)slice * row_bytes, /* ncclInt8 */ 0, c->comm, st);
+        if (rcn != 0) return fail(c, EPNN_E_CUDA, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rcn) : "?");
+        ++c->xchg_calls; c->xchg_bytes += (int64_t)slice * (w.shard_world - 1) * (int64_t)row_bytes;
+        return EPNN_OK;
+    };
     w.ek = EKof<R>::v;
     w.n_species = c->n_species;
     w.pair_tensor = c->pair_tensor && sizeof(R) == 4;
     w.pair_const = sizeof(R) == 4 ? c->pair_const : 0;
     w.wf_host = c->wf_host.data(); w.wf_dev = c->wf;
     w.work_counter = c->d_flags + 7;
+    w.near_counter = stats && !neighbors_only && c->bufs[B_MISC].p ? (unsigned long long*)c->bufs[B_MISC].p : nullptr;
     w.slot_counter = stats && c->bufs[B_MISC].p ? (unsigned long long*)c->bufs[B_MISC].p + 2 : nullptr;
     { void* pa; int rca = ensure(c, B_ARGS, 1024, &pa); if (rca != EPNN_OK) return rca; w.args_dev = pa; }
     w.xyz = d_xyz; w.species = d_species; w.Qsys = d_Q;
@@ -330,7 +397,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     w.dedup_far = c->dedup_far;
     ENS(B_ATOMB0, sizeof(int) * ((size_t)n_atoms + 1), atom_b0, int*);
     ENS(B_BNAT, sizeof(int) * ((size_t)n_atoms + 1), w.bundle_nat, int*);
-    ENS(B_QD, sizeof(double) * (size_t)n_atoms, w.q, double*);
+    ENS(B_QD, sizeof(double) * (size_t)rows_pad, w.q, double*);
     w.sys_off = off_local; w.npad = npad_local;
 
     // ---- bundles: greedy runs of consecutive small systems with <= BUNDLE_ATOMS atoms (host: the offsets are host data)
@@ -409,6 +476,17 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     if (w.nnz < 0 || w.P < 0 || w.n_far < 0) return fail(c, EPNN_E_UNSUPPORTED, "pair lists of one chunk exceed 2^31 entries; lower chunk_atoms");
     w.nsplit = 1;
     w.far_tc = 0;
+    w.rg_begin = 0; w.rg_end = w.n_rg_large;
+    if (sharded) {                                   // 4-row groups (numbered over the large systems in order) that overlap [row_lo, row_hi)
+        int g = 0, gb = -1, ge = 0;
+        for (int s = 0; s < n_sys; ++s) {
+            const int a0 = h_off[s] - base, ns_ = h_off[s + 1] - h_off[s];
+            if (ns_ <= SMALL_MAX) continue;
+            for (int i = 0; i < ns_; i += 4, ++g)
+                if (a0 + i + 3 >= w.row_lo && a0 + i < w.row_hi) { if (gb < 0) gb = g; ge = g + 1; }
+        }
+        w.rg_begin = gb < 0 ? 0 : gb; w.rg_end = gb < 0 ? 0 : ge;
+    }
     if (w.n_rg_large > 0) {
         if (c->far_tensor && sizeof(R) == 4) {       // tensor-core far kernel: CTA units = row group x column range
             int ns = div_up((int64_t)c->sm_count * 8, w.n_rg_large);
@@ -422,6 +500,13 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
                 if (ns_ > SMALL_MAX) for (int i = 0; i < ns_; i += 32) hb.push_back(make_int2(a0 + i, s));
             }
             w.n_rowblk = (int)hb.size();
+            w.blk_begin = 0; w.blk_end = w.n_rowblk;
+            if (sharded) {
+                int bb = -1, be = 0;
+                for (int k = 0; k < w.n_rowblk; ++k)
+                    if (hb[k].x + 31 >= w.row_lo && hb[k].x < w.row_hi) { if (bb < 0) bb = k; be = k + 1; }
+                w.blk_begin = bb < 0 ? 0 : bb; w.blk_end = bb < 0 ? 0 : be;
+            }
             int2* d_blk;
             ENS(B_ROWBLK, sizeof(int2) * (hb.size() + 1), d_blk, int2*);
             CU(c, cudaMemcpyAsync(d_blk, hb.data(), sizeof(int2) * hb.size(), cudaMemcpyHostToDevice, st));
@@ -458,6 +543,13 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
         w.n_sp_tab = w.n_rg_large / 8 + 2;
         ENS(B_SPTAB, sizeof(int) * 32 * (size_t)w.n_sp_tab, w.sp_tab, int*);
         ENS(B_SPSTAMP, sizeof(int) * 2 * (size_t)w.n_sp_tab, w.sp_stamp, int*);
+        if (sharded) {      // the tables' "a row has more than 255 neighbours" flag must come out the same on every rank: full degrees
+            int* dall;
+            ENS(B_DEGALL, sizeof(int) * (size_t)rows_pad, dall, int*);
+            CU(c, cudaMemcpyAsync(dall, w.deg, sizeof(int) * (size_t)n_atoms, cudaMemcpyDeviceToDevice, st));
+            if ((rc = gather_rows(dall, sizeof(int))) != EPNN_OK) return rc;
+            w.deg_all = dall;
+        }
         CU(c, launch_sp_tab_build(w, st, n_launch));
         w.dedup_rows = stats ? (unsigned long long*)c->bufs[B_MISC].p + 1 : nullptr;
     }
@@ -478,11 +570,11 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     if (neighbors_only) return EPNN_OK;
 
     const size_t state_sz = mixed ? sizeof(double) : sizeof(R);
-    ENS(B_H, state_sz * HD * (size_t)n_atoms, w.h, void*);
-    ENS(B_L2, state_sz * HID * (size_t)n_atoms, w.l2, void*);
+    ENS(B_H, state_sz * HD * (size_t)rows_pad, w.h, void*);
+    ENS(B_L2, state_sz * HID * (size_t)rows_pad, w.l2, void*);
     ENS(B_S, sizeof(R) * HID * (size_t)n_atoms * w.nsplit, w.S, void*);
     ENS(B_U, sizeof(R) * HID * (size_t)n_atoms, w.u, void*);
-    ENS(B_V, sizeof(R) * HID * (size_t)n_atoms, w.v, void*);
+    ENS(B_V, sizeof(R) * HID * (size_t)rows_pad, w.v, void*);
     ENS(B_DELTA, sizeof(R) * (size_t)(w.P + 1), w.delta, void*);
 #undef ENS
     CU(c, cudaMemsetAsync(w.h, 0, state_sz * HD * (size_t)n_atoms, st));
@@ -495,21 +587,36 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     std::vector<StepW<double>> msgd(mixed ? c->T : 0), pasd(mixed ? c->T : 0);
     for (int t = 0; t < (int)msgd.size(); ++t) { msgd[t] = step_view<double>(c->wd, c->po.msg[t]); pasd[t] = step_view<double>(c->wd, c->po.pas[t]); }
     // per-atom kernel in the precision of the call; prev / next index the message (0 .. T-1) and pass (T .. 2T-1) MLPs, -1 = none
-    auto atom = [&](int mode, int prev, int next, int h_is_zero, float* o32, double* o64) -> cudaError_t {
+    auto atom = [&](int mode, int prev, int next, int h_is_zero, float* o32, double* o64, int scope) -> cudaError_t {
         auto pick = [&](auto& ms, auto& ps, int i) { return i < 0 ? nullptr : (i < c->T ? &ms[i] : &ps[i - c->T]); };
-        if (mixed) return launch_atom_mixed(w, mode, pick(msgd, pasd, prev), &updd, pick(msgd, pasd, next), h_is_zero, o32, o64, st, n_launch);
-        return launch_atom<R>(w, mode, pick(msg, pas, prev), &upd, pick(msg, pas, next), h_is_zero, o32, o64, st, n_launch);
+        if (mixed) return launch_atom_mixed(w, mode, pick(msgd, pasd, prev), &updd, pick(msgd, pasd, next), h_is_zero, o32, o64, st, n_launch, scope);
+        return launch_atom<R>(w, mode, pick(msg, pas, prev), &upd, pick(msg, pas, next), h_is_zero, o32, o64, st, n_launch, scope);
     };
 
-    // Sharding only concerns the large-system pair kernels; a chunk without large systems runs replicated.
-    const bool sharded = c->shard_world > 1 && w.n_rg_large > 0;
-    if (!sharded) { w.shard_rank = 0; w.shard_world = 1; }
+    // Sharded call: rows of large systems outside [row_lo, row_hi) belong to other ranks.  Per-atom work runs on the owned rows
+    // (scope 1); the electron-passing projections also on the near neighbours of owned rows ("active", scope 2), because the
+    // pair kernel needs u / v of both members of a cut pair.  Exchanges (in-place all-gathers of equal slices, NCCL on the ctx
+    // stream): v after every message-passing step but the last (128 B/atom; the all-pairs sum reads every column), the update
+    // MLP's last hidden layer once after the last step (128 B/atom), the charges after every pass (8 B/atom).  Cut pairs are
+    // evaluated on both owners in the same canonical orientation, so no transfer is exchanged, and every row is computed by
+    // exactly the arithmetic of the single-GPU run: results are bit-identical.
+    const int own = sharded ? 1 : 0, act = sharded ? 2 : 0;
+    if (sharded) {
+        unsigned char* am;
+        if ((rc = ensure(c, B_ACTIVE, (size_t)n_atoms + 16, &p)) != EPNN_OK) return rc;
+        am = (unsigned char*)p;
+        active_mark_kernel<0><<<div_up(n_atoms, 256), 256, 0, st>>>(n_atoms, w.row_lo, w.row_hi, w.rowptr, w.col, am);
+        active_mark_kernel<1><<<div_up(n_atoms, 256), 256, 0, st>>>(n_atoms, w.row_lo, w.row_hi, w.rowptr, w.col, am);
+        *n_launch += 2;
+        CU(c, cudaGetLastError());
+        w.active = am;
+    }
+    const size_t state_row = (mixed ? sizeof(double) : sizeof(R)) * HID;
     // ---- GNN layer: T message-passing steps (charge_gn.py:60-74)
-    CU(c, atom(ATOM_PROJECT, -1, 0, 1, nullptr, nullptr));
+    CU(c, atom(ATOM_PROJECT, -1, 0, 1, nullptr, nullptr, 0));        // h = 0: u, v follow from species and q alone -- every rank, every atom
     tm.mark(4);
     for (int t = 0; t < c->T; ++t) {
-        if (sharded) CU(c, cudaMemsetAsync(w.S, 0, sizeof(R) * HID * (size_t)n_atoms * w.nsplit, st));
-        if (!sharded || c->shard_rank == 0) CU(c, launch_gnn_bundle<R>(w, msg[t], st, n_launch));
+        CU(c, launch_gnn_bundle<R>(w, msg[t], st, n_launch));
         w.stamp = w.sp_tab ? t + 1 : 0;             // large systems: are this step's v rows equal species by species?
         CU(c, launch_sp_check<R>(w, st, n_launch));
         if (w.far_tc == 1)
@@ -519,36 +626,41 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
             if (w.far_tc == 2) CU(c, launch_gnn_far_const(w, msg[t], w.nsplit - 1, st, n_launch));
         }
         CU(c, launch_gnn_pair<R>(w, msg[t], st, n_launch));
-        if (sharded && c->allreduce(c->allreduce_user, w.S, (size_t)HID * n_atoms * w.nsplit, sizeof(R) == 8, (void*)st) != 0)
-            return fail(c, EPNN_E_CUDA, "allreduce callback failed (GNN step %d)", t);
         tm.mark(3);
-        CU(c, atom(ATOM_UPDATE | ATOM_PROJECT | (t == 0 ? ATOM_FIRST : 0) | (t + 1 == c->T ? ATOM_WRITE_H : 0), t, t + 1, 0, nullptr, nullptr));
-        tm.mark(t + 1 < c->T ? 4 : 6);
+        const bool last = t + 1 == c->T;
+        if (!sharded) {
+            CU(c, atom(ATOM_UPDATE | ATOM_PROJECT | (t == 0 ? ATOM_FIRST : 0) | (last ? ATOM_WRITE_H : 0), t, t + 1, 0, nullptr, nullptr, 0));
+        } else if (!last) {
+            CU(c, atom(ATOM_UPDATE | ATOM_PROJECT | (t == 0 ? ATOM_FIRST : 0), t, t + 1, 0, nullptr, nullptr, own));
+            if ((rc = gather_rows(w.v, sizeof(R) * HID)) != EPNN_OK) return rc;
+        } else {
+            CU(c, atom(ATOM_UPDATE | ATOM_WRITE_H | (t == 0 ? ATOM_FIRST : 0), t, -1, 0, nullptr, nullptr, own));
+            if ((rc = gather_rows(w.l2, state_row)) != EPNN_OK) return rc;
+            if (c->keep_hidden && (rc = gather_rows(w.h, state_row / HID * HD)) != EPNN_OK) return rc;
+            CU(c, atom(ATOM_PROJECT, -1, c->T, 0, nullptr, nullptr, act));
+        }
+        tm.mark(!last ? 4 : 6);
     }
     // ---- EPN layer: T electron-passing passes (charge_gn.py:98-118)
     for (int t = 0; t < c->T; ++t) {
-        if (sharded) CU(c, cudaMemsetAsync(w.delta, 0, sizeof(R) * (size_t)(w.P + 1), st));
-        if (!sharded || c->shard_rank == 0) CU(c, launch_epn_bundle<R>(w, pas[t], st, n_launch));
+        CU(c, launch_epn_bundle<R>(w, pas[t], st, n_launch));
         CU(c, launch_epn_pair<R>(w, pas[t], st, n_launch));
-        if (sharded && w.P > 0 && c->allreduce(c->allreduce_user, w.delta, (size_t)w.P, sizeof(R) == 8, (void*)st) != 0)
-            return fail(c, EPNN_E_CUDA, "allreduce callback failed (EPN pass %d)", t);
         tm.mark(5);
-        if (t + 1 < c->T)
-            CU(c, atom(ATOM_QUPDATE | ATOM_PROJECT, -1, c->T + t + 1, 0, nullptr, nullptr));
-        else
-            CU(c, atom(ATOM_QUPDATE | ATOM_OUTPUT, -1, -1, 0, d_out32, d_out64));
+        const bool last = t + 1 == c->T;
+        if (!sharded) {
+            if (!last) CU(c, atom(ATOM_QUPDATE | ATOM_PROJECT, -1, c->T + t + 1, 0, nullptr, nullptr, 0));
+            else CU(c, atom(ATOM_QUPDATE | ATOM_OUTPUT, -1, -1, 0, d_out32, d_out64, 0));
+        } else {
+            CU(c, atom(ATOM_QUPDATE, -1, -1, 0, nullptr, nullptr, own));
+            if ((rc = gather_rows(w.q, sizeof(double))) != EPNN_OK) return rc;
+            if (!last) CU(c, atom(ATOM_PROJECT, -1, c->T + t + 1, 0, nullptr, nullptr, act));
+            else CU(c, atom(ATOM_OUTPUT, -1, -1, 0, d_out32, d_out64, 0));
+        }
         tm.mark(6);
     }
     c->hidden_atoms = n_atoms;
     c->hidden_precision = (sizeof(R) == 4 && !mixed) ? 32 : 64;
     return EPNN_OK;
-}
-
-__global__ void count_near_kernel(int64_t P, const unsigned char* __restrict__ near, unsigned long long* out) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = p < P ? near[p] : 0;
-    const unsigned b = __ballot_sync(0xffffffffu, v);
-    if ((threadIdx.x & 31) == 0 && b) atomicAdd(out, (unsigned long long)__popc(b));
 }
 
 // Splits [0, n_sys) into chunks of at most chunk_atoms atoms (a single larger system gets its own chunk).
@@ -680,10 +792,6 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
         else
             rc = run_chunk<float>(c, ns, na, off + s0, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
         if (rc != EPNN_OK) return rc;
-        if (stats && w.P > 0) {
-            count_near_kernel<<<div_up(w.P, 256), 256, 0, st>>>(w.P, w.near, d_near_count);
-            ++n_launch;
-        }
         if (host_io) {
             if (q_out) CU(c, cudaMemcpyAsync(q_out + a0, d_o32, sizeof(float) * (size_t)na, cudaMemcpyDeviceToHost, st));
             if (q_out64) CU(c, cudaMemcpyAsync(q_out64 + a0, d_o64, sizeof(double) * (size_t)na, cudaMemcpyDeviceToHost, st));
@@ -870,11 +978,47 @@ extern "C" int epnn_infer_dense(epnn_ctx* c, int32_t B, int32_t N, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------
-extern "C" int epnn_set_shard(epnn_ctx* c, int rank, int world, epnn_allreduce_fn fn, void* user) {
+extern "C" int epnn_shard_unique_id(void* id128) {
+    if (!id128) return EPNN_E_INVALID;
+    if (const char* e = load_nccl()) return fail(nullptr, EPNN_E_UNSUPPORTED, "%s", e);
+    const int rc = g_nccl.GetUniqueId(id128);
+    return rc == 0 ? EPNN_OK : fail(nullptr, EPNN_E_CUDA, "ncclGetUniqueId failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+}
+
+
+extern "C" int epnn_shard_slice(int64_t n_atoms, int rank, int world, int64_t* begin, int64_t* end) {
+    if (n_atoms < 0 || world < 1 || rank < 0 || rank >= world || !begin || !end) return EPNN_E_INVALID;
+    const int64_t s = shard_slice_rows(n_atoms, world);
+    *begin = s * rank < n_atoms ? s * rank : n_atoms;
+    *end = s * (rank + 1) < n_atoms ? s * (rank + 1) : n_atoms;
+    return EPNN_OK;
+}
+
+extern "C" int epnn_shard_init(epnn_ctx* c, int rank, int world, const void* id128) {
     if (!c) return EPNN_E_INVALID;
-    if (world < 1 || rank < 0 || rank >= world) return fail(c, EPNN_E_INVALID, "epnn_set_shard: rank %d not in [0,%d)", rank, world);
-    if (world > 1 && !fn) return fail(c, EPNN_E_INVALID, "epnn_set_shard: an allreduce callback is required for world > 1");
-    c->shard_rank = rank; c->shard_world = world; c->allreduce = fn; c->allreduce_user = user;
+    if (world < 1 || rank < 0 || rank >= world) return fail(c, EPNN_E_INVALID, "epnn_shard_init: rank %d not in [0,%d)", rank, world);
+    CU(c, cudaSetDevice(c->device));
+    if (c->comm) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        g_nccl.CommDestroy(c->comm);
+        c->comm = nullptr;
+    }
+    c->shard_rank = 0; c->shard_world = 1; c->xchg_calls = 0; c->xchg_bytes = 0;
+    if (world == 1) return EPNN_OK;
+    if (!id128) return fail(c, EPNN_E_INVALID, "epnn_shard_init: the NCCL unique id (epnn_shard_unique_id on rank 0, shared with every rank) is required for world > 1");
+    if (const char* e = load_nccl()) return fail(c, EPNN_E_UNSUPPORTED, "%s", e);
+    NcclId id;
+    memcpy(id.bytes, id128, sizeof(id.bytes));
+    const int rc = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (rc != 0) { c->comm = nullptr; return fail(c, EPNN_E_CUDA, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); }
+    c->shard_rank = rank; c->shard_world = world;
+    return EPNN_OK;
+}
+
+extern "C" int epnn_shard_stats(epnn_ctx* c, int64_t* calls, int64_t* bytes) {
+    if (!c) return EPNN_E_INVALID;
+    if (calls) *calls = c->xchg_calls;
+    if (bytes) *bytes = c->xchg_bytes;
     return EPNN_OK;
 }
 

@@ -30,6 +30,8 @@ template <typename R, typename IO> struct AtomArgs {
     const int* rowptr; const int* col; const int* pid; const IO* delta; double* q;
     const R* Pf; const R* Aq64; const R* Ax; IO* u; IO* v;
     float* q_out; double* q_out64;
+    // sharded call: which atoms of LARGE systems this launch touches (small systems are replicated on every rank)
+    int scope, row_lo, row_hi; const unsigned char* active;     // scope 0 all, 1 owned rows [row_lo, row_hi), 2 active[] (owned + halo)
 };
 template <typename R, typename IO> __device__ __forceinline__ Vec4<R> ld_io(const IO* p) {
     const Vec4<IO> t = ldv(p);
@@ -119,11 +121,16 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
 #endif
         // ---------------- per-slot scalars (lane = slot)
         {
-            int sp = 0, ns = 1; R npf = R(0);
+            int sp = 0, ns = 0; R npf = R(0);            // ns = 0 marks a slot this launch does not touch
             double qv = 0.0;
+            bool in = me_ok;
+            int sys = 0, nat = 0;
             if (me_ok) {
-                const int sys = a.atom_sys[me];
-                const int nat = a.sys_off[sys + 1] - a.sys_off[sys];
+                sys = a.atom_sys[me];
+                nat = a.sys_off[sys + 1] - a.sys_off[sys];
+                if (a.scope && nat > SMALL_MAX) in = a.scope == 1 ? (me >= a.row_lo && me < a.row_hi) : a.active[me] != 0;
+            }
+            if (in) {
                 sp = a.species[me];
                 ns = nat > SMALL_MAX ? a.nsplit : 1;
                 npf = (R)a.npad[sys];
@@ -145,6 +152,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
         }
         __syncwarp();
         if (!do_upd && !do_proj) continue;
+        if (a.scope && !__any_sync(0xffffffffu, slot_ns[lane] > 0)) continue;      // nothing of this tile belongs to the launch
 
         if (do_upd) {
             // (1) [l2_prev | S] tile: l2 of the previous step (zeros at the first step: h = 0), S = partial planes summed in fixed order
@@ -153,9 +161,9 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
                 const int sl = f >> 3, ch = f & 7;
                 const int at = base + sl;
                 Vec4<R> lv = vzero<R>(), sv = vzero<R>();
-                if (at < a.n_atoms) {
+                const int ns = slot_ns[sl];
+                if (ns > 0) {
                     if (!first) lv = ldv(a.l2 + (int64_t)at * HID + ch * 4);
-                    const int ns = slot_ns[sl];
                     for (int sp = 0; sp < ns; ++sp)
                         sv = vadd(sv, ld_io<R, IO>(a.Spart + ((int64_t)sp * a.n_atoms + at) * HID + ch * 4));
                 }
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
                 for (int s = 0; s < 8; ++s) {
                     Vec4<R> z; z.x = relu(acc[s][0] + cv.x); z.y = relu(acc[s][1] + cv.y); z.z = relu(acc[s][2] + cv.z); z.w = relu(acc[s][3] + cv.w);
                     const int at = base + pg * 8 + s;
-                    if (at < a.n_atoms) stv(a.l2 + (int64_t)at * HID + og * 4, z);
+                    if (slot_ns[pg * 8 + s] > 0) stv(a.l2 + (int64_t)at * HID + og * 4, z);
                     stv(T32b + tile_off(pg * 8 + s, og, HID), z);
                 }
             }
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
                     for (int s = 0; s < 8; ++s) {
                         Vec4<R> hv; hv.x = acc[s][0] + cv.x; hv.y = acc[s][1] + cv.y; hv.z = acc[s][2] + cv.z; hv.w = acc[s][3] + cv.w;
                         const int at = base + pg * 8 + s;
-                        if (at < a.n_atoms) stv(a.h + (int64_t)at * HD + og * 4, hv);
+                        if (slot_ns[pg * 8 + s] > 0) stv(a.h + (int64_t)at * HD + og * 4, hv);
                     }
                 }
                 zero_acc(acc);
@@ -214,7 +222,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
                     for (int s = 0; s < 8; ++s) {
                         Vec4<R> hv; hv.x = acc[s][0] + cv.x; hv.y = acc[s][1] + cv.y; hv.z = acc[s][2] + cv.z; hv.w = acc[s][3] + cv.w;
                         const int at = base + pg * 8 + s;
-                        if (at < a.n_atoms) stv(a.h + (int64_t)at * HD + HID + og * 4, hv);
+                        if (slot_ns[pg * 8 + s] > 0) stv(a.h + (int64_t)at * HD + HID + og * 4, hv);
                     }
                 }
             }
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
                 const int sl = f >> 3, ch = f & 7;
                 const int at = base + sl;
                 Vec4<R> lv = vzero<R>();
-                if (at < a.n_atoms) lv = ldv(a.l2 + (int64_t)at * HID + ch * 4);
+                if (slot_ns[sl] > 0) lv = ldv(a.l2 + (int64_t)at * HID + ch * 4);
                 stv(T32b + tile_off(sl, ch, HID), lv);
             }
             __syncwarp();
@@ -240,7 +248,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     const int at = base + pg * 8 + s;
-                    if (at < a.n_atoms) {
+                    if (slot_ns[pg * 8 + s] > 0) {
                         const Vec4<R> ax = ldv(sAx + slot_sp[pg * 8 + s] * 64 + half * HID + og * 4);
                         const R qv = slot_q[pg * 8 + s];
                         Vec4<R> o;
@@ -258,10 +266,10 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
 #ifndef EPNN_CPU_EMU
 template <typename R, typename IO>
 cudaError_t launch_atom_io(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd, const StepW<R>* next,
-                           int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl) {
+                           int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl, int scope) {
     if (w.n_atoms == 0) return cudaSuccess;
     if constexpr (sizeof(R) == 4) {
-        if (w.pair_const == 1) return launch_atom_const(w, mode, prev, upd, next, h_is_zero, q_out, q_out64, st, nl);   // experimental (epnn_atom_const.cu)
+        if (w.pair_const == 1 && scope == 0) return launch_atom_const(w, mode, prev, upd, next, h_is_zero, q_out, q_out64, st, nl);   // experimental (epnn_atom_const.cu)
     }
     constexpr int NW = sizeof(R) == 4 ? ATOM_NW : 4;
     AtomArgs<R, IO> aa;
@@ -273,6 +281,7 @@ cudaError_t launch_atom_io(const Workspace& w, int mode, const StepW<R>* prev, c
     aa.rowptr = w.rowptr; aa.col = w.col; aa.pid = w.pid; aa.delta = (const IO*)w.delta; aa.q = w.q;
     if (mode & ATOM_PROJECT) { aa.Pf = next->Pf; aa.Aq64 = next->Aq64; aa.Ax = h_is_zero ? next->Ax64 : next->Axf; }
     aa.u = (IO*)w.u; aa.v = (IO*)w.v; aa.q_out = q_out; aa.q_out64 = q_out64;
+    aa.scope = scope; aa.row_lo = w.row_lo; aa.row_hi = w.row_hi; aa.active = w.active;
     const size_t smem = sizeof(R) * (ATOM_W_UPD + ATOM_W_PROJ + (size_t)NW * ATOM_TILE + NW * 64) + sizeof(int) * NW * 64;
     cudaError_t e = cudaFuncSetAttribute(atom_kernel<R, NW, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -285,17 +294,17 @@ cudaError_t launch_atom_io(const Workspace& w, int mode, const StepW<R>* prev, c
 
 template <typename R>
 cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd, const StepW<R>* next,
-                        int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl) {
-    return launch_atom_io<R, R>(w, mode, prev, upd, next, h_is_zero, q_out, q_out64, st, nl);
+                        int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl, int scope) {
+    return launch_atom_io<R, R>(w, mode, prev, upd, next, h_is_zero, q_out, q_out64, st, nl, scope);
 }
 // "mixed" precision: FP64 per-atom arithmetic and state, FP32 buffers towards the pair kernels
 cudaError_t launch_atom_mixed(const Workspace& w, int mode, const StepW<double>* prev, const UpdW<double>* upd, const StepW<double>* next,
-                              int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl) {
-    return launch_atom_io<double, float>(w, mode, prev, upd, next, h_is_zero, q_out, q_out64, st, nl);
+                              int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* nl, int scope) {
+    return launch_atom_io<double, float>(w, mode, prev, upd, next, h_is_zero, q_out, q_out64, st, nl, scope);
 }
 
 template cudaError_t launch_atom<float>(const Workspace&, int, const StepW<float>*, const UpdW<float>*, const StepW<float>*,
-                                        int, float*, double*, cudaStream_t, int*);
+                                        int, float*, double*, cudaStream_t, int*, int);
 template cudaError_t launch_atom<double>(const Workspace&, int, const StepW<double>*, const UpdW<double>*, const StepW<double>*,
-                                         int, float*, double*, cudaStream_t, int*);
+                                         int, float*, double*, cudaStream_t, int*, int);
 #endif

@@ -581,8 +581,7 @@ cudaError_t launch_far0_fill(const Workspace& w, const int* atom_b0, cudaStream_
 // start at the first pair of the bundle (ustart[b0]); one thread per pair, the <= 31 other j's come from L1.
 __global__ void tile_perm_kernel(int64_t P, const int* __restrict__ pair_i, const int* __restrict__ pair_j,
                                  const int* __restrict__ atom_sys, const int* __restrict__ sys_off,
-                                 const int* __restrict__ atom_b0, const int2* __restrict__ bundle_of_atom_unused,
-                                 const int* __restrict__ ustart, const int* __restrict__ bundle_nat,
+                                 const int* __restrict__ atom_b0, const int* __restrict__ ustart, const int* __restrict__ bundle_nat,
                                  unsigned char* __restrict__ perm) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= P) return;
@@ -606,8 +605,8 @@ __global__ void tile_perm_kernel(int64_t P, const int* __restrict__ pair_i, cons
 #ifndef EPNN_CPU_EMU
 cudaError_t launch_far_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0 || w.n_bundles == 0) return cudaSuccess;
-    if (w.P > 0) {
-        tile_perm_kernel<<<div_up(w.P, 256), 256, 0, st>>>(w.P, w.pair_i, w.pair_j, w.atom_sys, w.sys_off, atom_b0, nullptr,
+    if (w.P > 0 && !(w.pair_const == 2 && w.ek == EDR)) {      // only the round-1 warp-tile GNN kernel reads perm_j
+        tile_perm_kernel<<<div_up(w.P, 256), 256, 0, st>>>(w.P, w.pair_i, w.pair_j, w.atom_sys, w.sys_off, atom_b0,
                                                            w.ustart, w.bundle_nat, w.perm_j);
         ++*nl;
     }

@@ -165,7 +165,7 @@ cudaError_t launch_epn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t
     if (e != cudaSuccess) return e;
     const int per_sm = sizeof(R) == 4 ? 2 : 1;
     const int64_t n_tiles = (w.P + 31) / 32;
-    ea.tile_begin = n_tiles * w.shard_rank / w.shard_world; ea.tile_end = n_tiles * (w.shard_rank + 1) / w.shard_world;
+    ea.tile_begin = 0; ea.tile_end = n_tiles;      // sharded call: the local pair list already holds only the pairs incident to owned rows
     int64_t grid = (ea.tile_end - ea.tile_begin + NW - 1) / NW;
     if (grid < 1) return cudaSuccess;
     if (grid > (int64_t)w.sm_count * per_sm) grid = (int64_t)w.sm_count * per_sm;

@@ -311,9 +311,10 @@ cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t
         // tensor-core mode: this kernel does the near pairs + pad pair only (one unit per row group, last plane)
         const int ns = w.far_tc ? 1 : w.nsplit;
         ga.skip_far = w.far_tc; ga.plane = w.far_tc ? w.nsplit - 1 : 0;
-        const int64_t total = (int64_t)w.n_rg_large * ns;      // this rank's contiguous slice of the work units
+        // sharded call: the row groups that overlap this rank's slice (rows of a boundary group that lie outside it are computed
+        // from whatever their u row holds and never read: S is only consumed for owned rows)
         ga.rg_atom = w.rg_large; ga.nsplit = ns;
-        ga.unit_begin = (int)(total * w.shard_rank / w.shard_world); ga.n_units = (int)(total * (w.shard_rank + 1) / w.shard_world);
+        ga.unit_begin = w.rg_begin * ns; ga.n_units = w.rg_end * ns;
         e = launch_one<R, true, 8>(ga, w.sm_count, st);
         ++*nl;
     }
@@ -389,7 +390,7 @@ __global__ void sp_tally_kernel(int n_entries, const int* __restrict__ tab, cons
 cudaError_t launch_sp_tab_build(const Workspace& w, cudaStream_t st, int* nl) {
     if (w.n_rg_large == 0 || w.n_sp_tab == 0) return cudaSuccess;
     sp_tab_init_kernel<<<div_up((int64_t)w.n_sp_tab * 32, 256), 256, 0, st>>>(w.n_sp_tab, w.sp_tab, w.sp_stamp);
-    sp_tab_fill_kernel<<<div_up(w.n_atoms, 256), 256, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.species, w.rgl_off, w.deg,
+    sp_tab_fill_kernel<<<div_up(w.n_atoms, 256), 256, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.species, w.rgl_off, w.deg_all ? w.deg_all : w.deg,
                                                                 w.sp_tab, w.sp_stamp);
     *nl += 2;
     return cudaGetLastError();

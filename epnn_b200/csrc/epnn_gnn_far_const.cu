@@ -160,8 +160,7 @@ cudaError_t launch_gnn_far_const(const Workspace& w, const StepW<float>& sw, int
     fa.sys_off = w.sys_off; fa.rowptr = w.rowptr; fa.col = w.col;
     fa.u = (const float*)w.u; fa.v = (const float*)w.v; fa.S = (float*)w.S;
     fa.rgl_off = w.rgl_off; fa.sp_stamp = w.sp_stamp; fa.stamp = w.stamp;
-    const int64_t total = (int64_t)w.n_rowblk * nsplit_far;          // this rank's contiguous slice of the work units
-    fa.unit_begin = (int)(total * w.shard_rank / w.shard_world); fa.unit_end = (int)(total * (w.shard_rank + 1) / w.shard_world);
+    fa.unit_begin = w.blk_begin * nsplit_far; fa.unit_end = w.blk_end * nsplit_far;      // sharded call: the row blocks overlapping this rank's slice
     int grid = div_up(fa.unit_end - fa.unit_begin, FARC_NW);
     if (grid < 1) return cudaSuccess;
     if (grid > 2 * w.sm_count) grid = 2 * w.sm_count;

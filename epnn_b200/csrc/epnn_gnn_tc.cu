@@ -331,8 +331,7 @@ cudaError_t launch_gnn_far_tc(const Workspace& w, const float* Whi, const float*
     ga.atom_sys = w.atom_sys; ga.sys_off = w.sys_off; ga.rowptr = w.rowptr; ga.col = w.col;
     ga.u = (const float*)w.u; ga.v = (const float*)w.v; ga.Whi = Whi; ga.Wlo = Wlo; ga.b2 = b2; ga.S = (float*)w.S;
     ga.rgl_off = w.rgl_off; ga.sp_stamp = w.sp_stamp; ga.stamp = w.stamp;
-    const int64_t total = (int64_t)w.n_rg_large * nsplit_tc;
-    ga.unit_begin = (int)(total * w.shard_rank / w.shard_world); ga.unit_end = (int)(total * (w.shard_rank + 1) / w.shard_world);
+    ga.unit_begin = w.rg_begin * nsplit_tc; ga.unit_end = w.rg_end * nsplit_tc;          // sharded call: the row groups overlapping this rank's slice
     int grid = ga.unit_end - ga.unit_begin;
     if (grid < 1) return cudaSuccess;
     if (grid > 2 * w.sm_count) grid = 2 * w.sm_count;

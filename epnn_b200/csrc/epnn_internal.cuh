@@ -226,6 +226,7 @@ struct Workspace {
     const float* xyz; const int* species; const int* sys_off; const float* Qsys; const int* npad;
     // derived
     int* atom_sys;
+    const int* deg_all;                // sharded calls: the degrees of ALL rows (all-gathered copy); NULL otherwise
     int* deg; int* degU; int* rowptr; int* ustart; int* col; int* pid;
     int* pair_i; int* pair_j; double* pair_D; float* e; unsigned char* near;
     int ek;                            // floats per row of `e`: ED (48 descriptor values) or EDR (16 basis coefficients)
@@ -240,7 +241,10 @@ struct Workspace {
     int far_tc;                                   // 1: the far part of the big-system message sum runs on the tensor cores (2: on the
                                                   //    experimental row-per-thread FP32 kernel, epnn_gnn_far_const.cu);
                                                   //    planes [0, nsplit-1) of S are theirs, the SIMT kernel (near only) owns the last
-    int shard_rank, shard_world;                  // this rank's slice of the large-system pair kernels (world 1 = everything)
+    int shard_rank, shard_world;                  // sharded call (epnn_shard_init): large systems are split by rows over the ranks
+    int row_lo, row_hi;                           // rows [row_lo, row_hi) of the chunk belong to this rank (unsharded: [0, n_atoms))
+    int rg_begin, rg_end, blk_begin, blk_end;     // 4-row groups / 32-row blocks of the large systems that overlap the slice
+    const unsigned char* active;                  // sharded: 1 for owned atoms and their near neighbours (rows whose projections are needed here)
     // species tables of the large systems (exact de-duplication of their far columns, epnn_gnn.cu): entry
     // rgl_off[sys] >> 3 (a large system has >= 13 row groups, so the entries of two systems never collide)
     const int* rgl_off;                           // [n_sys + 1] first row group of every system
@@ -253,6 +257,7 @@ struct Workspace {
                                                   // 2 (default) row-run GNN bundle kernel + pair-per-thread EPN bundle kernel + row-per-thread far kernel
     void* args_dev;                               // 1 KB device scratch: argument block of the kernels that take theirs through global memory
     const float* wf_host; const float* wf_dev;    // packed FP32 weights: host mirror and device base (pair_const passes weights as kernel parameters)
+    unsigned long long* near_counter;             // device counter (statistics, may be NULL): unordered pairs in the is_near set
     unsigned long long* slot_counter;             // device counters (statistics): [0] near, [1] far slots evaluated by the row-run GNN kernel
     unsigned long long* dedup_rows;               // device counter (statistics): rows whose far part was collapsed, summed over steps
     void* h; void* S; void* u; void* v; void* delta;   // precision-dependent (float or double)
@@ -310,9 +315,9 @@ template <typename R> cudaError_t launch_epn_pair(const Workspace& w, const Step
 #ifndef EPNN_CPU_EMU
 template <typename R> cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd,
                                               const StepW<R>* next, int h_is_zero, float* q_out, double* q_out64,
-                                              cudaStream_t st, int* n_launch);
+                                              cudaStream_t st, int* n_launch, int scope = 0);      // scope: see AtomArgs (sharded calls)
 cudaError_t launch_atom_mixed(const Workspace& w, int mode, const StepW<double>* prev, const UpdW<double>* upd, const StepW<double>* next,
-                              int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* n_launch);   // precision 48
+                              int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* n_launch, int scope = 0);   // precision 48
 cudaError_t launch_atom_const(const Workspace& w, int mode, const StepW<float>* prev, const UpdW<float>* upd, const StepW<float>* next,
                               int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* n_launch);   // option pair_const
 

@@ -168,11 +168,17 @@ __global__ void nbr_kernel(int n_atoms, const int* __restrict__ atom_sys, const 
                            const int* __restrict__ rowptr, const int* __restrict__ ustart, int* __restrict__ col,
                            int* __restrict__ pair_i, int* __restrict__ pair_j, double* __restrict__ pair_D,
                            const CellGrid* __restrict__ grid, const int* __restrict__ cell_start,
-                           const int* __restrict__ cell_atoms, double* __restrict__ Dtmp) {
+                           const int* __restrict__ cell_atoms, double* __restrict__ Dtmp, int row_lo, int row_hi) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_atoms) return;
     const int s = atom_sys[i];
     const int a0 = sys_off[s], a1 = sys_off[s + 1];
+    // Sharded call (epnn_shard_init): rows of LARGE systems are built by the rank that owns them, [row_lo, row_hi); small
+    // systems are replicated.  A pair is listed under row i if j > i, or if j lies below the slice ("foreign lower": row j
+    // is not built here) -- always as (min, max), so every rank evaluates a cut pair in the same canonical orientation.
+    const bool large = a1 - a0 > SMALL_MAX;
+    if (large && (i < row_lo || i >= row_hi)) { if (!FILL) { deg[i] = 0; degU[i] = 0; } return; }
+    const int flo = large ? row_lo : a0;            // columns below flo are foreign lowers (none for small systems: j >= a0)
     const float xi = xyz[3 * i], yi = xyz[3 * i + 1], zi = xyz[3 * i + 2];
     int c = 0, cu = 0;
     int wp = 0, wu = 0;
@@ -184,12 +190,13 @@ __global__ void nbr_kernel(int n_atoms, const int* __restrict__ atom_sys, const 
             if (far_reject(xi, yi, zi, xj, yj, zj)) continue;
             const double D = dist64(xi, yi, zi, xj, yj, zj);
             if (D < 3.0) {
+                const bool listed = j > i || j < flo;
                 if (FILL) {
                     col[wp + c] = j;
-                    if (j > i) { pair_i[wu + cu] = i; pair_j[wu + cu] = j; pair_D[wu + cu] = D; }
+                    if (listed) { pair_i[wu + cu] = min(i, j); pair_j[wu + cu] = max(i, j); pair_D[wu + cu] = D; }
                 }
                 ++c;
-                cu += (j > i);
+                cu += listed;
             }
         }
     } else {
@@ -214,7 +221,7 @@ __global__ void nbr_kernel(int n_atoms, const int* __restrict__ atom_sys, const 
                     if (D < 3.0) {
                         if (FILL) { col[wp + c] = j; Dtmp[wp + c] = D; }
                         ++c;
-                        cu += (j > i);
+                        cu += (j > i || j < flo);
                     }
                 }
             }
@@ -230,7 +237,7 @@ __global__ void nbr_kernel(int n_atoms, const int* __restrict__ atom_sys, const 
             int k = 0;
             for (int p = 0; p < c; ++p) {
                 const int j = col[wp + p];
-                if (j > i) { pair_i[wu + k] = i; pair_j[wu + k] = j; pair_D[wu + k] = Dtmp[wp + p]; ++k; }
+                if (j > i || j < flo) { pair_i[wu + k] = min(i, j); pair_j[wu + k] = max(i, j); pair_D[wu + k] = Dtmp[wp + p]; ++k; }
             }
         }
     }
@@ -242,32 +249,39 @@ cudaError_t launch_nbr_count(const Workspace& w, const CellWork& cw, cudaStream_
     if (w.n_atoms == 0) return cudaSuccess;
     nbr_kernel<false><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, w.deg, w.degU,
                                                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                              cw.grid, cw.cell_start, cw.cell_atoms, nullptr);
+                                                              cw.grid, cw.cell_start, cw.cell_atoms, nullptr, w.row_lo, w.row_hi);
     ++*nl;
     return cudaGetLastError();
 }
 #endif
 
-// pid of every CSR entry: upper entries (j > i) are numbered ustart[i] + rank; lower entries (j < i)
-// look the pair up in row j's upper part (binary search; rows are sorted).
+// pid of every CSR entry.  Row r lists degU[r] pairs in column order: its foreign lowers (sharded calls only: columns
+// below the slice, always at the head of the ascending row) and its uppers (col > r, the tail of the row).  An entry
+// (i, j) of row i is either listed there (rank among the listed entries of row i), or j is an owned lower: then the pair
+// sits among the uppers of row j (binary search; rows are sorted).
 __global__ void nbr_rev_kernel(int n_atoms, const int* __restrict__ rowptr, const int* __restrict__ ustart,
                                const int* __restrict__ degU, const int* __restrict__ col, int* __restrict__ pid) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_atoms) return;
     const int r0 = rowptr[i], r1 = rowptr[i + 1];
-    const int nlow = (r1 - r0) - degU[i];
+    int nup = 0;
+    for (int k = r1 - 1; k >= r0 && col[k] > i; --k) ++nup;
+    const int nfl = degU[i] - nup;                  // foreign lowers of row i
     for (int k = r0; k < r1; ++k) {
         const int j = col[k];
-        if (k - r0 >= nlow) {
-            pid[k] = ustart[i] + (k - r0 - nlow);
+        if (k - r0 < nfl) {
+            pid[k] = ustart[i] + (k - r0);
+        } else if (j > i) {
+            pid[k] = ustart[i] + nfl + (k - (r1 - nup));
         } else {
             const int jr1 = rowptr[j + 1];
-            int lo = jr1 - degU[j], hi = jr1 - 1;      // upper part of row j, must contain i
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (col[mid] < i) lo = mid + 1; else hi = mid;
-            }
-            pid[k] = ustart[j] + (lo - (jr1 - degU[j]));
+            int lo = rowptr[j], hi = jr1;           // first entry of row j with col > j
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[mid] > j) hi = mid; else lo = mid + 1; }
+            const int fu = lo;
+            const int nflj = degU[j] - (jr1 - fu);
+            hi = jr1 - 1;                           // uppers of row j contain i
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (col[mid] < i) lo = mid + 1; else hi = mid; }
+            pid[k] = ustart[j] + nflj + (lo - fu);
         }
     }
 }
@@ -287,10 +301,12 @@ __global__ void nbr_rev_kernel(int n_atoms, const int* __restrict__ rowptr, cons
 #define EDGE_PAIRS 128
 template <int EKOUT>
 __global__ void __launch_bounds__(EDGE_PAIRS) edge_desc_kernel(int64_t P, const double* __restrict__ pair_D,
-                                                               float* __restrict__ e, unsigned char* __restrict__ near) {
+                                                               float* __restrict__ e, unsigned char* __restrict__ near,
+                                                               unsigned long long* __restrict__ near_count) {
     __shared__ float tile[EDGE_PAIRS][ED + 1];
     const int64_t p0 = (int64_t)blockIdx.x * EDGE_PAIRS;
     const int64_t p = p0 + threadIdx.x;
+    bool is_near = false;
     if (p < P) {
         const double D = pair_D[p];
         const double C = cutoff_fn(D);
@@ -315,7 +331,8 @@ __global__ void __launch_bounds__(EDGE_PAIRS) edge_desc_kernel(int64_t P, const 
             row[kc + dk] = ef;
             emax = fmaxf(emax, ef);
         }
-        near[p] = emax > 1e-5f ? 1 : 0;
+        is_near = emax > 1e-5f;
+        near[p] = is_near ? 1 : 0;
         if (EKOUT != ED) {
             double cr[EDR];
 #pragma unroll
@@ -329,6 +346,10 @@ __global__ void __launch_bounds__(EDGE_PAIRS) edge_desc_kernel(int64_t P, const 
             for (int r = 0; r < EDR; ++r) row[r] = __double2float_rn(cr[r]);
         }
     }
+    if (near_count) {                                   // statistics (integer: order-independent): near pairs of this block
+        const unsigned b = __ballot_sync(0xffffffffu, is_near);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(near_count, (unsigned long long)__popc(b));
+    }
     __syncthreads();
     const int rows = (int)min((int64_t)EDGE_PAIRS, P - p0);
     float* dst = e + p0 * EKOUT;
@@ -340,13 +361,13 @@ cudaError_t launch_nbr_fill(const Workspace& w, const CellWork& cw, cudaStream_t
     if (w.n_atoms == 0) return cudaSuccess;
     nbr_kernel<true><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, nullptr, nullptr,
                                                              w.rowptr, w.ustart, w.col, w.pair_i, w.pair_j, w.pair_D,
-                                                             cw.grid, cw.cell_start, cw.cell_atoms, cw.Dtmp);
+                                                             cw.grid, cw.cell_start, cw.cell_atoms, cw.Dtmp, w.row_lo, w.row_hi);
     ++*nl;
     nbr_rev_kernel<<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.rowptr, w.ustart, w.degU, w.col, w.pid);
     ++*nl;
     if (w.P > 0) {
-        if (w.ek == ED) edge_desc_kernel<ED><<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near);
-        else            edge_desc_kernel<EDR><<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near);
+        if (w.ek == ED) edge_desc_kernel<ED><<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near, w.near_counter);
+        else            edge_desc_kernel<EDR><<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near, w.near_counter);
         ++*nl;
     }
     return cudaGetLastError();

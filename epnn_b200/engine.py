@@ -62,14 +62,22 @@ class Engine:
         return p.value or 0
 
     def set_shard(self, rank: int, world: int, group=None):
-        """Split the large-system pair kernels over ``world`` ranks (epnn_set_shard); the per-step exchange is a
-        ``torch.distributed.all_reduce`` on this ctx's stream.  ``world == 1`` switches sharding off."""
+        """Shard the large systems of every following call over ``world`` ranks (epnn_shard_init; collective).  The NCCL
+        unique id is made on rank 0 and broadcast through ``torch.distributed`` (any backend); the data-path exchanges
+        are ncclAllGather calls inside the library, on this ctx's stream.  ``world == 1`` switches sharding off."""
         if world > 1:
-            from .shard import make_allreduce
-            self._shard_cb, self.shard_state = make_allreduce(group, self.device, self.stream)
+            from .shard import broadcast_unique_id
+            uid = broadcast_unique_id(self.lib, rank, group, self.device)
+            self._check(self.lib.epnn_shard_init(self._h, rank, world, uid))
         else:
-            self._shard_cb, self.shard_state = _capi.ALLREDUCE_FN(0), None
-        self._check(self.lib.epnn_set_shard(self._h, rank, world, self._shard_cb, None))
+            self._check(self.lib.epnn_shard_init(self._h, 0, 1, None))
+
+    @property
+    def shard_state(self):
+        """{"calls", "bytes"}: all-gathers issued and bytes received by this rank since ``set_shard``."""
+        calls, nbytes = C.c_int64(0), C.c_int64(0)
+        self._check(self.lib.epnn_shard_stats(self._h, C.byref(calls), C.byref(nbytes)))
+        return {"calls": calls.value, "bytes": nbytes.value}
 
     def measure_fp32_peak(self, repeats: int = 5) -> float:
         """Measured FP32 FMA peak of this GPU in TFLOP/s (epnn_measure_fp32_peak)."""

@@ -182,18 +182,32 @@ void epnn_xyz_free(epnn_xyz_batch* b);
 int epnn_host_alloc(void** ptr, size_t bytes);
 int epnn_host_free(void* ptr);
 
-/* Multi-GPU sharding of LARGE systems (n > 48 atoms; BASELINE config 5: one big system on several GPUs).
- * Every rank is given the SAME epnn_infer_batch call.  Everything that is O(atoms) -- neighbour lists, per-atom
- * kernels, the charge reduction -- is replicated; the two kernels that carry the work are split by contiguous
- * ranges (message-passing: rows of the exact all-pairs sum; electron passing: tiles of the near-pair list), the
- * rest of their output buffers is zero-filled, and after each of the T steps / T passes the library calls
- * `allreduce` once (sum over ranks, in place, on the ctx stream) on the partial-sum buffer S, respectively on the
- * per-pair transfers delta.  Each element is non-zero on one rank only, so the sum is exact and the result is
- * bit-identical to a single-GPU run whatever order the collective adds in.  The callback is the NVLink exchange
- * step (torch.distributed / NCCL in this repo's host code); rank 0 also runs the small-system bundles.
- *   allreduce(user, dev_ptr, count, is_double, stream) -> 0 on success.   world == 1 switches sharding off. */
-typedef int (*epnn_allreduce_fn)(void* user, void* dev_ptr, size_t count, int is_double, void* stream);
-int epnn_set_shard(epnn_ctx* ctx, int rank, int world, epnn_allreduce_fn allreduce, void* user);
+/* Multi-GPU sharding of LARGE systems (n > 48 atoms; BASELINE config 5: one big system on several GPUs of one node).
+ * (No counterpart in the reference: infer.py:62-73 is single-process, batch 1.)
+ * One process per GPU; every rank is given the SAME epnn_infer_batch call.  The atom index space of a batch is cut into
+ * `world` equal slices (epnn_shard_slice); a rank OWNS the rows of large systems that fall into its slice:
+ *   - the neighbour list, the descriptors and the pair list are built for owned rows only (a pair cut by a slice boundary
+ *     is held by both owners, always as (min, max));
+ *   - per-atom kernels (update MLP, projections, charge reduction) run on owned rows; the electron-passing projections
+ *     additionally on the near neighbours of owned rows;
+ *   - the message-passing kernels (the exact all-pairs sum) run on owned rows against ALL columns;
+ *   - exchanges, each one in-place ncclAllGather of equal slices on the ctx stream (NVLink / NVSwitch): v after every
+ *     message-passing step but the last (128 B/atom), the update MLP's last hidden layer once (128 B/atom), the charges
+ *     after every electron-passing pass (8 B/atom).  Cut pairs are evaluated by both owners in the same orientation, so
+ *     no transfer is exchanged and charge conservation holds on every rank.
+ * Small systems (n <= 48) of the same call are replicated on every rank.  Every row is computed by exactly the
+ * arithmetic of a single-GPU run: the result is bit-identical to it, on every rank (each rank returns all charges).
+ * NCCL is bound at run time (dlopen of libnccl.so.2: the copy already in the process, e.g. torch's, else the system's).
+ *   epnn_shard_unique_id(id)             rank 0: a fresh 128-byte ncclUniqueId, to be handed to every rank by the caller
+ *                                        (torch.distributed.broadcast in epnn_b200/shard.py, MPI_Bcast, a file, ...)
+ *   epnn_shard_init(ctx, rank, world, id) collective over the `world` ranks: builds this ctx's communicator.
+ *                                        world == 1 (id may be NULL) tears it down and switches sharding off.
+ *   epnn_shard_slice(n, rank, world, &b, &e)  the rows [b, e) rank owns in a batch of n atoms (pure function)
+ *   epnn_shard_stats(ctx, &calls, &bytes) all-gathers issued / bytes received by this rank since epnn_shard_init */
+int epnn_shard_unique_id(void* id128);
+int epnn_shard_init(epnn_ctx* ctx, int rank, int world, const void* id128);
+int epnn_shard_slice(int64_t n_atoms, int rank, int world, int64_t* begin, int64_t* end);
+int epnn_shard_stats(epnn_ctx* ctx, int64_t* calls, int64_t* bytes);
 
 /* The CUDA stream (cudaStream_t, returned as void*) every kernel and copy of this ctx is enqueued on, so
  * that a caller can record its own CUDA events around a sequence of calls (bench.py does). */

@@ -1,5 +1,6 @@
-"""Two real GPUs (skipped on a 1-GPU box): the sharded large-system path (epnn_set_shard + NCCL all-reduce per
-step / pass) must reproduce the single-GPU charges BIT FOR BIT, including a batch that mixes small systems in."""
+"""Two real GPUs (skipped on a 1-GPU box): the sharded large-system path (epnn_shard_init: rows owned per rank,
+ncclAllGather of v / l2 / q inside the library) must reproduce the single-GPU charges BIT FOR BIT on every rank,
+including a batch that mixes small systems in, a system cut in the middle of a row block, and the hidden state."""
 import os
 import socket
 
@@ -48,10 +49,16 @@ def _worker(rank, world, port, tmp):
             w = load_weights(os.path.join(root, "tests", "golden", "checkpoints", name))
             eng = Engine(w, device=rank)
             single = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
+            eng.set_option("keep_hidden", 1)
+            eng.infer_batch(offs, xyz, sp, Q, npad)
+            h1 = eng.hidden(int(offs[-1])).copy()
             eng.set_shard(rank, world)
             sharded = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
-            assert eng.shard_state["error"] is None and eng.shard_state["calls"] == 2 * w.T
+            h2 = eng.hidden(int(offs[-1])).copy()
+            st = eng.shard_state
+            assert st["calls"] == (w.T - 1) + 2 + w.T + 1 and st["bytes"] > 0      # v per step but the last, l2 + h, q per pass, full degrees
             assert np.array_equal(single, sharded), (name, np.abs(single - sharded).max())
+            assert np.array_equal(h1, h2)
             eng.set_shard(0, 1)
             again = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1]
             assert np.array_equal(single, again)

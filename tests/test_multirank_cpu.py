@@ -1,9 +1,10 @@
 """World-size-2 tests on CPU (gloo): the host-side logic of both multi-GPU modes.
 
 No CUDA here: what is exercised is (a) the molecule-stream sharding bench.py uses for config 4 (disjoint, complete,
-independent of the world size), (b) the slicing formula shared with libepnn_b200 and (c) the all-reduce callback
-epnn_set_shard calls -- through the very ctypes function object the library would call -- with each rank owning a
-slice of an otherwise zero buffer, which must reproduce the unsharded buffer bit for bit."""
+independent of the world size), (b) the row-slice formula of the sharded large-system path -- the Python mirror against
+the library's own epnn_shard_slice, equal slices that tile [0, n) -- and an emulation of the in-place all-gather of equal
+slices the library performs with NCCL (every rank ends with every owner's rows, bit for bit), and (c) the hand-over of
+rank 0's NCCL unique id to every rank through torch.distributed (gloo here, nccl on the GPUs)."""
 import ctypes as C
 import os
 import socket
@@ -39,27 +40,48 @@ def _worker(rank, world, port, tmp):
         counts = torch.tensor([int(offs[-1])], dtype=torch.int64)
         dist.all_reduce(counts)
         assert int(counts.item()) == int(full[0][-1])
-        # (b) slicing covers [0, n) without gaps or overlap for awkward n
-        for n in (0, 1, 7, 555 * 18, 10 ** 10 + 3):
-            b, e = shard.slice_range(n, rank, world)
+        # (b) row slices: equal sizes (multiples of 32), tile [0, n), agree with the library's own formula
+        from epnn_b200 import _capi
+        lib = _capi.load()
+        for n in (1, 7, 2220, 2220 + 700 + 90, 1_000_000, 2 ** 31 - 1):
+            b, e = shard.slice_rows(n, rank, world)
+            cb, ce = C.c_int64(-1), C.c_int64(-1)
+            assert lib.epnn_shard_slice(n, rank, world, C.byref(cb), C.byref(ce)) == 0
+            assert (cb.value, ce.value) == (b, e)
             lo = torch.tensor([b, e], dtype=torch.int64)
             allr = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
             dist.all_gather(allr, lo)
             assert allr[0][0] == 0 and allr[-1][1] == n
             assert all(int(allr[k][1]) == int(allr[k + 1][0]) for k in range(world - 1))
-        # (c) the callback, called the way the C library calls it
-        cb, state = shard.make_allreduce(group=None, device=None)
+            size = -(-n // world); size = (size + 31) // 32 * 32
+            assert all(int(a[1] - a[0]) in (size, max(0, n - size * k)) for k, a in enumerate(allr))
+        assert lib.epnn_shard_slice(10, 2, 2, C.byref(cb), C.byref(ce)) == -1        # rank out of range
+        # in-place all-gather of equal slices, the exchange the library issues after every step / pass: each rank fills the
+        # rows it owns of a padded array, the gather must hand every rank the complete array
         rng = np.random.default_rng(42)
-        for dtype, is_double in ((np.float32, 0), (np.float64, 1)):
-            ref = rng.normal(size=10007).astype(dtype)              # same on both ranks (same seed)
-            ref[::13] = 0.0
-            mine = np.zeros_like(ref)
-            b, e = shard.slice_range(len(ref), rank, world)
-            mine[b:e] = ref[b:e]
-            rc = cb(None, mine.ctypes.data_as(C.c_void_p), len(mine), is_double, None)
-            assert rc == 0 and state["error"] is None
-            assert np.array_equal(mine, ref)                        # x + 0 is exact: bit-identical to the unsharded buffer
-        assert state["calls"] == 2
+        n = 2220 + 700 + 90
+        ref = rng.normal(size=(n, 32)).astype(np.float32)               # same on both ranks (same seed)
+        size = (-(-n // world) + 31) // 32 * 32
+        mine = np.full((size * world, 32), np.nan, np.float32)
+        b, e = shard.slice_rows(n, rank, world)
+        mine[b:e] = ref[b:e]
+        parts = [torch.zeros(size, 32) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(mine[size * rank:size * (rank + 1)]))
+        full = torch.cat(parts).numpy()
+        assert np.array_equal(full[:n], ref)
+        # (c) the NCCL unique id travels from rank 0 to every rank (gloo: host tensor).  ncclGetUniqueId needs no GPU; if this
+        # box has no usable libnccl the library says so instead of handing out garbage
+        got = None
+        try:
+            got = shard.broadcast_unique_id(lib, rank)
+        except _capi.EpnnError as ex:
+            assert rank == 0 and "nccl" in str(ex).lower()
+        flag = torch.tensor([0 if got is None else 1])
+        dist.all_reduce(flag)
+        if int(flag.item()) == world:
+            ids = [torch.zeros(128, dtype=torch.uint8) for _ in range(world)]
+            dist.all_gather(ids, torch.frombuffer(bytearray(bytes(got)), dtype=torch.uint8))
+            assert all(torch.equal(ids[0], x) for x in ids) and int(ids[0].sum()) > 0
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
@@ -71,8 +93,9 @@ def test_world_size_2_gloo(tmp_path):
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
 
 
-def test_set_shard_argument_checks():
+def test_shard_init_argument_checks():
     """No GPU needed: a NULL ctx is rejected before anything else."""
     from epnn_b200 import _capi
     lib = _capi.load()
-    assert lib.epnn_set_shard(None, 0, 2, _capi.ALLREDUCE_FN(0), None) == -1
+    assert lib.epnn_shard_init(None, 0, 2, None) == -1
+    assert lib.epnn_shard_unique_id(None) == -1

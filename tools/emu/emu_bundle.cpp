@@ -22,7 +22,7 @@ extern "C" int emu_bundle_lists(int n_atoms, int n_bundles, const int* bundle_xy
     exclusive_scan(cnt.data(), far_off, n_atoms);
     emu_launch_simple(div_up(n_atoms, 128), 128, [&] { far_fill_kernel(n_atoms, atom_sys, sys_off, npad, rowptr, col, atom_b0, far_off, far_list); });
     if (P > 0)
-        emu_launch_simple(div_up(P, 256), 256, [&] { tile_perm_kernel((int64_t)P, pair_i, pair_j, atom_sys, sys_off, atom_b0, nullptr, ustart, bundle_nat, perm_j); });
+        emu_launch_simple(div_up(P, 256), 256, [&] { tile_perm_kernel((int64_t)P, pair_i, pair_j, atom_sys, sys_off, atom_b0, ustart, bundle_nat, perm_j); });
     std::vector<int> cnt0(n_atoms + 1, 0);
     emu_launch_simple(div_up(n_atoms, 128), 128, [&] {
         far0_kernel<0>(n_atoms, atom_sys, sys_off, npad, species, rowptr, col, nullptr, rep, cnt0.data(), nullptr, nullptr, nullptr); });

@@ -85,7 +85,7 @@ extern "C" int emu_infer(int T, int n_x, const float* w_packed, size_t n_w, int 
     }
     emu_launch_simple(div_up(n, 128), 128, [&] {
         k_nbr::nbr_kernel<false>(n, atom_sys.data(), off, xyz, deg.data(), degU.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                 grid.data(), cell_start.data(), cell_atoms.data(), nullptr); });
+                                 grid.data(), cell_start.data(), cell_atoms.data(), nullptr, 0, n); });
     exclusive_scan(deg.data(), rowptr.data(), n);
     exclusive_scan(degU.data(), ustart.data(), n);
     const int nnz = rowptr[n], Pn = ustart[n];
@@ -95,10 +95,10 @@ extern "C" int emu_infer(int T, int n_x, const float* w_packed, size_t n_w, int 
     std::vector<unsigned char> near(Pn + 16), perm_j(Pn + 16);
     emu_launch_simple(div_up(n, 128), 128, [&] {
         k_nbr::nbr_kernel<true>(n, atom_sys.data(), off, xyz, nullptr, nullptr, rowptr.data(), ustart.data(), col.data(), pair_i.data(), pair_j.data(),
-                                pair_D.data(), grid.data(), cell_start.data(), cell_atoms.data(), Dtmp.data()); });
+                                pair_D.data(), grid.data(), cell_start.data(), cell_atoms.data(), Dtmp.data(), 0, n); });
     emu_launch_simple(div_up(n, 128), 128, [&] { k_nbr::nbr_rev_kernel(n, rowptr.data(), ustart.data(), degU.data(), col.data(), pid.data()); });
     if (Pn > 0)
-        emu_launch_grid(div_up(Pn, EDGE_PAIRS), EDGE_PAIRS / 32, 0, [&] { k_nbr::edge_desc_kernel<EDR>((int64_t)Pn, pair_D.data(), e.data(), near.data()); });
+        emu_launch_grid(div_up(Pn, EDGE_PAIRS), EDGE_PAIRS / 32, 0, [&] { k_nbr::edge_desc_kernel<EDR>((int64_t)Pn, pair_D.data(), e.data(), near.data(), nullptr); });
 
     // ---------------------------------------------------------------- bundles, far lists, row groups, species tables
     std::vector<int2> bundles;
@@ -124,7 +124,7 @@ extern "C" int emu_infer(int T, int n_x, const float* w_packed, size_t n_w, int 
     if (n_bundles) {
         if (Pn > 0)
             emu_launch_simple(div_up(Pn, 256), 256, [&] {
-                k_bundle::tile_perm_kernel((int64_t)Pn, pair_i.data(), pair_j.data(), atom_sys.data(), off, atom_b0.data(), nullptr, ustart.data(),
+                k_bundle::tile_perm_kernel((int64_t)Pn, pair_i.data(), pair_j.data(), atom_sys.data(), off, atom_b0.data(), ustart.data(),
                                            bundle_nat.data(), perm_j.data()); });
         emu_launch_simple(div_up(n, 128), 128, [&] {
             k_bundle::far_fill_kernel(n, atom_sys.data(), off, npad.data(), rowptr.data(), col.data(), atom_b0.data(), far_off.data(), far_list.data()); });

@@ -30,7 +30,7 @@ extern "C" int emu_neighbor_counts(const double* mu, const double* B, int n_atom
         emu_launch_simple(div_up(n_atoms, 256), 256, [&] { cell_bin_kernel<1>(n_atoms, atom_sys, sys_off, xyz, grid, cnt.data(), cell_start, cell_atoms); });
     }
     emu_launch_simple(div_up(n_atoms, 128), 128, [&] {
-        nbr_kernel<false>(n_atoms, atom_sys, sys_off, xyz, deg, degU, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, grid, cell_start, cell_atoms, nullptr); });
+        nbr_kernel<false>(n_atoms, atom_sys, sys_off, xyz, deg, degU, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, grid, cell_start, cell_atoms, nullptr, 0, n_atoms); });
     exclusive_scan(deg, rowptr, n_atoms);
     exclusive_scan(degU, ustart, n_atoms);
     return 0;
@@ -42,12 +42,12 @@ extern "C" int emu_neighbor_fill(int n_atoms, const int* atom_sys, const int* sy
                                  int ek, float* e, unsigned char* near) {
     const CellGrid* grid = reinterpret_cast<const CellGrid*>(grid_ints);
     emu_launch_simple(div_up(n_atoms, 128), 128, [&] {
-        nbr_kernel<true>(n_atoms, atom_sys, sys_off, xyz, nullptr, nullptr, rowptr, ustart, col, pair_i, pair_j, pair_D, grid, cell_start, cell_atoms, Dtmp); });
+        nbr_kernel<true>(n_atoms, atom_sys, sys_off, xyz, nullptr, nullptr, rowptr, ustart, col, pair_i, pair_j, pair_D, grid, cell_start, cell_atoms, Dtmp, 0, n_atoms); });
     emu_launch_simple(div_up(n_atoms, 128), 128, [&] { nbr_rev_kernel(n_atoms, rowptr, ustart, degU, col, pid); });
     const int64_t P = ustart[n_atoms];
     if (P > 0) {
-        if (ek == ED) emu_launch_grid(div_up(P, EDGE_PAIRS), EDGE_PAIRS / 32, 0, [&] { edge_desc_kernel<ED>(P, pair_D, e, near); });
-        else          emu_launch_grid(div_up(P, EDGE_PAIRS), EDGE_PAIRS / 32, 0, [&] { edge_desc_kernel<EDR>(P, pair_D, e, near); });
+        if (ek == ED) emu_launch_grid(div_up(P, EDGE_PAIRS), EDGE_PAIRS / 32, 0, [&] { edge_desc_kernel<ED>(P, pair_D, e, near, nullptr); });
+        else          emu_launch_grid(div_up(P, EDGE_PAIRS), EDGE_PAIRS / 32, 0, [&] { edge_desc_kernel<EDR>(P, pair_D, e, near, nullptr); });
     }
     return 0;
 }
