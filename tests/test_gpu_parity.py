@@ -83,10 +83,12 @@ def test_init_edges_matches_reference_descriptor(engines, mixed):
 
 
 def test_neighbor_synthetic_shell_pairs(engines):
-    """Pairs drawn right around the decision boundary D* ~ 2.99396 and the 3.0 cutoff (hardest cases)."""
+    """10^6 pairs drawn right around the decision boundary D* ~ 2.99396 of is_near and the 3.0 cutoff (the hardest cases: the
+    flag rests on CUDA's float64 exp / cos agreeing with the host libm at float32 rounding boundaries)."""
     rng = np.random.default_rng(5)
-    n_sys = 20000
-    D = np.concatenate([rng.uniform(2.9935, 2.9945, n_sys // 2), rng.uniform(2.9995, 3.0005, n_sys // 2)])
+    n_sys = 1_000_000
+    D = np.concatenate([rng.uniform(2.9935, 2.9945, n_sys // 4), rng.uniform(2.99390, 2.99402, n_sys // 4),
+                        rng.uniform(2.9995, 3.0005, n_sys // 4), rng.uniform(2.99998, 3.00002, n_sys // 4)])
     u = rng.normal(size=(n_sys, 3))
     u /= np.linalg.norm(u, axis=1, keepdims=True)
     a = rng.uniform(-5, 5, size=(n_sys, 3))
