@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <mutex>
 #include <new>
 #include <string>
@@ -61,6 +62,9 @@ static inline int64_t shard_slice_rows(int64_t n, int world) { const int64_t s =
 struct epnn_ctx {
     int device = 0, T = 0, n_x = 0, n_species = 0, sm_count = 0;
     cudaStream_t stream = nullptr;
+    // host-buffer calls: chunk k + 1 is uploaded and chunk k - 1 downloaded while chunk k computes (two staging slots)
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     int precision = 32, timing = 0, keep_hidden = 0;      // precision: 32, 48 (mixed), 64, 0 (auto: probe on the first call)
     int eff_precision = 32;      // precision of the call in flight (32 / 48 / 64)
     int auto_choice = 0;         // precision chosen by the probe (0 = not probed yet)
@@ -94,7 +98,7 @@ static thread_local std::string g_create_err;
 enum {
     B_XYZ, B_SPECIES, B_OFF, B_Q, B_NPAD, B_ATOMSYS, B_DEG, B_DEGU, B_ROWPTR, B_USTART, B_COL, B_PID, B_PI, B_PJ, B_PD,
     B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_FAR0CNT, B_FAR0OFF, B_FAR0LIST, B_FAR0W, B_REP, B_ATOMB0, B_BNAT, B_PERM, B_LARGESYS, B_GRID, B_CELLCNT, B_CELLSTART, B_CELLATOMS, B_DTMP, B_H, B_L2, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
-    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_ROWBLK, B_ROWL, B_ARGS, B_DEGALL, B_ACTIVE, B_COUNT
+    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_ROWBLK, B_ROWL, B_ARGS, B_DEGALL, B_ACTIVE, B_XYZ_1, B_SPECIES_1, B_Q_1, B_OUT32_1, B_OUT64_1, B_OFFIN_1, B_COUNT
 };
 
 static int fail(epnn_ctx* c, int code, const char* fmt, ...) {
@@ -178,6 +182,13 @@ extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_
     CUC(cudaSetDevice(device));
     CUC(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        CUC(cudaEventCreateWithFlags(&c->ev_h2d[k], cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
+        CUC(cudaEventCreateWithFlags(&c->ev_d2h[k], cudaEventDisableTiming));
+    }
     CUC(cudaMalloc(&c->d_flags, 8 * sizeof(int)));
     CUC(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
     double mu[48];
@@ -228,6 +239,13 @@ extern "C" void epnn_destroy(epnn_ctx* c) {
     if (c->w2split) cudaFree(c->w2split);
     if (c->d_flags) cudaFree(c->d_flags);
     if (c->h_flags) cudaFreeHost(c->h_flags);
+    for (int k = 0; k < 2; ++k) {
+        if (c->ev_h2d[k]) cudaEventDestroy(c->ev_h2d[k]);
+        if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+        if (c->ev_d2h[k]) cudaEventDestroy(c->ev_d2h[k]);
+    }
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -755,32 +773,55 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
     d_near_count = (unsigned long long*)p;
     CU(c, cudaMemsetAsync(d_near_count, 0, 4 * sizeof(unsigned long long), st));      // [0] near pairs, [1] de-duplicated rows, [2] near / [3] far slots run by the bundle GNN kernel
     tm.mark(0);
-    for (size_t ci = 0; ci + 1 < bounds.size(); ++ci) {
+    // ---- staging: two slots, sized once for the largest chunk (no regrow while copies are in flight).  Host-buffer calls
+    // pipeline the chunks: upload(k + 1) and download(k - 1) run on their own streams while chunk k computes.
+    const size_t n_chunks = bounds.size() - 1;
+    int64_t max_na = 0, max_ns = 0;
+    for (size_t ci = 0; ci < n_chunks; ++ci) {
+        max_na = std::max<int64_t>(max_na, off[bounds[ci + 1]] - off[bounds[ci]]);
+        max_ns = std::max<int64_t>(max_ns, bounds[ci + 1] - bounds[ci]);
+    }
+    struct Slot { int* off = nullptr; float* xyz = nullptr; int* sp = nullptr; float* Q = nullptr; float* o32 = nullptr; double* o64 = nullptr; } slot[2];
+    const int n_slots = host_io && n_chunks > 1 ? 2 : 1;
+    for (int k = 0; k < n_slots; ++k) {
+        if ((rc = ensure(c, k ? B_OFFIN_1 : B_OFFIN, sizeof(int) * ((size_t)max_ns + 1) * 2 + 64, &p)) != EPNN_OK) return rc; slot[k].off = (int*)p;
+        if (!host_io) continue;
+        if ((rc = ensure(c, k ? B_XYZ_1 : B_XYZ, sizeof(float) * 3 * (size_t)max_na, &p)) != EPNN_OK) return rc; slot[k].xyz = (float*)p;
+        if ((rc = ensure(c, k ? B_SPECIES_1 : B_SPECIES, sizeof(int) * (size_t)max_na, &p)) != EPNN_OK) return rc; slot[k].sp = (int*)p;
+        if ((rc = ensure(c, k ? B_Q_1 : B_Q, sizeof(float) * (size_t)max_ns, &p)) != EPNN_OK) return rc; slot[k].Q = (float*)p;
+        if (q_out) { if ((rc = ensure(c, k ? B_OUT32_1 : B_OUT32, sizeof(float) * (size_t)max_na, &p)) != EPNN_OK) return rc; slot[k].o32 = (float*)p; }
+        if (q_out64) { if ((rc = ensure(c, k ? B_OUT64_1 : B_OUT64, sizeof(double) * (size_t)max_na, &p)) != EPNN_OK) return rc; slot[k].o64 = (double*)p; }
+    }
+    const bool piped = n_slots == 2;
+    cudaStream_t up = piped ? c->h2d_stream : st, down = piped ? c->d2h_stream : st;
+    auto upload = [&](size_t ci, int k) -> int {      // offsets / npad always come from the host: they drive launch geometry
+        const int64_t s0 = bounds[ci], s1 = bounds[ci + 1];
+        const int ns = (int)(s1 - s0), a0 = off[s0], na = off[s1] - off[s0];
+        CU(c, cudaMemcpyAsync(slot[k].off, off + s0, sizeof(int) * ((size_t)ns + 1), cudaMemcpyHostToDevice, up));
+        if (npad_host) CU(c, cudaMemcpyAsync(slot[k].off + ns + 1, npad_host + s0, sizeof(int) * (size_t)ns, cudaMemcpyHostToDevice, up));
+        if (host_io) {
+            CU(c, cudaMemcpyAsync(slot[k].xyz, xyz + 3 * (size_t)a0, sizeof(float) * 3 * (size_t)na, cudaMemcpyHostToDevice, up));
+            CU(c, cudaMemcpyAsync(slot[k].sp, species + a0, sizeof(int) * (size_t)na, cudaMemcpyHostToDevice, up));
+            CU(c, cudaMemcpyAsync(slot[k].Q, Q + s0, sizeof(float) * (size_t)ns, cudaMemcpyHostToDevice, up));
+        }
+        if (piped) CU(c, cudaEventRecord(c->ev_h2d[k], up));
+        return EPNN_OK;
+    };
+    if (piped) CU(c, cudaStreamWaitEvent(up, c->ev_done[0], 0));      // (events of an earlier call: already complete)
+    if ((rc = upload(0, 0)) != EPNN_OK) return rc;
+    for (size_t ci = 0; ci < n_chunks; ++ci) {
+        const int k = piped ? (int)(ci & 1) : 0;
         const int64_t s0 = bounds[ci], s1 = bounds[ci + 1];
         const int ns = (int)(s1 - s0);
         const int a0 = off[s0], a1 = off[s1];
         const int na = a1 - a0;
-        // offsets (and npad) always come from the host: they drive launch geometry
-        int* d_off; int* d_npad_in = nullptr;
-        if ((rc = ensure(c, B_OFFIN, sizeof(int) * ((size_t)ns + 1) * 2 + 64, &p)) != EPNN_OK) return rc;
-        d_off = (int*)p;
-        CU(c, cudaMemcpyAsync(d_off, off + s0, sizeof(int) * ((size_t)ns + 1), cudaMemcpyHostToDevice, st));
-        if (npad_host) {
-            d_npad_in = d_off + ns + 1;
-            CU(c, cudaMemcpyAsync(d_npad_in, npad_host + s0, sizeof(int) * (size_t)ns, cudaMemcpyHostToDevice, st));
-        }
+        if (!piped && ci > 0 && (rc = upload(ci, 0)) != EPNN_OK) return rc;
+        if (piped) CU(c, cudaStreamWaitEvent(st, c->ev_h2d[k], 0));
+        int* d_off = slot[k].off;
+        int* d_npad_in = npad_host ? d_off + ns + 1 : nullptr;
         const float* d_xyz; const int* d_species; const float* d_Q; float* d_o32 = nullptr; double* d_o64 = nullptr;
         if (host_io) {
-            float* bx; int* bs; float* bq;
-            if ((rc = ensure(c, B_XYZ, sizeof(float) * 3 * (size_t)na, &p)) != EPNN_OK) return rc; bx = (float*)p;
-            if ((rc = ensure(c, B_SPECIES, sizeof(int) * (size_t)na, &p)) != EPNN_OK) return rc; bs = (int*)p;
-            if ((rc = ensure(c, B_Q, sizeof(float) * (size_t)ns, &p)) != EPNN_OK) return rc; bq = (float*)p;
-            CU(c, cudaMemcpyAsync(bx, xyz + 3 * (size_t)a0, sizeof(float) * 3 * (size_t)na, cudaMemcpyHostToDevice, st));
-            CU(c, cudaMemcpyAsync(bs, species + a0, sizeof(int) * (size_t)na, cudaMemcpyHostToDevice, st));
-            CU(c, cudaMemcpyAsync(bq, Q + s0, sizeof(float) * (size_t)ns, cudaMemcpyHostToDevice, st));
-            d_xyz = bx; d_species = bs; d_Q = bq;
-            if (q_out) { if ((rc = ensure(c, B_OUT32, sizeof(float) * (size_t)na, &p)) != EPNN_OK) return rc; d_o32 = (float*)p; }
-            if (q_out64) { if ((rc = ensure(c, B_OUT64, sizeof(double) * (size_t)na, &p)) != EPNN_OK) return rc; d_o64 = (double*)p; }
+            d_xyz = slot[k].xyz; d_species = slot[k].sp; d_Q = slot[k].Q; d_o32 = slot[k].o32; d_o64 = slot[k].o64;
         } else {
             d_xyz = xyz + 3 * (size_t)a0; d_species = species + a0; d_Q = Q + s0;
             d_o32 = q_out ? q_out + a0 : nullptr; d_o64 = q_out64 ? q_out64 + a0 : nullptr;
@@ -791,15 +832,29 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
             rc = run_chunk<double>(c, ns, na, off + s0, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
         else
             rc = run_chunk<float>(c, ns, na, off + s0, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
-        if (rc != EPNN_OK) return rc;
+        if (rc != EPNN_OK) { cudaStreamSynchronize(up); cudaStreamSynchronize(down); return rc; }
+        if (piped) {
+            // run_chunk returned after its one host sync (neighbour count): chunk ci - 1 is complete, the bulk of chunk ci is
+            // queued.  Its results go down on their own stream; the other slot is free for chunk ci + 1 once ITS download is done.
+            CU(c, cudaEventRecord(c->ev_done[k], st));
+            CU(c, cudaStreamWaitEvent(down, c->ev_done[k], 0));
+        }
         if (host_io) {
-            if (q_out) CU(c, cudaMemcpyAsync(q_out + a0, d_o32, sizeof(float) * (size_t)na, cudaMemcpyDeviceToHost, st));
-            if (q_out64) CU(c, cudaMemcpyAsync(q_out64 + a0, d_o64, sizeof(double) * (size_t)na, cudaMemcpyDeviceToHost, st));
-            // the staging buffers are reused by the next chunk: wait for the copies
-            CU(c, cudaStreamSynchronize(st));
+            if (q_out) CU(c, cudaMemcpyAsync(q_out + a0, d_o32, sizeof(float) * (size_t)na, cudaMemcpyDeviceToHost, down));
+            if (q_out64) CU(c, cudaMemcpyAsync(q_out64 + a0, d_o64, sizeof(double) * (size_t)na, cudaMemcpyDeviceToHost, down));
+        }
+        if (piped) {
+            CU(c, cudaEventRecord(c->ev_d2h[k], down));
+            if (ci + 1 < n_chunks) {
+                if (ci >= 1) CU(c, cudaEventSynchronize(c->ev_d2h[k ^ 1]));       // chunk ci - 1 has left slot k ^ 1
+                if ((rc = upload(ci + 1, k ^ 1)) != EPNN_OK) return rc;
+            }
+        } else if (host_io) {
+            CU(c, cudaStreamSynchronize(st));      // the single staging slot is reused by the next chunk
         }
         tm.mark(7);
     }
+    if (piped) { CU(c, cudaStreamSynchronize(up)); CU(c, cudaStreamSynchronize(down)); }
     CU(c, cudaStreamSynchronize(st));
     if (stats) {
         unsigned long long nn[4] = {0, 0, 0, 0};
