@@ -64,8 +64,8 @@ def parse_args():
     ap.add_argument("--precision", type=int, default=32, choices=[0, 32, 48, 64], help="0 auto (probe), 32 FP32, 48 mixed (FP64 per-atom kernel), 64 all FP64")
     ap.add_argument("--chunk-atoms", type=int, default=0, help="override the library's internal batch size")
     ap.add_argument("--ref-molecules", type=int, default=2048, help="molecules per step of the CPU reference arm")
-    ap.add_argument("--gnn-far-tensor", type=int, default=0, choices=[0, 1],
-                    help="big systems: far part of the message sum on tcgen05 tensor cores (3xTF32) instead of FP32 SIMT")
+    ap.add_argument("--gnn-far-tensor", type=int, default=2, choices=[0, 1, 2],
+                    help="big systems: far part of the message sum on tcgen05 tensor cores (3xTF32) instead of FP32 SIMT; 2 = auto (>= 16384 atoms)")
     ap.add_argument("--pair-tensor", type=int, default=0, choices=[0, 1],
                     help="small systems: electron-passing pair MLP on mma.sync 3xTF32 instead of FP32 SIMT (opt-in)")
     ap.add_argument("--pair-const", type=int, default=2, choices=[0, 1, 2],
@@ -363,8 +363,7 @@ def make_engine(box, args, ckpt, precision=None, timing=True):
         eng.set_option("timing", 1)
     if args.chunk_atoms:
         eng.set_option("chunk_atoms", args.chunk_atoms)
-    if args.gnn_far_tensor:
-        eng.set_option("gnn_far_tensor", 1)
+    eng.set_option("gnn_far_tensor", args.gnn_far_tensor)
     if not args.dedup_far:
         eng.set_option("dedup_far", 0)
     if args.pair_tensor:
@@ -647,7 +646,7 @@ def run_b200(args):
             if dd_rows > 0:          # the algorithmic count is meaningless once rows collapse: quote what really ran
                 roofline.update({"achieved": executed, "frac": executed / fp32_peak if fp32_peak else None,
                                  "achieved_is": "EXECUTED FLOPs (near pairs + species slots + column-by-column far rows) / CUDA-event time"})
-        if args.gnn_far_tensor and args.workload == "protein":
+        if (args.gnn_far_tensor == 1 or (args.gnn_far_tensor == 2 and n_atoms >= 16384)) and args.precision != 64 and args.workload == "protein":
             # the O(n^2) far part runs on tcgen05 (3xTF32): executed tensor FLOPs = 3 x (2*32*32) per far ordered pair per step
             far_pair_steps = (row_steps - dd_rows) * max(n_atoms - nnz / n_atoms, 0.0)
             tf32_exec = 3.0 * 2 * 32 * 32 * far_pair_steps / (ms_gnn * 1e-3) * 1e-12 / (world if sharded_system else 1)

@@ -70,7 +70,8 @@ struct epnn_ctx {
     int auto_choice = 0;         // precision chosen by the probe (0 = not probed yet)
     double auto_tol = 2.5e-6;    // a cheaper precision is accepted if its probe charges are within this of the FP64 kernels
     double probe_err32 = -1, probe_err48 = -1;
-    int far_tensor = 0;          // option "gnn_far_tensor"
+    int far_tensor = 2;          // option "gnn_far_tensor": 0 off, 1 on, 2 auto (on when a system of the chunk has >= far_tensor_min atoms)
+    int far_tensor_min = 16384;  // option "gnn_far_tensor_min"
     int dedup_far = 1;           // option "dedup_far": collapse species-equivalent far columns (exact)
     int pair_tensor = 0;         // option "pair_tensor": EPN bundle kernel on mma.sync 3xTF32 (precision 32 only)
     int pair_const = 2;          // option "pair_const": FP32 kernel set (0 warp-tile, 1 pair-per-thread everywhere, 2 default mix; see epnn_internal.cuh)
@@ -263,7 +264,13 @@ extern "C" int epnn_set_option(epnn_ctx* c, const char* key, double value) {
         c->auto_tol = value; c->auto_choice = 0;
     } else if (k == "timing") c->timing = value != 0;
     else if (k == "keep_hidden") c->keep_hidden = value != 0;
-    else if (k == "gnn_far_tensor") c->far_tensor = value != 0;
+    else if (k == "gnn_far_tensor") {
+        if (value != 0 && value != 1 && value != 2) return fail(c, EPNN_E_INVALID, "gnn_far_tensor must be 0 (off), 1 (on) or 2 (auto)");
+        c->far_tensor = (int)value;
+    } else if (k == "gnn_far_tensor_min") {
+        if (value < SMALL_MAX + 1) return fail(c, EPNN_E_INVALID, "gnn_far_tensor_min must exceed %d", SMALL_MAX);
+        c->far_tensor_min = (int)value;
+    }
     else if (k == "dedup_far") c->dedup_far = value != 0;
     else if (k == "pair_tensor") c->pair_tensor = value != 0;
     else if (k == "pair_const") {
@@ -506,7 +513,10 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
         w.rg_begin = gb < 0 ? 0 : gb; w.rg_end = gb < 0 ? 0 : ge;
     }
     if (w.n_rg_large > 0) {
-        if (c->far_tensor && sizeof(R) == 4) {       // tensor-core far kernel: CTA units = row group x column range
+        int max_n = 0;
+        for (int s = 0; s < n_sys; ++s) max_n = std::max(max_n, h_off[s + 1] - h_off[s]);
+        const bool use_tc = c->far_tensor == 1 || (c->far_tensor == 2 && max_n >= c->far_tensor_min);
+        if (use_tc && sizeof(R) == 4) {              // tensor-core far kernel: CTA units = row group x column range
             int ns = div_up((int64_t)c->sm_count * 8, w.n_rg_large);
             ns = ns < 1 ? 1 : (ns > 15 ? 15 : ns);
             w.far_tc = 1;

@@ -153,6 +153,11 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
         __syncwarp();
         if (!do_upd && !do_proj) continue;
         if (a.scope && !__any_sync(0xffffffffu, slot_ns[lane] > 0)) continue;      // nothing of this tile belongs to the launch
+        unsigned okm = 0u;                                                         // bit s: slot pg * 8 + s belongs to the launch
+        {
+            const int4 n0 = *reinterpret_cast<const int4*>(slot_ns + pg * 8), n1 = *reinterpret_cast<const int4*>(slot_ns + pg * 8 + 4);
+            okm = (n0.x > 0) | (n0.y > 0) << 1 | (n0.z > 0) << 2 | (n0.w > 0) << 3 | (n1.x > 0) << 4 | (n1.y > 0) << 5 | (n1.z > 0) << 6 | (n1.w > 0) << 7;
+        }
 
         if (do_upd) {
             // (1) [l2_prev | S] tile: l2 of the previous step (zeros at the first step: h = 0), S = partial planes summed in fixed order
@@ -196,7 +201,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
                 for (int s = 0; s < 8; ++s) {
                     Vec4<R> z; z.x = relu(acc[s][0] + cv.x); z.y = relu(acc[s][1] + cv.y); z.z = relu(acc[s][2] + cv.z); z.w = relu(acc[s][3] + cv.w);
                     const int at = base + pg * 8 + s;
-                    if (slot_ns[pg * 8 + s] > 0) stv(a.l2 + (int64_t)at * HID + og * 4, z);
+                    if ((okm >> s) & 1u) stv(a.l2 + (int64_t)at * HID + og * 4, z);
                     stv(T32b + tile_off(pg * 8 + s, og, HID), z);
                 }
             }
@@ -211,7 +216,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
                     for (int s = 0; s < 8; ++s) {
                         Vec4<R> hv; hv.x = acc[s][0] + cv.x; hv.y = acc[s][1] + cv.y; hv.z = acc[s][2] + cv.z; hv.w = acc[s][3] + cv.w;
                         const int at = base + pg * 8 + s;
-                        if (slot_ns[pg * 8 + s] > 0) stv(a.h + (int64_t)at * HD + og * 4, hv);
+                        if ((okm >> s) & 1u) stv(a.h + (int64_t)at * HD + og * 4, hv);
                     }
                 }
                 zero_acc(acc);
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
                     for (int s = 0; s < 8; ++s) {
                         Vec4<R> hv; hv.x = acc[s][0] + cv.x; hv.y = acc[s][1] + cv.y; hv.z = acc[s][2] + cv.z; hv.w = acc[s][3] + cv.w;
                         const int at = base + pg * 8 + s;
-                        if (slot_ns[pg * 8 + s] > 0) stv(a.h + (int64_t)at * HD + HID + og * 4, hv);
+                        if ((okm >> s) & 1u) stv(a.h + (int64_t)at * HD + HID + og * 4, hv);
                     }
                 }
             }
@@ -248,7 +253,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
 #pragma unroll
                 for (int s = 0; s < 8; ++s) {
                     const int at = base + pg * 8 + s;
-                    if (slot_ns[pg * 8 + s] > 0) {
+                    if ((okm >> s) & 1u) {
                         const Vec4<R> ax = ldv(sAx + slot_sp[pg * 8 + s] * 64 + half * HID + og * 4);
                         const R qv = slot_q[pg * 8 + s];
                         Vec4<R> o;

@@ -96,17 +96,20 @@ const char* epnn_last_error(const epnn_ctx* ctx);
  * species: an exact reuse of identical messages, checked on the device at every step, switched off only for
  * ablation.  For systems with more than 48 atoms this turns the O(n^2) unmasked message sum of a step into
  * O(n * species) whenever the check holds; otherwise the full sum runs;
- * "gnn_far_tensor" 0 (default) / 1: systems with more than 48 atoms evaluate the e == 0 ("far") part of the
- * message sum -- the O(n^2) part -- on the tcgen05 tensor cores with a 3xTF32 error-compensated split and FP32
- * accumulation in tensor memory instead of FP32 SIMT (precision 32 only; results differ from the SIMT path at
- * the level of FP32 round-off, about 1e-6 relative in the hidden state);
+ * "gnn_far_tensor" 2 (default: auto) / 1 (on) / 0 (off): systems with more than 48 atoms evaluate the e == 0 ("far") part of
+ * the message sum -- the O(n^2) part -- on the tcgen05 tensor cores with a 3xTF32 error-compensated split and FP32
+ * accumulation in tensor memory instead of FP32 SIMT (FP32 / mixed precision only; results differ from the SIMT path at
+ * the level of FP32 round-off, about 1e-6 relative in the hidden state).  Auto switches it on for calls that hold a
+ * system of at least "gnn_far_tensor_min" atoms (default 16384), where the O(n^2) part is > 99 % of the work and the
+ * tensor kernel is 1.5x the FP32 SIMT one;
  * "pair_tensor" 0 (default) / 1: systems with at most 48 atoms evaluate the electron-passing pair MLP on the warp-level
  * tensor path (mma.sync m16n8k8 TF32 inputs, 3xTF32 split, FP32 accumulation, operands chained through registers)
  * instead of FP32 SIMT (precision 32 only; per-pair transfers differ from the SIMT path by about 1e-6 relative);
- * "pair_const" 0 (default) / 1: EXPERIMENTAL, not yet validated on a GPU (see epnn_bundle_const.cu): plain-FP32
- * variant of both small-system pair kernels (one thread owns one pair), of the per-atom kernel (one thread owns one
- * atom) and of the far part of the big-system message sum (one thread owns one row) in which the weights are uniform
- * operands passed as kernel parameters (precision 32 only). */
+ * "pair_const": the FP32 kernel set.  2 (default): row-run GNN bundle kernel (epnn_bundle_run.cu: one contiguous run of
+ * pair slots per lane, row sums in registers) + pair-per-thread EPN bundle kernel + row-per-thread far kernel for large
+ * systems, all with the weights as uniform FFMA2 operands (kernel parameters); 1: pair-per-thread kernels everywhere
+ * (incl. the per-atom kernel; slower, kept for A/B); 0: the round-1 warp-tile kernels (shared-memory operands).  All three
+ * evaluate the same formulas in plain FP32; only the -- fixed -- order of the additions differs. */
 int epnn_set_option(epnn_ctx* ctx, const char* key, double value);
 
 /* Charge inference for a packed batch of systems, host buffers.
