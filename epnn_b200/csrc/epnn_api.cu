@@ -72,6 +72,7 @@ struct epnn_ctx {
     double probe_err32 = -1, probe_err48 = -1;
     int far_tensor = 2;          // option "gnn_far_tensor": 0 off, 1 on, 2 auto (on when a system of the chunk has >= far_tensor_min atoms)
     int far_tensor_min = 16384;  // option "gnn_far_tensor_min"
+    int far_tc_impl = 1;         // option "gnn_far_tensor_impl": 1 round-1 kernel (epnn_gnn_tc.cu), 2 warp-specialised (epnn_gnn_tc2.cu)
     int dedup_far = 1;           // option "dedup_far": collapse species-equivalent far columns (exact)
     int pair_tensor = 0;         // option "pair_tensor": EPN bundle kernel on mma.sync 3xTF32 (precision 32 only)
     int pair_const = 2;          // option "pair_const": FP32 kernel set (0 warp-tile, 1 pair-per-thread everywhere, 2 default mix; see epnn_internal.cuh)
@@ -267,6 +268,9 @@ extern "C" int epnn_set_option(epnn_ctx* c, const char* key, double value) {
     else if (k == "gnn_far_tensor") {
         if (value != 0 && value != 1 && value != 2) return fail(c, EPNN_E_INVALID, "gnn_far_tensor must be 0 (off), 1 (on) or 2 (auto)");
         c->far_tensor = (int)value;
+    } else if (k == "gnn_far_tensor_impl") {
+        if (value != 1 && value != 2) return fail(c, EPNN_E_INVALID, "gnn_far_tensor_impl must be 1 or 2");
+        c->far_tc_impl = (int)value;
     } else if (k == "gnn_far_tensor_min") {
         if (value < SMALL_MAX + 1) return fail(c, EPNN_E_INVALID, "gnn_far_tensor_min must exceed %d", SMALL_MAX);
         c->far_tensor_min = (int)value;
@@ -647,9 +651,14 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
         CU(c, launch_gnn_bundle<R>(w, msg[t], st, n_launch));
         w.stamp = w.sp_tab ? t + 1 : 0;             // large systems: are this step's v rows equal species by species?
         CU(c, launch_sp_check<R>(w, st, n_launch));
-        if (w.far_tc == 1)
-            CU(c, launch_gnn_far_tc(w, c->w2split + (size_t)t * 2048, c->w2split + (size_t)t * 2048 + 1024, (const float*)msg[t].b2,
-                                    w.nsplit - 1, st, n_launch));
+        if (w.far_tc == 1) {
+            if (c->far_tc_impl == 2)
+                CU(c, launch_gnn_far_tc2(w, c->w2split + (size_t)t * 2048, c->w2split + (size_t)t * 2048 + 1024, (const float*)msg[t].b2,
+                                         w.nsplit - 1, st, n_launch));
+            else
+                CU(c, launch_gnn_far_tc(w, c->w2split + (size_t)t * 2048, c->w2split + (size_t)t * 2048 + 1024, (const float*)msg[t].b2,
+                                        w.nsplit - 1, st, n_launch));
+        }
         if constexpr (sizeof(R) == 4) {
             if (w.far_tc == 2) CU(c, launch_gnn_far_const(w, msg[t], w.nsplit - 1, st, n_launch));
         }

@@ -300,6 +300,8 @@ cudaError_t launch_csr_rowl(const Workspace& w, const int* atom_b0, cudaStream_t
 cudaError_t launch_gnn_far_const(const Workspace& w, const StepW<float>& sw, int nsplit_far, cudaStream_t st, int* n_launch);   // option pair_const
 cudaError_t launch_gnn_far_tc(const Workspace& w, const float* Whi, const float* Wlo, const float* b2, int nsplit_tc,
                               cudaStream_t st, int* n_launch);
+cudaError_t launch_gnn_far_tc2(const Workspace& w, const float* Whi, const float* Wlo, const float* b2, int nsplit_tc,
+                               cudaStream_t st, int* n_launch);      // warp-specialised variant (epnn_gnn_tc2.cu)
 template <typename R> cudaError_t launch_gnn_pair(const Workspace& w, const StepW<R>& sw, cudaStream_t st, int* n_launch);
 cudaError_t launch_sp_tab_build(const Workspace& w, cudaStream_t st, int* n_launch);                    // once per chunk
 template <typename R> cudaError_t launch_sp_check(const Workspace& w, cudaStream_t st, int* n_launch);  // once per step (needs w.stamp)

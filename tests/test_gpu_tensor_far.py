@@ -9,16 +9,18 @@ from oracle import epnn_oracle as O
 pytestmark = pytest.mark.gpu
 
 
-def _engine(weights, name):
+def _engine(weights, name, impl=1):
     from epnn_b200.engine import Engine
     eng = Engine(weights[name], device=0)
     eng.set_option("gnn_far_tensor", 1)
+    eng.set_option("gnn_far_tensor_impl", impl)      # 1: round-1 kernel (epnn_gnn_tc.cu), 2: warp-specialised pipeline (epnn_gnn_tc2.cu)
     eng.set_option("keep_hidden", 1)
     return eng
 
 
-def test_protein_golden_with_tensor_far(weights, protein):
-    eng = _engine(weights, "decay_model_weights")
+@pytest.mark.parametrize("impl", [1, 2])
+def test_protein_golden_with_tensor_far(weights, protein, impl):
+    eng = _engine(weights, "decay_model_weights", impl)
     n = len(protein["Z"])
     offs = np.array([0, n], np.int32)
     sp = O.species_from_Z(protein["Z"], 9)
@@ -28,15 +30,16 @@ def test_protein_golden_with_tensor_far(weights, protein):
     eng.close()
 
 
+@pytest.mark.parametrize("impl", [1, 2])
 @pytest.mark.parametrize("name,rtol_q,rtol_h", [("model2_weights", 2e-4, 2e-5), ("model_weights", 2e-2, 2e-5)])
-def test_live_gnn_tensor_far_vs_oracle_and_simt(weights, protein, engines, name, rtol_q, rtol_h):
+def test_live_gnn_tensor_far_vs_oracle_and_simt(weights, protein, engines, name, rtol_q, rtol_h, impl):
     w = weights[name]
     n = 700
     xyz = protein["xyz"][:n]
     sp = O.species_from_Z(protein["Z"][:n], w.n_x)
     offs = np.array([0, n], np.int32)
     Q = np.array([1.0], np.float32)
-    eng = _engine(weights, name)
+    eng = _engine(weights, name, impl)
     simt = engines(name)
     for npad in (None, 730):
         q64 = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
