@@ -344,6 +344,7 @@ __global__ void active_mark_kernel(int n_atoms, int row_lo, int row_hi, const in
 
 struct Timer {
     bool on; cudaStream_t st; std::vector<cudaEvent_t> ev; std::vector<int> tag;
+    ~Timer() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }      // early returns (errors) must not leak the events
     void mark(int t) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); tag.push_back(t); }
     void finish(epnn_stats* s) {
         if (!on) return;

@@ -141,6 +141,14 @@ extern "C" int epnn_xyz_load(const char* const* paths, int64_t n_files, int n_x,
     work();
     for (auto& th : pool) th.join();
     b->offsets.assign((size_t)n_files + 1, 0);
+    int64_t total = 0;                                   // the packed offsets are int32 (the C-ABI of epnn_infer_batch): refuse to wrap
+    for (int64_t i = 0; i < n_files; ++i) total += (int64_t)files[(size_t)i].species.size();
+    if (total > 0x7fffffffLL) {
+        b->error = 2; b->error_file = -1;
+        b->message = "more than 2^31 - 1 atoms in one batch (" + std::to_string(total) + "); load the directory in several batches";
+        *out = b;
+        return EPNN_E_UNSUPPORTED;
+    }
     for (int64_t i = 0; i < n_files; ++i) {
         const ParsedFile& pf = files[(size_t)i];
         if (pf.error && !b->error) {
