@@ -59,7 +59,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 #define ATOM_W_PROJ (HID * 64 + 64 + MAX_SPECIES * 64)                                      // 3136
 #define ATOM_TILE (32 * 64 + 32 * HID)                                                      // 3072 per warp
 
-template <typename R, int NW, typename IO>
+// SCOPED = false: every atom (unsharded calls; the scope fields of AtomArgs are ignored and cost nothing).
+template <typename R, int NW, typename IO, bool SCOPED>
 __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) {
 #ifdef EPNN_CPU_EMU
     unsigned char* smem_raw = reinterpret_cast<unsigned char*>(emu_smem);
@@ -128,7 +129,7 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
             if (me_ok) {
                 sys = a.atom_sys[me];
                 nat = a.sys_off[sys + 1] - a.sys_off[sys];
-                if (a.scope && nat > SMALL_MAX) in = a.scope == 1 ? (me >= a.row_lo && me < a.row_hi) : a.active[me] != 0;
+                if (SCOPED && a.scope && nat > SMALL_MAX) in = a.scope == 1 ? (me >= a.row_lo && me < a.row_hi) : a.active[me] != 0;
             }
             if (in) {
                 sp = a.species[me];
@@ -152,9 +153,12 @@ __global__ void __launch_bounds__(NW * 32) atom_kernel(const AtomArgs<R, IO> a) 
         }
         __syncwarp();
         if (!do_upd && !do_proj) continue;
-        if (a.scope && !__any_sync(0xffffffffu, slot_ns[lane] > 0)) continue;      // nothing of this tile belongs to the launch
+        if (SCOPED && a.scope && !__any_sync(0xffffffffu, slot_ns[lane] > 0)) continue;      // nothing of this tile belongs to the launch
         unsigned okm = 0u;                                                         // bit s: slot pg * 8 + s belongs to the launch
-        {
+        if (!SCOPED) {
+            const int left = a.n_atoms - (base + pg * 8);
+            okm = left >= 8 ? 0xFFu : (left > 0 ? (1u << left) - 1u : 0u);
+        } else {
             const int4 n0 = *reinterpret_cast<const int4*>(slot_ns + pg * 8), n1 = *reinterpret_cast<const int4*>(slot_ns + pg * 8 + 4);
             okm = (n0.x > 0) | (n0.y > 0) << 1 | (n0.z > 0) << 2 | (n0.w > 0) << 3 | (n1.x > 0) << 4 | (n1.y > 0) << 5 | (n1.z > 0) << 6 | (n1.w > 0) << 7;
         }
@@ -288,11 +292,12 @@ cudaError_t launch_atom_io(const Workspace& w, int mode, const StepW<R>* prev, c
     aa.u = (IO*)w.u; aa.v = (IO*)w.v; aa.q_out = q_out; aa.q_out64 = q_out64;
     aa.scope = scope; aa.row_lo = w.row_lo; aa.row_hi = w.row_hi; aa.active = w.active;
     const size_t smem = sizeof(R) * (ATOM_W_UPD + ATOM_W_PROJ + (size_t)NW * ATOM_TILE + NW * 64) + sizeof(int) * NW * 64;
-    cudaError_t e = cudaFuncSetAttribute(atom_kernel<R, NW, IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(scope ? atom_kernel<R, NW, IO, true> : atom_kernel<R, NW, IO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int grid = div_up(div_up(w.n_atoms, 32), NW);
     if (grid > w.sm_count) grid = w.sm_count;
-    atom_kernel<R, NW, IO><<<grid, NW * 32, smem, st>>>(aa);
+    if (scope) atom_kernel<R, NW, IO, true><<<grid, NW * 32, smem, st>>>(aa);
+    else atom_kernel<R, NW, IO, false><<<grid, NW * 32, smem, st>>>(aa);
     ++*nl;
     return cudaGetLastError();
 }

@@ -24,7 +24,7 @@ extern "C" int emu_atom_kernel(int mode, int h_is_zero, int n_atoms, int nsplit,
     aa.u = u; aa.v = v; aa.q_out = q_out; aa.q_out64 = q_out64;
     constexpr int NW = 4;
     const size_t smem = sizeof(float) * (ATOM_W_UPD + ATOM_W_PROJ + (size_t)NW * ATOM_TILE + NW * 64) + sizeof(int) * NW * 64;
-    emu_launch_grid(2, NW, smem / sizeof(float) + 8, [&] { atom_kernel<float, NW, float>(aa); });
+    emu_launch_grid(2, NW, smem / sizeof(float) + 8, [&] { atom_kernel<float, NW, float, false>(aa); });
     return 0;
 }
 

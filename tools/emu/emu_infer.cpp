@@ -191,7 +191,7 @@ extern "C" int emu_infer(int T, int n_x, const float* w_packed, size_t n_w, int 
         aa.u = u.data(); aa.v = v.data(); aa.q_out = q_out; aa.q_out64 = q_out64;
         constexpr int ANW = 4;
         const size_t smem = sizeof(float) * (ATOM_W_UPD + ATOM_W_PROJ + (size_t)ANW * ATOM_TILE + ANW * 64) + sizeof(int) * ANW * 64;
-        emu_launch_grid(2, ANW, smem / sizeof(float) + 8, [&] { k_atom::atom_kernel<float, ANW, float>(aa); });
+        emu_launch_grid(2, ANW, smem / sizeof(float) + 8, [&] { k_atom::atom_kernel<float, ANW, float, false>(aa); });
     };
     auto bundle = [&](bool epn, const StepW<float>& sw) {
         if (!n_bundles) return;
