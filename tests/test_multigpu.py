@@ -69,6 +69,16 @@ def _worker(rank, world, port, tmp):
             tc2 = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
             assert np.array_equal(tc1, tc2), (name, "tensor", np.abs(tc1 - tc2).max())
             eng.close()
+        # the all-FP64 kernels and the mixed precision shard the same way; several chunks per call (the staging pipeline) too
+        w = load_weights(os.path.join(root, "tests", "golden", "checkpoints", "model2_weights"))
+        for precision in (64, 48):
+            eng = Engine(w, device=rank, precision=precision)
+            eng.set_option("chunk_atoms", 3000)              # 3 chunks: small systems | protein | 700-atom system
+            single = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
+            eng.set_shard(rank, world)
+            sharded = eng.infer_batch(offs, xyz, sp, Q, npad, want_f64=True)[1].copy()
+            assert np.array_equal(single, sharded), (precision, np.abs(single - sharded).max())
+            eng.close()
         open(os.path.join(tmp, f"ok{rank}"), "w").write("ok")
     finally:
         dist.destroy_process_group()
