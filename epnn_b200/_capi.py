@@ -57,6 +57,7 @@ SIGNATURES = {
     "epnn_shard_slice": (C.c_int, [C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "epnn_shard_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "epnn_get_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "epnn_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "epnn_measure_fp32_peak": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double)]),
     "epnn_xyz_load": (C.c_int, [C.POINTER(C.c_char_p), C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "epnn_xyz_parse_text": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),

@@ -61,7 +61,8 @@ static inline int64_t shard_slice_rows(int64_t n, int world) { const int64_t s =
 
 struct epnn_ctx {
     int device = 0, T = 0, n_x = 0, n_species = 0, sm_count = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;           // the stream every kernel / copy of the ctx is enqueued on (own_stream, or the caller's: epnn_set_stream)
+    cudaStream_t own_stream = nullptr;
     // host-buffer calls: chunk k + 1 is uploaded and chunk k - 1 downloaded while chunk k computes (two staging slots)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -183,7 +184,8 @@ extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_
     } while (0)
     CUC(cudaSetDevice(device));
     CUC(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     CUC(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     for (int k = 0; k < 2; ++k) {
@@ -248,7 +250,7 @@ extern "C" void epnn_destroy(epnn_ctx* c) {
     }
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -1094,6 +1096,14 @@ extern "C" int epnn_shard_stats(epnn_ctx* c, int64_t* calls, int64_t* bytes) {
     if (!c) return EPNN_E_INVALID;
     if (calls) *calls = c->xchg_calls;
     if (bytes) *bytes = c->xchg_bytes;
+    return EPNN_OK;
+}
+
+extern "C" int epnn_set_stream(epnn_ctx* c, void* stream) {
+    if (!c) return EPNN_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaStreamSynchronize(c->stream));          // nothing of the ctx is in flight on the old stream when it switches
+    c->stream = stream ? (cudaStream_t)stream : c->own_stream;
     return EPNN_OK;
 }
 

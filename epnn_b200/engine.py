@@ -61,6 +61,11 @@ class Engine:
         self._check(self.lib.epnn_get_stream(self._h, C.byref(p)))
         return p.value or 0
 
+    def set_stream(self, handle: int = 0):
+        """Enqueue on the caller's CUDA stream (integer cudaStream_t, e.g. ``torch.cuda.current_stream().cuda_stream``);
+        0 restores the ctx's own stream (epnn_set_stream)."""
+        self._check(self.lib.epnn_set_stream(self._h, C.c_void_p(handle or None)))
+
     def set_shard(self, rank: int, world: int, group=None):
         """Shard the large systems of every following call over ``world`` ranks (epnn_shard_init; collective).  The NCCL
         unique id is made on rank 0 and broadcast through ``torch.distributed`` (any backend); the data-path exchanges

@@ -216,6 +216,12 @@ int epnn_shard_stats(epnn_ctx* ctx, int64_t* calls, int64_t* bytes);
  * that a caller can record its own CUDA events around a sequence of calls (bench.py does). */
 int epnn_get_stream(epnn_ctx* ctx, void** stream_out);
 
+/* Make the ctx enqueue on the CALLER's stream (a cudaStream_t passed as void*; must belong to the ctx's device and outlive
+ * its use) -- what the `_dev` entry points need to be ordered after the producer of their inputs without a host sync.
+ * NULL restores the ctx's own stream.  The call synchronises the stream in use before switching.  (The legacy default
+ * stream, handle 0, cannot be selected: NULL means "own stream".) */
+int epnn_set_stream(epnn_ctx* ctx, void* stream);
+
 /* FP32 FMA micro-benchmark on the ctx device: the measured SIMT peak (TFLOP/s, 2 flops per FMA, best of
  * `repeats` launches timed with CUDA events) that the pair-MLP kernels' roofline fraction is quoted against
  * (MEASURED_PEAKS.json only holds HBM and tensor peaks). */

@@ -282,6 +282,34 @@ def test_chunking_is_invisible(engines, weights, mixed):
     assert np.array_equal(a, b)
 
 
+def test_caller_stream_and_device_pointers(weights, mixed):
+    """epnn_set_stream + epnn_infer_batch_dev: the library runs on the caller's stream, ordered after the kernels that
+    produce its inputs there, and leaves its outputs in HBM -- same charges as the host-buffer call."""
+    import torch
+    from epnn_b200.engine import Engine
+    w = weights["decay_model_weights"]
+    idx = mixed.usable(w.n_x)[:600:3].tolist()
+    offs, xyz, sp, Q = mixed.batch(idx, w.n_x)
+    eng = Engine(w, device=0)
+    try:
+        ref = eng.infer_batch(offs, xyz, sp, Q, 41)
+        own = eng.stream
+        st = torch.cuda.Stream()
+        eng.set_stream(st.cuda_stream)
+        assert eng.stream == st.cuda_stream
+        with torch.cuda.stream(st):
+            d_xyz = (torch.from_numpy(xyz).cuda() * 2.0) * 0.5          # produced on the caller's stream, not synchronised
+            d_sp, d_Q = torch.from_numpy(sp).cuda(), torch.from_numpy(Q).cuda()
+            d_out = torch.empty(int(offs[-1]), dtype=torch.float32, device="cuda")
+            eng.infer_batch_dev(offs, d_xyz.data_ptr(), d_sp.data_ptr(), d_Q.data_ptr(), np.full(len(idx), 41, np.int32), d_out.data_ptr())
+        assert np.array_equal(d_out.cpu().numpy(), ref)
+        eng.set_stream(0)
+        assert eng.stream == own
+        assert np.array_equal(eng.infer_batch(offs, xyz, sp, Q, 41), ref)
+    finally:
+        eng.close()
+
+
 def test_edge_cases(engines, weights):
     w = weights["decay_model_weights"]
     eng = engines("decay_model_weights", 64)
