@@ -28,7 +28,7 @@
 #ifndef RUN_UNROLL
 #define RUN_UNROLL 1
 #endif
-constexpr int kRunUnroll = RUN_UNROLL;     // unroll factor of the slot loop (2: ptxas then rotates 8 uniform quads instead of 2)
+constexpr int kRunUnroll = RUN_UNROLL;     // unroll factor of the slot loop (2 makes ptxas rotate 8 uniform quads instead of 2, but spills 4 KB: stays 1)
 #ifndef RUN_CTAS
 #define RUN_CTAS 2                      // CTAs per SM (16 warps per SM: 128 registers per thread)
 #endif
@@ -259,11 +259,7 @@ __global__ void __launch_bounds__(RUN_NW * 32, RUN_CTAS) bundle_run_kernel(const
                     }
                 }
                 float z[HID];
-#ifdef ABL_SKIP_STAGE1
-                if (false) {
-#else
-                if (near) {                                          // z = u + C^T c
-#endif
+                if (near) {                                          // z = u + C^T c  (c = descriptor coefficients of the pair)
                     r2_t t2[HID / 2];
 #pragma unroll
                     for (int o = 0; o < HID / 2; ++o) t2[o] = rpack2(uu[2 * o], uu[2 * o + 1]);
@@ -286,11 +282,7 @@ __global__ void __launch_bounds__(RUN_NW * 32, RUN_CTAS) bundle_run_kernel(const
 #pragma unroll
                     for (int c = 0; c < HID; ++c) z[c] = uu[c];
                 }
-#ifdef ABL_NO_VCONFLICT
-                const float* vrow = vS + (lane & 7) * VST;
-#else
                 const float* vrow = vS + lj * VST;
-#endif
 #pragma unroll
                 for (int c = 0; c < HID / 4; ++c) {
                     const float4 x = *reinterpret_cast<const float4*>(vrow + 4 * c);
