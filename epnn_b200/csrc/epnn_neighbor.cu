@@ -162,13 +162,30 @@ cudaError_t launch_cell_build(const Workspace& w, const CellWork& cw, int* scant
 // Neighbour search: one thread per atom row, two passes (count, fill).  Systems with n <= CELL_MIN scan their own
 // atoms (columns come out ascending because j is scanned ascending); bigger systems walk the 27 cells around the
 // atom and sort the row afterwards, so both paths emit identical, ascending, bit-exact lists.
+#define NBR_BLOCK 128
+#define NBR_STAGE 1280                      // atoms whose coordinates fit the staging buffer (15 KB)
 template <bool FILL>
-__global__ void nbr_kernel(int n_atoms, const int* __restrict__ atom_sys, const int* __restrict__ sys_off,
+__global__ void __launch_bounds__(NBR_BLOCK) nbr_kernel(int n_atoms, const int* __restrict__ atom_sys, const int* __restrict__ sys_off,
                            const float* __restrict__ xyz, int* __restrict__ deg, int* __restrict__ degU,
                            const int* __restrict__ rowptr, const int* __restrict__ ustart, int* __restrict__ col,
                            int* __restrict__ pair_i, int* __restrict__ pair_j, double* __restrict__ pair_D,
                            const CellGrid* __restrict__ grid, const int* __restrict__ cell_start,
                            const int* __restrict__ cell_atoms, double* __restrict__ Dtmp, int row_lo, int row_hi) {
+    // Coordinates of the block's systems, staged once in shared memory with coalesced loads (the AoS float3 array is read as
+    // a flat run of floats): the block's atoms are consecutive, so the systems they belong to cover one contiguous range of
+    // atoms -- at most NBR_BLOCK + 2 * 511 of them unless a cell-list system (n > CELL_MIN) is involved, in which case that
+    // system's rows read global memory through the cell list as before.
+    __shared__ float sxyz[3 * NBR_STAGE];
+    const int i_first = blockIdx.x * blockDim.x;
+    const int i_last = min(n_atoms, i_first + (int)blockDim.x) - 1;
+    const int st_lo = sys_off[atom_sys[i_first]];
+    const int st_hi = sys_off[atom_sys[i_last] + 1];
+    const bool staged = st_hi - st_lo <= NBR_STAGE;
+    if (staged) {
+        const float* src = xyz + 3 * (int64_t)st_lo;
+        for (int f = threadIdx.x; f < 3 * (st_hi - st_lo); f += blockDim.x) sxyz[f] = src[f];
+    }
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_atoms) return;
     const int s = atom_sys[i];
@@ -184,9 +201,10 @@ __global__ void nbr_kernel(int n_atoms, const int* __restrict__ atom_sys, const 
     int wp = 0, wu = 0;
     if (FILL) { wp = rowptr[i]; wu = ustart[i]; }
     if (a1 - a0 <= CELL_MIN) {
+        const float* cx = staged ? sxyz - 3 * (int64_t)st_lo : xyz;      // same values either way: the lists cannot differ
         for (int j = a0; j < a1; ++j) {
             if (j == i) continue;
-            const float xj = xyz[3 * j], yj = xyz[3 * j + 1], zj = xyz[3 * j + 2];
+            const float xj = cx[3 * j], yj = cx[3 * j + 1], zj = cx[3 * j + 2];
             if (far_reject(xi, yi, zi, xj, yj, zj)) continue;
             const double D = dist64(xi, yi, zi, xj, yj, zj);
             if (D < 3.0) {
@@ -247,7 +265,7 @@ __global__ void nbr_kernel(int n_atoms, const int* __restrict__ atom_sys, const 
 #ifndef EPNN_CPU_EMU
 cudaError_t launch_nbr_count(const Workspace& w, const CellWork& cw, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0) return cudaSuccess;
-    nbr_kernel<false><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, w.deg, w.degU,
+    nbr_kernel<false><<<div_up(w.n_atoms, NBR_BLOCK), NBR_BLOCK, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, w.deg, w.degU,
                                                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                                               cw.grid, cw.cell_start, cw.cell_atoms, nullptr, w.row_lo, w.row_hi);
     ++*nl;
@@ -359,7 +377,7 @@ __global__ void __launch_bounds__(EDGE_PAIRS) edge_desc_kernel(int64_t P, const 
 #ifndef EPNN_CPU_EMU
 cudaError_t launch_nbr_fill(const Workspace& w, const CellWork& cw, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0) return cudaSuccess;
-    nbr_kernel<true><<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, nullptr, nullptr,
+    nbr_kernel<true><<<div_up(w.n_atoms, NBR_BLOCK), NBR_BLOCK, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.xyz, nullptr, nullptr,
                                                              w.rowptr, w.ustart, w.col, w.pair_i, w.pair_j, w.pair_D,
                                                              cw.grid, cw.cell_start, cw.cell_atoms, cw.Dtmp, w.row_lo, w.row_hi);
     ++*nl;

@@ -83,7 +83,7 @@ extern "C" int emu_infer(int T, int n_x, const float* w_packed, size_t n_w, int 
         std::fill(cnt.begin(), cnt.end(), 0);
         emu_launch_simple(div_up(n, 256), 256, [&] { k_nbr::cell_bin_kernel<1>(n, atom_sys.data(), off, xyz, grid.data(), cnt.data(), cell_start.data(), cell_atoms.data()); });
     }
-    emu_launch_simple(div_up(n, 128), 128, [&] {
+    emu_launch_grid(div_up(n, 128), 4, 0, [&] {
         k_nbr::nbr_kernel<false>(n, atom_sys.data(), off, xyz, deg.data(), degU.data(), nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                  grid.data(), cell_start.data(), cell_atoms.data(), nullptr, 0, n); });
     exclusive_scan(deg.data(), rowptr.data(), n);
@@ -93,7 +93,7 @@ extern "C" int emu_infer(int T, int n_x, const float* w_packed, size_t n_w, int 
     std::vector<double> pair_D(Pn + 1), Dtmp(nnz + 1);
     std::vector<float> e((size_t)(Pn + 1) * EDR);
     std::vector<unsigned char> near(Pn + 16), perm_j(Pn + 16);
-    emu_launch_simple(div_up(n, 128), 128, [&] {
+    emu_launch_grid(div_up(n, 128), 4, 0, [&] {
         k_nbr::nbr_kernel<true>(n, atom_sys.data(), off, xyz, nullptr, nullptr, rowptr.data(), ustart.data(), col.data(), pair_i.data(), pair_j.data(),
                                 pair_D.data(), grid.data(), cell_start.data(), cell_atoms.data(), Dtmp.data(), 0, n); });
     emu_launch_simple(div_up(n, 128), 128, [&] { k_nbr::nbr_rev_kernel(n, rowptr.data(), ustart.data(), degU.data(), col.data(), pid.data()); });

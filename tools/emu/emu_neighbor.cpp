@@ -29,7 +29,7 @@ extern "C" int emu_neighbor_counts(const double* mu, const double* B, int n_atom
         std::fill(cnt.begin(), cnt.end(), 0);
         emu_launch_simple(div_up(n_atoms, 256), 256, [&] { cell_bin_kernel<1>(n_atoms, atom_sys, sys_off, xyz, grid, cnt.data(), cell_start, cell_atoms); });
     }
-    emu_launch_simple(div_up(n_atoms, 128), 128, [&] {
+    emu_launch_grid(div_up(n_atoms, 128), 4, 0, [&] {
         nbr_kernel<false>(n_atoms, atom_sys, sys_off, xyz, deg, degU, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, grid, cell_start, cell_atoms, nullptr, 0, n_atoms); });
     exclusive_scan(deg, rowptr, n_atoms);
     exclusive_scan(degU, ustart, n_atoms);
@@ -41,7 +41,7 @@ extern "C" int emu_neighbor_fill(int n_atoms, const int* atom_sys, const int* sy
                                  int* col, int* pid, int* pair_i, int* pair_j, double* pair_D, double* Dtmp,
                                  int ek, float* e, unsigned char* near) {
     const CellGrid* grid = reinterpret_cast<const CellGrid*>(grid_ints);
-    emu_launch_simple(div_up(n_atoms, 128), 128, [&] {
+    emu_launch_grid(div_up(n_atoms, 128), 4, 0, [&] {
         nbr_kernel<true>(n_atoms, atom_sys, sys_off, xyz, nullptr, nullptr, rowptr, ustart, col, pair_i, pair_j, pair_D, grid, cell_start, cell_atoms, Dtmp, 0, n_atoms); });
     emu_launch_simple(div_up(n_atoms, 128), 128, [&] { nbr_rev_kernel(n_atoms, rowptr, ustart, degU, col, pid); });
     const int64_t P = ustart[n_atoms];
