@@ -45,3 +45,35 @@ def test_b200_arm_has_no_cpu_fallback():
     out = _run("--steps", "1", "--warmup", "0", "--no-cpu-baseline")
     assert out.returncode != 0
     assert "no CPU fallback" in (out.stderr + out.stdout)
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_b200_arm_prints_the_contract_line_with_roofline_baseline_and_secondary_blocks():
+    """The driver's own invocation shape (`python bench.py`), shrunk: one JSON line on stdout carrying the base contract, the
+    roofline / cpu_baseline / e2e objects of this tier and the secondary blocks (strong scaling, live-GNN checkpoints, the
+    reference's three own configurations)."""
+    out = _run("--molecules", "20000", "--steps", "2", "--warmup", "3", "--ref-molecules", "64", "--strong-atoms", "3000")
+    assert out.returncode == 0, out.stderr[-800:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "secondary"):
+        assert k in d, k
+    assert d["unit"] == "atoms/s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["vs_baseline"] is None
+    assert d["value"] > 1e6 and d["gpu_launches"] > 20 and "workload" in d["config"] and "model" not in d["config"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "fp32" and 0 < r["frac"] < 1 and r["peak"] > 50 and r["traffic"] and 0 < r["algorithmic"]["frac"] < 1.2
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "64 molecules" in cb["sample"]
+    assert d["checks"]["max_abs_sum_q_minus_Q"] < 1e-6
+    s = d["secondary"]
+    for k in ("strong_qm9", "strong_protein", "live_gnn_model2_weights", "live_gnn_model_weights", "config_qm9_test", "config_ssi", "config_galectin3c"):
+        assert k in s and s[k]["value"] > 0, k
+    assert s["config_qm9_test"]["precision_used"] == 64 and s["config_ssi"]["precision_used"] == 32
+    assert s["config_galectin3c"]["max_abs_dq_vs_reference_preds_npy"] < 1e-5
+    assert s["strong_protein"]["checks"]["max_abs_sum_q_minus_Q"] < 1e-6
