@@ -76,6 +76,7 @@ struct epnn_ctx {
     int far_tc_impl = 1;         // option "gnn_far_tensor_impl": 1 round-1 kernel (epnn_gnn_tc.cu), 2 warp-specialised (epnn_gnn_tc2.cu)
     int dedup_far = 1;           // option "dedup_far": collapse species-equivalent far columns (exact)
     int pair_tensor = 0;         // option "pair_tensor": EPN bundle kernel on mma.sync 3xTF32 (precision 32 only)
+    int atom_tensor = 1;         // option "atom_tensor": FP32 per-atom kernel on mma.sync 3xTF32 (epnn_atom_mma.cu); 0 = the FP32 SIMT warp-tile kernel
     int pair_const = 2;          // option "pair_const": FP32 kernel set (0 warp-tile, 1 pair-per-thread everywhere, 2 default mix; see epnn_internal.cuh)
     std::vector<float> wf_host;  // host mirror of wf (pair_const passes a step's weights as kernel parameters)
     float* w2split = nullptr;    // [T][2][32][32]: hi / lo parts of W2^T of every message MLP (tensor-core far kernel)
@@ -279,6 +280,7 @@ extern "C" int epnn_set_option(epnn_ctx* c, const char* key, double value) {
     }
     else if (k == "dedup_far") c->dedup_far = value != 0;
     else if (k == "pair_tensor") c->pair_tensor = value != 0;
+    else if (k == "atom_tensor") c->atom_tensor = value != 0;
     else if (k == "pair_const") {
         if (value != 0 && value != 1 && value != 2) return fail(c, EPNN_E_INVALID, "pair_const must be 0, 1 or 2");
         c->pair_const = (int)value;
@@ -399,6 +401,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     w.n_species = c->n_species;
     w.pair_tensor = c->pair_tensor && sizeof(R) == 4;
     w.pair_const = sizeof(R) == 4 ? c->pair_const : 0;
+    w.atom_tensor = c->atom_tensor;
     w.wf_host = c->wf_host.data(); w.wf_dev = c->wf;
     w.work_counter = c->d_flags + 7;
     w.near_counter = stats && !neighbors_only && c->bufs[B_MISC].p ? (unsigned long long*)c->bufs[B_MISC].p : nullptr;

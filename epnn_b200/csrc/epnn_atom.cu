@@ -21,18 +21,6 @@
 // Work unit = one warp on a tile of 32 consecutive atoms; the dense layers run through tile_gemm.
 #include "epnn_internal.cuh"
 
-// R = arithmetic and state type (weights, l2, h); IO = type of the buffers shared with the pair kernels (S planes in, u / v out,
-// delta in).  IO = float with R = double is the "mixed" precision: FP32 pair kernels around an FP64 per-atom kernel.
-template <typename R, typename IO> struct AtomArgs {
-    int n_atoms, mode, nsplit, h_is_zero;
-    const int* atom_sys; const int* sys_off; const int* npad; const int* species;
-    const IO* Spart; R* h; R* l2; const R* HG; const R* g; const R* cb; UpdW<R> upd;
-    const int* rowptr; const int* col; const int* pid; const IO* delta; double* q;
-    const R* Pf; const R* Aq64; const R* Ax; IO* u; IO* v;
-    float* q_out; double* q_out64;
-    // sharded call: which atoms of LARGE systems this launch touches (small systems are replicated on every rank)
-    int scope, row_lo, row_hi; const unsigned char* active;     // scope 0 all, 1 owned rows [row_lo, row_hi), 2 active[] (owned + halo)
-};
 template <typename R, typename IO> __device__ __forceinline__ Vec4<R> ld_io(const IO* p) {
     const Vec4<IO> t = ldv(p);
     Vec4<R> r; r.x = (R)t.x; r.y = (R)t.y; r.z = (R)t.z; r.w = (R)t.w; return r;
@@ -291,6 +279,9 @@ cudaError_t launch_atom_io(const Workspace& w, int mode, const StepW<R>* prev, c
     if (mode & ATOM_PROJECT) { aa.Pf = next->Pf; aa.Aq64 = next->Aq64; aa.Ax = h_is_zero ? next->Ax64 : next->Axf; }
     aa.u = (IO*)w.u; aa.v = (IO*)w.v; aa.q_out = q_out; aa.q_out64 = q_out64;
     aa.scope = scope; aa.row_lo = w.row_lo; aa.row_hi = w.row_hi; aa.active = w.active;
+    if constexpr (sizeof(R) == 4 && sizeof(IO) == 4) {       // FP32 calls: launches with a dense layer run on the warp-level tensor path
+        if (w.atom_tensor && ((mode & ATOM_UPDATE) || ((mode & ATOM_PROJECT) && !h_is_zero))) return launch_atom_mma(w, aa, st, nl);
+    }
     const size_t smem = sizeof(R) * (ATOM_W_UPD + ATOM_W_PROJ + (size_t)NW * ATOM_TILE + NW * 64) + sizeof(int) * NW * 64;
     cudaError_t e = cudaFuncSetAttribute(scope ? atom_kernel<R, NW, IO, true> : atom_kernel<R, NW, IO, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -1,0 +1,330 @@
+// Per-atom kernel on the warp-level tensor path (FP32 calls; option "atom_tensor", default on).
+//
+// Same modes, inputs and outputs as atom_kernel<float, NW, float> (epnn_atom.cu; reference charge_gn.py:70-74, :116-118 and
+// the first-layer projections of :62-68 / :101-110), but the three dense layers of a step
+//     [l2_prev | S] (64) -> l1 (32) -> l2 (32) -> u | v (64)      (+ h = U3^T l2 + c3 (48) at the last message-passing step)
+// are real GEMMs over all atoms of the chunk (M = atoms, K / N = 32 .. 64), so they run as mma.sync.m16n8k8 (TF32 inputs,
+// FP32 accumulation) with the 3xTF32 error-compensated split  x = hi + lo:  lo*hi + hi*lo + hi*hi.  hi is x rounded to
+// TF32 (nearest, ties away), lo = x - hi exactly (the tensor core ignores its low 13 bits: representation error of an
+// operand <= 2^-21 |x|, the dropped lo*lo term <= 2^-22 |x||w|) -- the same order as the FP32 rounding of the SIMT kernel
+// (tests/test_gpu_parity.py keeps its tolerances; profiles/r02 noise-floor log).  With the FP32 pipe out of the way the
+// kernel is bound by its HBM traffic (640 B per atom and step) instead of by shared-memory operand reads.
+//
+// A warp owns a tile of 32 consecutive atoms = two 16-row m-tiles; thread (g = lane >> 2, t = lane & 3) owns rows
+// g, g + 8, g + 16, g + 24.  ONE index map serves every operand,
+//     amap(blk, t, h) = 16 (blk >> 1) + 4 t + 2 (blk & 1) + h          blk = 8-wide k block or n tile, h = 0 / 1
+// fragment position t (h = 0) / t + 4 (h = 1) of k block blk, and C-fragment column 2t + h of n tile blk, both stand for
+// the actual feature index amap(blk, t, h).  Consequences: (1) what a thread holds of blocks 2m, 2m + 1 is the float4 at
+// columns 16m + 4t .. + 3 of its rows, so every global load and store is a 128-bit access and a warp instruction touches
+// 8 rows x 64 contiguous bytes; (2) the C fragments a layer leaves behind ARE the A fragments of the next layer (after bias,
+// ReLU and the split) -- no shared-memory stage between layers; (3) the weights are permuted once per CTA into B fragments in
+// shared memory: fragment (kb, nt) = 32 lanes x {b0 hi, b1 hi, b0 lo, b1 lo}, one conflict-free LDS.128 per lane feeds six MMAs.
+#include "epnn_internal.cuh"
+
+#define AM_NW 8
+#define AM_FRAG 128                              // words per B fragment (32 lanes x 4)
+#define AM_B1 0                                  // [8 kb][4 nt]  first update layer  [U3 U1_h ; W3 U1_M]
+#define AM_B2 (AM_B1 + 32 * AM_FRAG)             // [4][4]        second update layer U2
+#define AM_B3 (AM_B2 + 16 * AM_FRAG)             // [4][8]        projections of the next pair kernel, U3 Ah64 (u | v)
+#define AM_BH (AM_B3 + 32 * AM_FRAG)             // [4][6]        h = U3^T l2 (last message-passing step)
+#define AM_VEC (AM_BH + 24 * AM_FRAG)            // cb[32] g[32] c2[32] c3[48] aq[64]
+#define AM_AX (AM_VEC + 208)                     // [MAX_SPECIES][64]
+#define AM_SLOT (AM_AX + MAX_SPECIES * 64)       // per warp: q[32] np[32] sp[32] ns[32]
+#define AM_SMEM_WORDS (AM_SLOT + AM_NW * 128)
+
+#ifdef EPNN_CPU_EMU
+__device__ __forceinline__ void am_mma(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    const unsigned b[2] = {b0, b1};
+    emu_mma_m16n8k8_tf32(d, a, b);
+}
+__device__ __forceinline__ void am_prefetch(const void*) {}
+struct am_u4 { unsigned x, y, z, w; };
+#else
+__device__ __forceinline__ void am_mma(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void am_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+typedef uint4 am_u4;
+#endif
+
+// x = hi + lo: hi = x rounded to TF32 (nearest, ties away from zero: integer add on the magnitude bits), lo = x - hi exactly
+__device__ __forceinline__ void am_split(float x, unsigned& hi, unsigned& lo) {
+    hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ int am_map(int blk, int t, int h) { return 16 * (blk >> 1) + 4 * t + 2 * (blk & 1) + h; }
+
+// B fragments of W[K][ld] columns col0 .. col0 + 8 NT: dst[(kb * NT + nt) * 128 + lane * 4] = {b0 hi, b1 hi, b0 lo, b1 lo},
+// b0 = W[amap(kb, t, 0)][col0 + amap(nt, g >> 1, g & 1)], b1 = W[amap(kb, t, 1)][same column].
+__device__ __forceinline__ void am_stage(unsigned* dst, const float* __restrict__ W, int ld, int col0, int KB, int NT, int tid, int nthr) {
+    for (int f = tid; f < KB * NT * 32; f += nthr) {
+        const int ln = f & 31, fr = f >> 5, kb = fr / NT, nt = fr - kb * NT, g = ln >> 2, t = ln & 3;
+        const int n = col0 + am_map(nt, g >> 1, g & 1);
+        unsigned h0, l0, h1, l1;
+        am_split(W[am_map(kb, t, 0) * ld + n], h0, l0);
+        am_split(W[am_map(kb, t, 1) * ld + n], h1, l1);
+        unsigned* d = dst + (size_t)f * 4;
+        d[0] = h0; d[1] = h1; d[2] = l0; d[3] = l1;
+    }
+}
+
+// acc[mt][nt] += A (two m-tiles, KB k blocks, hi / lo) * B fragments sB[(kb0 + kb) * ntot + nt0 + nt]
+template <int KB, int NT>
+__device__ __forceinline__ void am_layer(const unsigned (&ah)[2][KB][4], const unsigned (&al)[2][KB][4], const unsigned* __restrict__ sB,
+                                         int kb0, int ntot, int nt0, int lane, float (&acc)[2][NT][4]) {
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const am_u4 b = *reinterpret_cast<const am_u4*>(sB + ((size_t)((kb0 + kb) * ntot + nt0 + nt) * 32 + lane) * 4);
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                am_mma(acc[mt][nt], al[mt][kb], b.x, b.y);
+                am_mma(acc[mt][nt], ah[mt][kb], b.z, b.w);
+                am_mma(acc[mt][nt], ah[mt][kb], b.x, b.y);
+            }
+        }
+}
+
+// C-fragment values z[mt][nt][e] (e: d0 (row, 2t) d1 (row, 2t + 1) d2 (row + 8, 2t) d3 (row + 8, 2t + 1)) -> A fragments of the
+// next layer: k block nt, a0 = d0, a1 = d2, a2 = d1, a3 = d3
+template <int NB>
+__device__ __forceinline__ void am_to_a(const float (&z)[2][NB][4], unsigned (&ah)[2][NB][4], unsigned (&al)[2][NB][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            am_split(z[mt][nb][0], ah[mt][nb][0], al[mt][nb][0]);
+            am_split(z[mt][nb][2], ah[mt][nb][1], al[mt][nb][1]);
+            am_split(z[mt][nb][1], ah[mt][nb][2], al[mt][nb][2]);
+            am_split(z[mt][nb][3], ah[mt][nb][3], al[mt][nb][3]);
+        }
+}
+template <int NB> __device__ __forceinline__ void am_zero(float (&acc)[2][NB][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) acc[mt][nb][0] = acc[mt][nb][1] = acc[mt][nb][2] = acc[mt][nb][3] = 0.f;
+}
+// row i (0..3 <-> g + 8 i) and column pair m of a [2][NB][4] fragment set as the float4 at columns 16 m + 4 t .. + 3
+template <int NB> __device__ __forceinline__ float4 am_get4(const float (&z)[2][NB][4], int i, int m) {
+    const int mt = i >> 1, e = (i & 1) * 2;
+    return make_float4(z[mt][2 * m][e], z[mt][2 * m][e + 1], z[mt][2 * m + 1][e], z[mt][2 * m + 1][e + 1]);
+}
+template <int NB> __device__ __forceinline__ void am_put4(float (&z)[2][NB][4], int i, int m, float4 v) {
+    const int mt = i >> 1, e = (i & 1) * 2;
+    z[mt][2 * m][e] = v.x; z[mt][2 * m][e + 1] = v.y; z[mt][2 * m + 1][e] = v.z; z[mt][2 * m + 1][e + 1] = v.w;
+}
+__device__ __forceinline__ float4 am_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void am_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float am_relu(float x) { return x > 0.f ? x : 0.f; }
+
+template <bool SCOPED>
+__global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<float, float> a) {
+#ifdef EPNN_CPU_EMU
+    unsigned* sm = reinterpret_cast<unsigned*>(emu_smem);
+#else
+    extern __shared__ __align__(16) unsigned sm[];
+#endif
+    float* sv = reinterpret_cast<float*>(sm + AM_VEC);
+    float* scb = sv, *sg = sv + 32, *sc2 = sv + 64, *sc3 = sv + 96, *saq = sv + 144;
+    float* sAx = reinterpret_cast<float*>(sm + AM_AX);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    float* slot_q = reinterpret_cast<float*>(sm + AM_SLOT + warp * 128);
+    float* slot_np = slot_q + 32;
+    int* slot_sp = reinterpret_cast<int*>(slot_np + 32);
+    int* slot_ns = slot_sp + 32;
+
+    const bool do_upd = a.mode & ATOM_UPDATE, do_q = a.mode & ATOM_QUPDATE, do_proj = a.mode & ATOM_PROJECT;
+    const bool first = a.mode & ATOM_FIRST, write_h = a.mode & ATOM_WRITE_H;
+    const bool proj_gemm = do_proj && !a.h_is_zero;
+    const int nthr = AM_NW * 32;
+    if (do_upd) {
+        am_stage(sm + AM_B1, a.HG, HID, 0, 8, 4, threadIdx.x, nthr);
+        am_stage(sm + AM_B2, a.upd.U2, HID, 0, 4, 4, threadIdx.x, nthr);
+        if (write_h) am_stage(sm + AM_BH, a.upd.U3, HD, 0, 4, 6, threadIdx.x, nthr);
+        if (threadIdx.x < HID) { scb[threadIdx.x] = a.cb[threadIdx.x]; sg[threadIdx.x] = a.g[threadIdx.x]; sc2[threadIdx.x] = a.upd.c2[threadIdx.x]; }
+        if (threadIdx.x < HD) sc3[threadIdx.x] = a.upd.c3[threadIdx.x];
+    }
+    if (do_proj) {
+        if (proj_gemm) am_stage(sm + AM_B3, a.Pf, 64, 0, 4, 8, threadIdx.x, nthr);
+        for (int f = threadIdx.x; f < MAX_SPECIES * 64; f += nthr) sAx[f] = a.Ax[f];
+        if (threadIdx.x < 64) saq[threadIdx.x] = a.Aq64[threadIdx.x];
+    }
+    __syncthreads();
+
+    const int n_tiles = (a.n_atoms + 31) / 32;
+    for (int tile = blockIdx.x * AM_NW + warp; tile < n_tiles; tile += gridDim.x * AM_NW) {
+        const int base = tile * 32;
+        const int me = base + lane;
+        const bool me_ok = me < a.n_atoms;
+        {   // this warp's NEXT tile -> L2 while the current one computes (one 128-byte row per lane)
+            const int64_t nb = (int64_t)(tile + gridDim.x * AM_NW) * 32;
+            if (nb + lane < a.n_atoms) {
+                if ((do_upd && !first) || (proj_gemm && !do_upd)) am_prefetch(a.l2 + (nb + lane) * HID);
+                if (do_upd) am_prefetch(a.Spart + (nb + lane) * HID);
+            }
+        }
+        // ---------------- per-slot scalars and the charge update (lane = slot)
+        {
+            int sp = 0, ns = 0; float npf = 0.f;         // ns = 0 marks a slot this launch does not touch
+            double qv = 0.0;
+            bool in = me_ok;
+            int sys = 0, nat = 0;
+            if (me_ok) {
+                sys = a.atom_sys[me];
+                nat = a.sys_off[sys + 1] - a.sys_off[sys];
+                if (SCOPED && a.scope && nat > SMALL_MAX) in = a.scope == 1 ? (me >= a.row_lo && me < a.row_hi) : a.active[me] != 0;
+            }
+            if (in) {
+                sp = a.species[me];
+                ns = nat > SMALL_MAX ? a.nsplit : 1;
+                npf = (float)a.npad[sys];
+                qv = a.q[me];
+                if (do_q) {
+                    const int r0 = a.rowptr[me], r1 = a.rowptr[me + 1];
+                    for (int k = r0; k < r1; ++k) {          // fixed (ascending column) order
+                        const double d = (double)a.delta[a.pid[k]];
+                        qv += a.col[k] > me ? d : -d;
+                    }
+                    a.q[me] = qv;
+                }
+                if (a.mode & ATOM_OUTPUT) {
+                    if (a.q_out) a.q_out[me] = (float)qv;
+                    if (a.q_out64) a.q_out64[me] = qv;
+                }
+            }
+            slot_sp[lane] = sp; slot_ns[lane] = ns; slot_np[lane] = npf; slot_q[lane] = (float)qv;
+        }
+        __syncwarp();
+        if (!do_upd && !do_proj) continue;
+        int rns[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rns[i] = slot_ns[g + 8 * i];
+        if (SCOPED && a.scope && !__any_sync(0xffffffffu, rns[0] | rns[1] | rns[2] | rns[3])) { __syncwarp(); continue; }
+
+        unsigned ah[2][4][4], al[2][4][4];               // A fragments of the layer about to run (k blocks 0..3)
+        float z[2][4][4];
+        if (do_upd) {
+            // ---- first layer: relu([U3 U1_h ; W3 U1_M]^T [l2_prev | S] + cb + npad g), 16 input columns (two k blocks) at a time
+            float acc[2][4][4];
+            am_zero<4>(acc);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < 2 && first) continue;            // h = 0: no previous l2
+                float zz[2][2][4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int64_t at = base + g + 8 * i;
+                    if (rns[i] > 0) {
+                        if (j < 2) x = am_ld4(a.l2 + at * HID + 16 * j + 4 * t);
+                        else
+                            for (int sp = 0; sp < rns[i]; ++sp) {       // partial planes summed in fixed order
+                                const float4 p = am_ld4(a.Spart + ((int64_t)sp * a.n_atoms + at) * HID + 16 * (j - 2) + 4 * t);
+                                x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w;
+                            }
+                    }
+                    am_put4<2>(zz, i, 0, x);
+                }
+                unsigned ah1[2][2][4], al1[2][2][4];
+                am_to_a<2>(zz, ah1, al1);
+                am_layer<2, 4>(ah1, al1, sm + AM_B1, 2 * j, 4, 0, lane, acc);
+            }
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const float4 cv = am_ld4(scb + 16 * m + 4 * t), gv = am_ld4(sg + 16 * m + 4 * t);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float np = slot_np[g + 8 * i];
+                    float4 v = am_get4<4>(acc, i, m);
+                    v.x = am_relu(fmaf(np, gv.x, v.x + cv.x)); v.y = am_relu(fmaf(np, gv.y, v.y + cv.y));
+                    v.z = am_relu(fmaf(np, gv.z, v.z + cv.z)); v.w = am_relu(fmaf(np, gv.w, v.w + cv.w));
+                    am_put4<4>(z, i, m, v);
+                }
+            }
+            am_to_a<4>(z, ah, al);
+            // ---- second layer: l2 = relu(U2^T l1 + c2)
+            am_zero<4>(acc);
+            am_layer<4, 4>(ah, al, sm + AM_B2, 0, 4, 0, lane, acc);
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const float4 cv = am_ld4(sc2 + 16 * m + 4 * t);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 v = am_get4<4>(acc, i, m);
+                    v.x = am_relu(v.x + cv.x); v.y = am_relu(v.y + cv.y); v.z = am_relu(v.z + cv.z); v.w = am_relu(v.w + cv.w);
+                    if (rns[i] > 0) am_st4(a.l2 + (int64_t)(base + g + 8 * i) * HID + 16 * m + 4 * t, v);
+                    am_put4<4>(z, i, m, v);
+                }
+            }
+            am_to_a<4>(z, ah, al);
+            // ---- last message-passing step only: the hidden state itself, h = U3^T l2 + c3, one 16-column pair at a time
+            if (write_h) {
+                for (int m = 0; m < 3; ++m) {
+                    float ha[2][2][4];
+                    am_zero<2>(ha);
+                    am_layer<4, 2>(ah, al, sm + AM_BH, 0, 6, 2 * m, lane, ha);
+                    const float4 cv = am_ld4(sc3 + 16 * m + 4 * t);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 v = am_get4<2>(ha, i, 0);
+                        v.x += cv.x; v.y += cv.y; v.z += cv.z; v.w += cv.w;
+                        if (rns[i] > 0) am_st4(a.h + (int64_t)(base + g + 8 * i) * HD + 16 * m + 4 * t, v);
+                    }
+                }
+            }
+        } else if (proj_gemm) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {            // l2 of the last message-passing step
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rns[i] > 0) v = am_ld4(a.l2 + (int64_t)(base + g + 8 * i) * HID + 16 * m + 4 * t);
+                    am_put4<4>(z, i, m, v);
+                }
+            am_to_a<4>(z, ah, al);
+        }
+
+        if (do_proj) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {       // half 0 -> u (a_i block), half 1 -> v (a_j block, + b1)
+                float acc[2][4][4];
+                am_zero<4>(acc);
+                if (proj_gemm) am_layer<4, 4>(ah, al, sm + AM_B3, 0, 8, 4 * half, lane, acc);
+                float* dst = half == 0 ? a.u : a.v;
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const float4 aq = am_ld4(saq + half * HID + 16 * m + 4 * t);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (rns[i] > 0) {
+                            const float4 ax = am_ld4(sAx + slot_sp[g + 8 * i] * 64 + half * HID + 16 * m + 4 * t);
+                            const float qv = slot_q[g + 8 * i];
+                            float4 v = am_get4<4>(acc, i, m);
+                            v.x += fmaf(qv, aq.x, ax.x); v.y += fmaf(qv, aq.y, ax.y); v.z += fmaf(qv, aq.z, ax.z); v.w += fmaf(qv, aq.w, ax.w);
+                            am_st4(dst + (int64_t)(base + g + 8 * i) * HID + 16 * m + 4 * t, v);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+#ifndef EPNN_CPU_EMU
+cudaError_t launch_atom_mma(const Workspace& w, const AtomArgs<float, float>& aa, cudaStream_t st, int* nl) {
+    const size_t smem = sizeof(unsigned) * AM_SMEM_WORDS;
+    cudaError_t e = cudaFuncSetAttribute(aa.scope ? atom_mma_kernel<true> : atom_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int grid = div_up(div_up(w.n_atoms, 32), AM_NW);
+    if (grid > 2 * w.sm_count) grid = 2 * w.sm_count;
+    if (aa.scope) atom_mma_kernel<true><<<grid, AM_NW * 32, smem, st>>>(aa);
+    else atom_mma_kernel<false><<<grid, AM_NW * 32, smem, st>>>(aa);
+    ++*nl;
+    return cudaGetLastError();
+}
+#endif

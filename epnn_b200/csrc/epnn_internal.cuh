@@ -255,6 +255,7 @@ struct Workspace {
     int pair_tensor;                              // 1: electron-passing bundle kernel on the warp-level tensor path (3xTF32, FP32 only)
     int pair_const;                               // FP32 kernel set: 0 warp-tile kernels (round 1), 1 pair-per-thread kernels everywhere,
                                                   // 2 (default) row-run GNN bundle kernel + pair-per-thread EPN bundle kernel + row-per-thread far kernel
+    int atom_tensor;                              // 1 (default): FP32 per-atom kernel on the warp-level tensor path (3xTF32, epnn_atom_mma.cu)
     void* args_dev;                               // 1 KB device scratch: argument block of the kernels that take theirs through global memory
     const float* wf_host; const float* wf_dev;    // packed FP32 weights: host mirror and device base (pair_const passes weights as kernel parameters)
     unsigned long long* near_counter;             // device counter (statistics, may be NULL): unordered pairs in the is_near set
@@ -314,12 +315,25 @@ template <typename R> cudaError_t launch_epn_pair(const Workspace& w, const Step
 #define ATOM_OUTPUT  8     // write q to the output buffers
 #define ATOM_FIRST   16    // first message-passing step: h = 0, there is no previous l2
 #define ATOM_WRITE_H 32    // also materialise h = U3^T l2 + c3 (last message-passing step: epnn_get_hidden)
+// R = arithmetic and state type (weights, l2, h); IO = type of the buffers shared with the pair kernels (S planes in, u / v out,
+// delta in).  IO = float with R = double is the "mixed" precision: FP32 pair kernels around an FP64 per-atom kernel.
+template <typename R, typename IO> struct AtomArgs {
+    int n_atoms, mode, nsplit, h_is_zero;
+    const int* atom_sys; const int* sys_off; const int* npad; const int* species;
+    const IO* Spart; R* h; R* l2; const R* HG; const R* g; const R* cb; UpdW<R> upd;
+    const int* rowptr; const int* col; const int* pid; const IO* delta; double* q;
+    const R* Pf; const R* Aq64; const R* Ax; IO* u; IO* v;
+    float* q_out; double* q_out64;
+    // sharded call: which atoms of LARGE systems this launch touches (small systems are replicated on every rank)
+    int scope, row_lo, row_hi; const unsigned char* active;     // scope 0 all, 1 owned rows [row_lo, row_hi), 2 active[] (owned + halo)
+};
 #ifndef EPNN_CPU_EMU
 template <typename R> cudaError_t launch_atom(const Workspace& w, int mode, const StepW<R>* prev, const UpdW<R>* upd,
                                               const StepW<R>* next, int h_is_zero, float* q_out, double* q_out64,
                                               cudaStream_t st, int* n_launch, int scope = 0);      // scope: see AtomArgs (sharded calls)
 cudaError_t launch_atom_mixed(const Workspace& w, int mode, const StepW<double>* prev, const UpdW<double>* upd, const StepW<double>* next,
                               int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* n_launch, int scope = 0);   // precision 48
+cudaError_t launch_atom_mma(const Workspace& w, const AtomArgs<float, float>& aa, cudaStream_t st, int* n_launch);   // option atom_tensor (epnn_atom_mma.cu)
 cudaError_t launch_atom_const(const Workspace& w, int mode, const StepW<float>* prev, const UpdW<float>* upd, const StepW<float>* next,
                               int h_is_zero, float* q_out, double* q_out64, cudaStream_t st, int* n_launch);   // option pair_const
 

@@ -105,6 +105,10 @@ const char* epnn_last_error(const epnn_ctx* ctx);
  * "pair_tensor" 0 (default) / 1: systems with at most 48 atoms evaluate the electron-passing pair MLP on the warp-level
  * tensor path (mma.sync m16n8k8 TF32 inputs, 3xTF32 split, FP32 accumulation, operands chained through registers)
  * instead of FP32 SIMT (precision 32 only; per-pair transfers differ from the SIMT path by about 1e-6 relative);
+ * "atom_tensor" 1 (default) / 0: FP32 calls run the dense layers of the per-atom kernel (folded update MLP, first-layer
+ * projections: GEMMs over all atoms of a chunk) on the warp-level tensor path, 3xTF32 split with FP32 accumulation
+ * (epnn_atom_mma.cu), which leaves that kernel bound by its HBM traffic; 0 = the FP32 SIMT warp-tile kernel.  Same
+ * formulas; results differ at the level of FP32 round-off.  Mixed / FP64 calls are not affected;
  * "pair_const": the FP32 kernel set.  2 (default): row-run GNN bundle kernel (epnn_bundle_run.cu: one contiguous run of
  * pair slots per lane, row sums in registers) + pair-per-thread EPN bundle kernel + row-per-thread far kernel for large
  * systems, all with the weights as uniform FFMA2 operands (kernel parameters); 1: pair-per-thread kernels everywhere

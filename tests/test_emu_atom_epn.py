@@ -24,6 +24,7 @@ def emu():
     lib = C.CDLL(LIB)
     lib.emu_atom_kernel.argtypes = [C.c_int] * 4 + [C.c_void_p] * 18
     lib.emu_atom_const_kernel.argtypes = [C.c_int] * 4 + [C.c_void_p] * 18
+    lib.emu_atom_mma_kernel.argtypes = [C.c_int] * 4 + [C.c_void_p] * 18
     lib.emu_epn_pair_kernel.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
     return lib
 
@@ -47,7 +48,8 @@ def _lists(protein, mixed, rng):
     return L, npad
 
 
-@pytest.mark.parametrize("kernel", ["emu_atom_kernel", "emu_atom_const_kernel"])     # default kernel; experimental atom-per-thread variant
+# FP32 SIMT warp-tile kernel; experimental atom-per-thread variant; warp-level tensor kernel (3xTF32, the FP32 default)
+@pytest.mark.parametrize("kernel", ["emu_atom_kernel", "emu_atom_const_kernel", "emu_atom_mma_kernel"])
 def test_emulated_atom_kernel_modes(emu, protein, mixed, kernel):
     rng = np.random.default_rng(21)
     L, npad = _lists(protein, mixed, rng)

@@ -5,6 +5,7 @@
 #include "../../epnn_b200/csrc/epnn_atom.cu"
 #include "../../epnn_b200/csrc/epnn_epn.cu"
 #include "../../epnn_b200/csrc/epnn_atom_const.cu"
+#include "../../epnn_b200/csrc/epnn_atom_mma.cu"
 
 // wu: HG[64*32] | cb[32] | g[32] | U2[32*32] | c2[32] | U3[32*48] | c3[48]        (update side, already folded)
 // wp: Pf[32*64] | Aq64[64] | Ax[16*64]                                            (projection side of the NEXT pair kernel)
@@ -25,6 +26,25 @@ extern "C" int emu_atom_kernel(int mode, int h_is_zero, int n_atoms, int nsplit,
     constexpr int NW = 4;
     const size_t smem = sizeof(float) * (ATOM_W_UPD + ATOM_W_PROJ + (size_t)NW * ATOM_TILE + NW * 64) + sizeof(int) * NW * 64;
     emu_launch_grid(2, NW, smem / sizeof(float) + 8, [&] { atom_kernel<float, NW, float, false>(aa); });
+    return 0;
+}
+
+// the warp-level tensor variant (epnn_atom_mma.cu: FP32 default), same inputs
+extern "C" int emu_atom_mma_kernel(int mode, int h_is_zero, int n_atoms, int nsplit, const float* wu, const float* wp,
+                                   const int* atom_sys, const int* sys_off, const int* npad, const int* species,
+                                   const float* Spart, float* h, float* l2, const int* rowptr, const int* col, const int* pid,
+                                   const float* delta, double* q, float* u, float* v, float* q_out, double* q_out64) {
+    AtomArgs<float, float> aa;
+    memset(&aa, 0, sizeof(aa));
+    aa.n_atoms = n_atoms; aa.mode = mode; aa.nsplit = nsplit; aa.h_is_zero = h_is_zero;
+    aa.atom_sys = atom_sys; aa.sys_off = sys_off; aa.npad = npad; aa.species = species;
+    aa.Spart = Spart; aa.h = h; aa.l2 = l2;
+    aa.HG = wu; aa.cb = wu + 64 * HID; aa.g = aa.cb + HID;
+    aa.upd.U2 = aa.g + HID; aa.upd.c2 = aa.upd.U2 + HID * HID; aa.upd.U3 = aa.upd.c2 + HID; aa.upd.c3 = aa.upd.U3 + HID * HD;
+    aa.rowptr = rowptr; aa.col = col; aa.pid = pid; aa.delta = delta; aa.q = q;
+    aa.Pf = wp; aa.Aq64 = wp + HID * 64; aa.Ax = aa.Aq64 + 64;
+    aa.u = u; aa.v = v; aa.q_out = q_out; aa.q_out64 = q_out64;
+    emu_launch_grid(2, AM_NW, AM_SMEM_WORDS + 8, [&] { atom_mma_kernel<false>(aa); });
     return 0;
 }
 

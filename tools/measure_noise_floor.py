@@ -1,5 +1,5 @@
 """Measured distance of every precision mode to the float64 oracle (development aid; the output is the evidence behind the
-tolerances in tests/test_gpu_parity.py and DESIGN.md section 2).   python tools/measure_noise_floor.py [n_systems]"""
+tolerances in tests/test_gpu_parity.py and DESIGN.md section 2).   python tools/measure_noise_floor.py [n_systems] [OPTION=VALUE ...]"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -10,6 +10,7 @@ from epnn_b200.engine import Engine
 from oracle import epnn_oracle as O
 
 n_sys = int(sys.argv[1]) if len(sys.argv) > 1 else 400
+opts = [a.split("=") for a in sys.argv[2:]]
 mx = Mixed()
 for name in CKPTS:
     w = load_weights(os.path.join(GOLDEN, "checkpoints", name))
@@ -22,6 +23,8 @@ for name in CKPTS:
         for prec in (32, 48, 64, 0):
             eng = Engine(w, device=0, precision=prec)
             eng.set_option("timing", 1)
+            for k, v in opts:
+                eng.set_option(k, float(v))
             q, q64 = eng.infer_batch(offs, xyz, sp, Q, npads, want_f64=True)
             st = eng.last_stats
             per_sys = np.maximum.reduceat(np.abs(q64 - ref), offs[:-1])
