@@ -4,10 +4,10 @@
 // the first-layer projections of :62-68 / :101-110), but the three dense layers of a step
 //     [l2_prev | S] (64) -> l1 (32) -> l2 (32) -> u | v (64)      (+ h = U3^T l2 + c3 (48) at the last message-passing step)
 // are real GEMMs over all atoms of the chunk (M = atoms, K / N = 32 .. 64), so they run as mma.sync.m16n8k8 (TF32 inputs,
-// FP32 accumulation) with the 3xTF32 error-compensated split  x = hi + lo:  lo*hi + hi*lo + hi*hi.  hi is x rounded to
-// TF32 (nearest, ties away), lo = x - hi exactly (the tensor core ignores its low 13 bits: representation error of an
-// operand <= 2^-21 |x|, the dropped lo*lo term <= 2^-22 |x||w|) -- the same order as the FP32 rounding of the SIMT kernel
-// (tests/test_gpu_parity.py keeps its tolerances; profiles/r02 noise-floor log).  With the FP32 pipe out of the way the
+// FP32 accumulation) with the 3xTF32 error-compensated split  x = hi + lo:  lo*hi + hi*lo + hi*hi.  hi and lo are rounded to
+// TF32 (nearest, ties away): representation error of an operand <= 2^-22 |x|, the dropped lo*lo term <= 2^-22 |x||w|; the
+// hi*hi blocks are summed on the FP32 pipe (am_pair) -- the same order of error as the FP32 rounding of the SIMT kernel
+// (tests/test_gpu_parity.py keeps its tolerances; noise-floor log in profiles/r02).  With the FP32 pipe out of the way the
 // kernel is bound by its HBM traffic (640 B per atom and step) instead of by shared-memory operand reads.
 //
 // A warp owns a tile of 32 consecutive atoms = two 16-row m-tiles; thread (g = lane >> 2, t = lane & 3) owns rows
@@ -21,7 +21,9 @@
 // shared memory: fragment (kb, nt) = 32 lanes x {b0 hi, b1 hi, b0 lo, b1 lo}, one conflict-free LDS.128 per lane feeds six MMAs.
 #include "epnn_internal.cuh"
 
+#ifndef AM_NW
 #define AM_NW 8
+#endif
 #define AM_FRAG 128                              // words per B fragment (32 lanes x 4)
 #define AM_B1 0                                  // [8 kb][4 nt]  first update layer  [U3 U1_h ; W3 U1_M]
 #define AM_B2 (AM_B1 + 32 * AM_FRAG)             // [4][4]        second update layer U2
@@ -49,10 +51,11 @@ __device__ __forceinline__ void am_prefetch(const void* p) { asm volatile("prefe
 typedef uint4 am_u4;
 #endif
 
-// x = hi + lo: hi = x rounded to TF32 (nearest, ties away from zero: integer add on the magnitude bits), lo = x - hi exactly
+// x = hi + lo: hi = x rounded to TF32 (nearest, ties away from zero: integer add on the magnitude bits), lo = x - hi (exact)
+// rounded to TF32 the same way -- the tensor core would truncate it
 __device__ __forceinline__ void am_split(float x, unsigned& hi, unsigned& lo) {
     hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
-    lo = __float_as_uint(x - __uint_as_float(hi));
+    lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
 }
 __device__ __forceinline__ int am_map(int blk, int t, int h) { return 16 * (blk >> 1) + 4 * t + 2 * (blk & 1) + h; }
 
@@ -70,52 +73,75 @@ __device__ __forceinline__ void am_stage(unsigned* dst, const float* __restrict_
     }
 }
 
-// acc[mt][nt] += A (two m-tiles, KB k blocks, hi / lo) * B fragments sB[(kb0 + kb) * ntot + nt0 + nt]
-template <int KB, int NT>
-__device__ __forceinline__ void am_layer(const unsigned (&ah)[2][KB][4], const unsigned (&al)[2][KB][4], const unsigned* __restrict__ sB,
-                                         int kb0, int ntot, int nt0, int lane, float (&acc)[2][NT][4]) {
+// Fragment sets are stored per column pair: z[m][mt][n][e] = C-fragment element e (d0 (row, 2t) d1 (row, 2t + 1) d2 (row + 8, 2t)
+// d3 (row + 8, 2t + 1)) of m-tile mt and n tile 2m + n.
+//
+// acc[mt][n] += A (two m-tiles, KB k blocks, hi / lo) * B fragments (kb0 + kb, nt0 + n) for one column pair.  The tensor core
+// rounds its FP32 accumulator toward zero, a bias that grows linearly with the length of an accumulation chain (first GPU
+// run of this kernel: model2_weights 3.9e-6 -> 9.8e-6 from the oracle).  So, as in Ootomo & Yokota's error-corrected TF32 GEMM,
+// every hi*hi product block is an MMA into a ZERO accumulator that is added to the running sum on the FP32 pipe (round to
+// nearest), and only the two small correction terms lo*hi + hi*lo chain inside the tensor core (2^-11 of the main term: their
+// rounding is irrelevant) and are added once at the end.
+template <int KB>
+__device__ __forceinline__ void am_pair(const unsigned (&ah)[2][KB][4], const unsigned (&al)[2][KB][4], const unsigned* __restrict__ sB,
+                                        int kb0, int ntot, int nt0, int lane, float (&acc)[2][2][4]) {
+    float corr[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < 2; ++n) corr[mt][n][0] = corr[mt][n][1] = corr[mt][n][2] = corr[mt][n][3] = 0.f;
 #pragma unroll
     for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-            const am_u4 b = *reinterpret_cast<const am_u4*>(sB + ((size_t)((kb0 + kb) * ntot + nt0 + nt) * 32 + lane) * 4);
+        for (int n = 0; n < 2; ++n) {
+            const am_u4 b = *reinterpret_cast<const am_u4*>(sB + ((size_t)((kb0 + kb) * ntot + nt0 + n) * 32 + lane) * 4);
 #pragma unroll
             for (int mt = 0; mt < 2; ++mt) {
-                am_mma(acc[mt][nt], al[mt][kb], b.x, b.y);
-                am_mma(acc[mt][nt], ah[mt][kb], b.z, b.w);
-                am_mma(acc[mt][nt], ah[mt][kb], b.x, b.y);
+                am_mma(corr[mt][n], al[mt][kb], b.x, b.y);
+                am_mma(corr[mt][n], ah[mt][kb], b.z, b.w);
+                float tmp[4] = {0.f, 0.f, 0.f, 0.f};
+                am_mma(tmp, ah[mt][kb], b.x, b.y);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[mt][n][e] += tmp[e];
             }
         }
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < 2; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[mt][n][e] += corr[mt][n][e];
 }
 
-// C-fragment values z[mt][nt][e] (e: d0 (row, 2t) d1 (row, 2t + 1) d2 (row + 8, 2t) d3 (row + 8, 2t + 1)) -> A fragments of the
-// next layer: k block nt, a0 = d0, a1 = d2, a2 = d1, a3 = d3
-template <int NB>
-__device__ __forceinline__ void am_to_a(const float (&z)[2][NB][4], unsigned (&ah)[2][NB][4], unsigned (&al)[2][NB][4]) {
+// C-fragment values of NP column pairs -> A fragments of the next layer: k block 2m + n, a0 = d0, a1 = d2, a2 = d1, a3 = d3
+template <int NP>
+__device__ __forceinline__ void am_to_a(const float (&z)[NP][2][2][4], unsigned (&ah)[2][2 * NP][4], unsigned (&al)[2][2 * NP][4]) {
+#pragma unroll
+    for (int m = 0; m < NP; ++m)
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                am_split(z[m][mt][n][0], ah[mt][2 * m + n][0], al[mt][2 * m + n][0]);
+                am_split(z[m][mt][n][2], ah[mt][2 * m + n][1], al[mt][2 * m + n][1]);
+                am_split(z[m][mt][n][1], ah[mt][2 * m + n][2], al[mt][2 * m + n][2]);
+                am_split(z[m][mt][n][3], ah[mt][2 * m + n][3], al[mt][2 * m + n][3]);
+            }
+}
+__device__ __forceinline__ void am_zero(float (&acc)[2][2][4]) {
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int nb = 0; nb < NB; ++nb) {
-            am_split(z[mt][nb][0], ah[mt][nb][0], al[mt][nb][0]);
-            am_split(z[mt][nb][2], ah[mt][nb][1], al[mt][nb][1]);
-            am_split(z[mt][nb][1], ah[mt][nb][2], al[mt][nb][2]);
-            am_split(z[mt][nb][3], ah[mt][nb][3], al[mt][nb][3]);
-        }
+        for (int n = 0; n < 2; ++n) acc[mt][n][0] = acc[mt][n][1] = acc[mt][n][2] = acc[mt][n][3] = 0.f;
 }
-template <int NB> __device__ __forceinline__ void am_zero(float (&acc)[2][NB][4]) {
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nb = 0; nb < NB; ++nb) acc[mt][nb][0] = acc[mt][nb][1] = acc[mt][nb][2] = acc[mt][nb][3] = 0.f;
-}
-// row i (0..3 <-> g + 8 i) and column pair m of a [2][NB][4] fragment set as the float4 at columns 16 m + 4 t .. + 3
-template <int NB> __device__ __forceinline__ float4 am_get4(const float (&z)[2][NB][4], int i, int m) {
+// row i (0..3 <-> g + 8 i) of one column pair as the float4 at columns 16 m + 4 t .. + 3
+__device__ __forceinline__ float4 am_get4(const float (&z)[2][2][4], int i) {
     const int mt = i >> 1, e = (i & 1) * 2;
-    return make_float4(z[mt][2 * m][e], z[mt][2 * m][e + 1], z[mt][2 * m + 1][e], z[mt][2 * m + 1][e + 1]);
+    return make_float4(z[mt][0][e], z[mt][0][e + 1], z[mt][1][e], z[mt][1][e + 1]);
 }
-template <int NB> __device__ __forceinline__ void am_put4(float (&z)[2][NB][4], int i, int m, float4 v) {
+__device__ __forceinline__ void am_put4(float (&z)[2][2][4], int i, float4 v) {
     const int mt = i >> 1, e = (i & 1) * 2;
-    z[mt][2 * m][e] = v.x; z[mt][2 * m][e + 1] = v.y; z[mt][2 * m + 1][e] = v.z; z[mt][2 * m + 1][e + 1] = v.w;
+    z[mt][0][e] = v.x; z[mt][0][e + 1] = v.y; z[mt][1][e] = v.z; z[mt][1][e + 1] = v.w;
 }
 __device__ __forceinline__ float4 am_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void am_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
@@ -206,15 +232,14 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
         if (SCOPED && a.scope && !__any_sync(0xffffffffu, rns[0] | rns[1] | rns[2] | rns[3])) { __syncwarp(); continue; }
 
         unsigned ah[2][4][4], al[2][4][4];               // A fragments of the layer about to run (k blocks 0..3)
-        float z[2][4][4];
+        float z[2][2][2][4];                             // a layer's 32 output columns: two column pairs
         if (do_upd) {
             // ---- first layer: relu([U3 U1_h ; W3 U1_M]^T [l2_prev | S] + cb + npad g), 16 input columns (two k blocks) at a time
-            float acc[2][4][4];
-            am_zero<4>(acc);
+            am_zero(z[0]); am_zero(z[1]);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (j < 2 && first) continue;            // h = 0: no previous l2
-                float zz[2][2][4];
+                float zz[1][2][2][4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -227,11 +252,12 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
                                 x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w;
                             }
                     }
-                    am_put4<2>(zz, i, 0, x);
+                    am_put4(zz[0], i, x);
                 }
                 unsigned ah1[2][2][4], al1[2][2][4];
-                am_to_a<2>(zz, ah1, al1);
-                am_layer<2, 4>(ah1, al1, sm + AM_B1, 2 * j, 4, 0, lane, acc);
+                am_to_a<1>(zz, ah1, al1);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) am_pair<2>(ah1, al1, sm + AM_B1, 2 * j, 4, 2 * m, lane, z[m]);
             }
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
@@ -239,38 +265,38 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float np = slot_np[g + 8 * i];
-                    float4 v = am_get4<4>(acc, i, m);
+                    float4 v = am_get4(z[m], i);
                     v.x = am_relu(fmaf(np, gv.x, v.x + cv.x)); v.y = am_relu(fmaf(np, gv.y, v.y + cv.y));
                     v.z = am_relu(fmaf(np, gv.z, v.z + cv.z)); v.w = am_relu(fmaf(np, gv.w, v.w + cv.w));
-                    am_put4<4>(z, i, m, v);
+                    am_put4(z[m], i, v);
                 }
             }
-            am_to_a<4>(z, ah, al);
-            // ---- second layer: l2 = relu(U2^T l1 + c2)
-            am_zero<4>(acc);
-            am_layer<4, 4>(ah, al, sm + AM_B2, 0, 4, 0, lane, acc);
+            am_to_a<2>(z, ah, al);
+            // ---- second layer: l2 = relu(U2^T l1 + c2), one column pair at a time
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
+                am_zero(z[m]);
+                am_pair<4>(ah, al, sm + AM_B2, 0, 4, 2 * m, lane, z[m]);
                 const float4 cv = am_ld4(sc2 + 16 * m + 4 * t);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    float4 v = am_get4<4>(acc, i, m);
+                    float4 v = am_get4(z[m], i);
                     v.x = am_relu(v.x + cv.x); v.y = am_relu(v.y + cv.y); v.z = am_relu(v.z + cv.z); v.w = am_relu(v.w + cv.w);
                     if (rns[i] > 0) am_st4(a.l2 + (int64_t)(base + g + 8 * i) * HID + 16 * m + 4 * t, v);
-                    am_put4<4>(z, i, m, v);
+                    am_put4(z[m], i, v);
                 }
             }
-            am_to_a<4>(z, ah, al);
-            // ---- last message-passing step only: the hidden state itself, h = U3^T l2 + c3, one 16-column pair at a time
+            am_to_a<2>(z, ah, al);
+            // ---- last message-passing step only: the hidden state itself, h = U3^T l2 + c3
             if (write_h) {
                 for (int m = 0; m < 3; ++m) {
                     float ha[2][2][4];
-                    am_zero<2>(ha);
-                    am_layer<4, 2>(ah, al, sm + AM_BH, 0, 6, 2 * m, lane, ha);
+                    am_zero(ha);
+                    am_pair<4>(ah, al, sm + AM_BH, 0, 6, 2 * m, lane, ha);
                     const float4 cv = am_ld4(sc3 + 16 * m + 4 * t);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        float4 v = am_get4<2>(ha, i, 0);
+                        float4 v = am_get4(ha, i);
                         v.x += cv.x; v.y += cv.y; v.z += cv.z; v.w += cv.w;
                         if (rns[i] > 0) am_st4(a.h + (int64_t)(base + g + 8 * i) * HD + 16 * m + 4 * t, v);
                     }
@@ -283,30 +309,27 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
                 for (int i = 0; i < 4; ++i) {            // l2 of the last message-passing step
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (rns[i] > 0) v = am_ld4(a.l2 + (int64_t)(base + g + 8 * i) * HID + 16 * m + 4 * t);
-                    am_put4<4>(z, i, m, v);
+                    am_put4(z[m], i, v);
                 }
-            am_to_a<4>(z, ah, al);
+            am_to_a<2>(z, ah, al);
         }
 
         if (do_proj) {
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {       // half 0 -> u (a_i block), half 1 -> v (a_j block, + b1)
-                float acc[2][4][4];
-                am_zero<4>(acc);
-                if (proj_gemm) am_layer<4, 4>(ah, al, sm + AM_B3, 0, 8, 4 * half, lane, acc);
-                float* dst = half == 0 ? a.u : a.v;
+            for (int m = 0; m < 4; ++m) {                // column pairs 0, 1 -> u (a_i block), 2, 3 -> v (a_j block, + b1)
+                float acc[2][2][4];
+                am_zero(acc);
+                if (proj_gemm) am_pair<4>(ah, al, sm + AM_B3, 0, 8, 2 * m, lane, acc);
+                float* dst = m < 2 ? a.u : a.v;
+                const float4 aq = am_ld4(saq + 16 * m + 4 * t);
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
-                    const float4 aq = am_ld4(saq + half * HID + 16 * m + 4 * t);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        if (rns[i] > 0) {
-                            const float4 ax = am_ld4(sAx + slot_sp[g + 8 * i] * 64 + half * HID + 16 * m + 4 * t);
-                            const float qv = slot_q[g + 8 * i];
-                            float4 v = am_get4<4>(acc, i, m);
-                            v.x += fmaf(qv, aq.x, ax.x); v.y += fmaf(qv, aq.y, ax.y); v.z += fmaf(qv, aq.z, ax.z); v.w += fmaf(qv, aq.w, ax.w);
-                            am_st4(dst + (int64_t)(base + g + 8 * i) * HID + 16 * m + 4 * t, v);
-                        }
+                for (int i = 0; i < 4; ++i) {
+                    if (rns[i] > 0) {
+                        const float4 ax = am_ld4(sAx + slot_sp[g + 8 * i] * 64 + 16 * m + 4 * t);
+                        const float qv = slot_q[g + 8 * i];
+                        float4 v = am_get4(acc, i);
+                        v.x += fmaf(qv, aq.x, ax.x); v.y += fmaf(qv, aq.y, ax.y); v.z += fmaf(qv, aq.z, ax.z); v.w += fmaf(qv, aq.w, ax.w);
+                        am_st4(dst + (int64_t)(base + g + 8 * i) * HID + 16 * (m & 1) + 4 * t, v);
                     }
                 }
             }
