@@ -68,6 +68,8 @@ def parse_args():
                     help="big systems: far part of the message sum on tcgen05 tensor cores (3xTF32) instead of FP32 SIMT; 2 = auto (>= 16384 atoms)")
     ap.add_argument("--pair-tensor", type=int, default=0, choices=[0, 1],
                     help="small systems: electron-passing pair MLP on mma.sync 3xTF32 instead of FP32 SIMT (opt-in)")
+    ap.add_argument("--atom-tensor", type=int, default=1, choices=[0, 1],
+                    help="FP32 per-atom kernel (update MLP, projections: GEMMs over all atoms) on mma.sync 3xTF32 (default) instead of FP32 SIMT")
     ap.add_argument("--pair-const", type=int, default=2, choices=[0, 1, 2],
                     help="FP32 kernel set: 2 default (row-run GNN bundle kernel + pair-per-thread EPN kernel), 1 pair-per-thread everywhere, 0 round-1 warp-tile kernels")
     ap.add_argument("--dedup-far", type=int, default=1, choices=[0, 1], help="collapse species-equivalent far columns (exact; 0 = ablation)")
@@ -369,6 +371,7 @@ def make_engine(box, args, ckpt, precision=None, timing=True):
     if args.pair_tensor:
         eng.set_option("pair_tensor", 1)
     eng.set_option("pair_const", args.pair_const)
+    eng.set_option("atom_tensor", args.atom_tensor)
     return w, eng
 
 
@@ -513,9 +516,9 @@ def secondary_blocks(box, args, main_res, main_value):
             st = eng.last_stats
             out["config_" + wl] = {"workload": f"{n_sel} {'QM9 molecules' if wl == 'qm9_test' else 'SSI dimers'} of data/mixed, {ck}, pad N=41",
                                    "value": r["n_atoms"] * 10 / (r["ms_dev"] * 1e-3), "unit": UNIT, "ms_per_step": r["ms_dev"] / 10,
-                                   "e2e": r["n_atoms"] * 10 / (r["e2e_ms"] * 1e-3), "precision_used": st["precision_used"],
+                                   "e2e": r["n_atoms"] * 10 / (r["e2e_ms"] * 1e-3), "precision_used": st["precision_used"], "atom_tensor_used": st["atom_tensor_used"],
                                    "probe_max_abs_dq_fp32_vs_fp64_kernels": st["probe_err32"], "probe_max_abs_dq_mixed_vs_fp64_kernels": st["probe_err48"],
-                                   "note": "precision 0 (auto): cheapest kernel precision whose probe charges are within 2.5e-6 e of the FP64 kernels "
+                                   "note": "precision 0 (auto): cheapest candidate (FP32 with the tensor per-atom kernel, FP32 SIMT, mixed, FP64; -1 = not needed) whose probe charges are within 2.5e-6 e of the FP64 kernels "
                                            "(which agree with the float64 oracle to 1e-9, tests/test_gpu_parity.py)",
                                    "checks": conservation(r["q64"], offs, Q)}
             eng.close()
@@ -667,7 +670,7 @@ def run_b200(args):
         desc.update({"checkpoint": args.checkpoint, "parallelism": par,
                      "l2": "inputs larger than L2 (no flush needed)" if n_atoms * 16 > 126e6 else "inputs smaller than L2",
                      "atoms_per_gpu_per_step": n_atoms, "T": w.T, "precision": args.precision, "precision_used": int(acc["precision_used"] / args.steps),
-                     "gnn_far_tensor": args.gnn_far_tensor, "dedup_far": args.dedup_far, "pair_tensor": args.pair_tensor, "pair_const": args.pair_const})
+                     "gnn_far_tensor": args.gnn_far_tensor, "dedup_far": args.dedup_far, "pair_tensor": args.pair_tensor, "pair_const": args.pair_const, "atom_tensor": args.atom_tensor})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
                 "scaling": "strong" if sharded_system else "weak", "vs_baseline": None,

@@ -27,7 +27,8 @@ class Stats(C.Structure):
                 ("ms_total", C.c_float), ("ms_h2d", C.c_float), ("ms_neighbor", C.c_float), ("ms_gnn_pair", C.c_float),
                 ("ms_gnn_atom", C.c_float), ("ms_epn_pair", C.c_float), ("ms_epn_atom", C.c_float), ("ms_d2h", C.c_float),
                 ("n_far_dedup_rows", C.c_int64), ("n_gnn_near_slots", C.c_int64), ("n_gnn_far_slots", C.c_int64),
-                ("precision_used", C.c_int32), ("probe_err32", C.c_float), ("probe_err48", C.c_float)]
+                ("precision_used", C.c_int32), ("probe_err32", C.c_float), ("probe_err48", C.c_float),
+                ("atom_tensor_used", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -77,6 +77,8 @@ struct epnn_ctx {
     int dedup_far = 1;           // option "dedup_far": collapse species-equivalent far columns (exact)
     int pair_tensor = 0;         // option "pair_tensor": EPN bundle kernel on mma.sync 3xTF32 (precision 32 only)
     int atom_tensor = 1;         // option "atom_tensor": FP32 per-atom kernel on mma.sync 3xTF32 (epnn_atom_mma.cu); 0 = the FP32 SIMT warp-tile kernel
+    int auto_atom_tensor = 1;    // precision 0 (auto): what the probe decided for the FP32 per-atom kernel
+    int eff_atom_tensor = 1;     // per-atom kernel of the call in flight
     int pair_const = 2;          // option "pair_const": FP32 kernel set (0 warp-tile, 1 pair-per-thread everywhere, 2 default mix; see epnn_internal.cuh)
     std::vector<float> wf_host;  // host mirror of wf (pair_const passes a step's weights as kernel parameters)
     float* w2split = nullptr;    // [T][2][32][32]: hi / lo parts of W2^T of every message MLP (tensor-core far kernel)
@@ -401,7 +403,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     w.n_species = c->n_species;
     w.pair_tensor = c->pair_tensor && sizeof(R) == 4;
     w.pair_const = sizeof(R) == 4 ? c->pair_const : 0;
-    w.atom_tensor = c->atom_tensor;
+    w.atom_tensor = c->eff_atom_tensor;
     w.wf_host = c->wf_host.data(); w.wf_dev = c->wf;
     w.work_counter = c->d_flags + 7;
     w.near_counter = stats && !neighbors_only && c->bufs[B_MISC].p ? (unsigned long long*)c->bufs[B_MISC].p : nullptr;
@@ -754,22 +756,32 @@ static int probe_precision(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool 
         CU(c, cudaMemcpy(hQ.data(), Q, sizeof(float) * (size_t)ns, cudaMemcpyDeviceToHost));
         px = hx.data(); ps = hs.data(); pq = hQ.data();
     }
-    std::vector<double> q[3];
-    const int prec[3] = {64, 32, 48};
+    // candidates, cheapest first: FP32 with the per-atom kernel on the tensor path (if the option allows it), plain FP32 SIMT,
+    // mixed -- each measured against the FP64 kernels
+    std::vector<double> q[2];
     const int64_t hidden_atoms = c->hidden_atoms;
-    int rc = EPNN_OK;
-    for (int k = 0; k < 3 && rc == EPNN_OK; ++k) {
-        q[k].resize((size_t)na);
-        c->precision = prec[k];
-        rc = infer_impl(c, ns, off, true, px, ps, pq, npad_host, tmp.data(), q[k].data(), nullptr);
+    const int atom_tensor = c->atom_tensor;
+    auto run = [&](int prec, int tensor, std::vector<double>& out) {
+        out.resize((size_t)na);
+        c->precision = prec; c->atom_tensor = tensor;
+        return infer_impl(c, ns, off, true, px, ps, pq, npad_host, tmp.data(), out.data(), nullptr);
+    };
+    auto dist = [&]() { double e = 0; for (int64_t i = 0; i < na; ++i) e = fmax(e, fabs(q[1][i] - q[0][i])); return e; };
+    int rc = run(64, 0, q[0]);
+    int choice = 64, tensor = atom_tensor;
+    if (rc == EPNN_OK && atom_tensor) {
+        if ((rc = run(32, 1, q[1])) == EPNN_OK) { c->probe_err32 = dist(); if (c->probe_err32 <= c->auto_tol) choice = 32; }
     }
-    c->precision = 0;
+    if (rc == EPNN_OK && choice == 64) {
+        if ((rc = run(32, 0, q[1])) == EPNN_OK) { c->probe_err32 = dist(); if (c->probe_err32 <= c->auto_tol) { choice = 32; tensor = 0; } }
+    }
+    if (rc == EPNN_OK && choice == 64) {
+        if ((rc = run(48, 0, q[1])) == EPNN_OK) { c->probe_err48 = dist(); if (c->probe_err48 <= c->auto_tol) choice = 48; }
+    }
+    c->precision = 0; c->atom_tensor = atom_tensor;
     c->hidden_atoms = hidden_atoms;
     if (rc != EPNN_OK) return rc;
-    double e32 = 0, e48 = 0;
-    for (int64_t i = 0; i < na; ++i) { e32 = fmax(e32, fabs(q[1][i] - q[0][i])); e48 = fmax(e48, fabs(q[2][i] - q[0][i])); }
-    c->probe_err32 = e32; c->probe_err48 = e48;
-    c->auto_choice = e32 <= c->auto_tol ? 32 : (e48 <= c->auto_tol ? 48 : 64);
+    c->auto_choice = choice; c->auto_atom_tensor = tensor;
     return EPNN_OK;
 }
 
@@ -786,6 +798,7 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
         if (rc != EPNN_OK) return rc;
     }
     c->eff_precision = c->precision == 0 ? c->auto_choice : c->precision;
+    c->eff_atom_tensor = c->precision == 0 ? c->auto_atom_tensor : c->atom_tensor;
     CU(c, cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     std::vector<int64_t> bounds;
@@ -891,6 +904,7 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
         stats->n_launches = n_launch;
         stats->precision_used = c->eff_precision;
         stats->probe_err32 = (float)c->probe_err32; stats->probe_err48 = (float)c->probe_err48;
+        stats->atom_tensor_used = c->eff_precision == 32 ? c->eff_atom_tensor : 0;
     }
     tm.finish(stats);
     if (bounds.size() != 2) c->hidden_atoms = 0;       // hidden state only meaningful for single-chunk calls

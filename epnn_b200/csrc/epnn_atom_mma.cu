@@ -22,7 +22,7 @@
 #include "epnn_internal.cuh"
 
 #ifndef AM_NW
-#define AM_NW 8
+#define AM_NW 6
 #endif
 #define AM_FRAG 128                              // words per B fragment (32 lanes x 4)
 #define AM_B1 0                                  // [8 kb][4 nt]  first update layer  [U3 U1_h ; W3 U1_M]
@@ -32,23 +32,48 @@
 #define AM_VEC (AM_BH + 24 * AM_FRAG)            // cb[32] g[32] c2[32] c3[48] aq[64]
 #define AM_AX (AM_VEC + 208)                     // [MAX_SPECIES][64]
 #define AM_SLOT (AM_AX + MAX_SPECIES * 64)       // per warp: q[32] np[32] sp[32] ns[32]
-#define AM_SMEM_WORDS (AM_SLOT + AM_NW * 128)
+#define AM_BAR (AM_SLOT + AM_NW * 128)           // per warp: one mbarrier (8 bytes) -- "this warp's input tile has landed"
+#define AM_STAGE ((AM_BAR + 2 * AM_NW + 31) / 32 * 32)   // (128-byte aligned) per warp: the tile's l2 rows [32][32] | plane 0 of its S rows [32][32], filled by bulk copies
+#define AM_SMEM_WORDS (AM_STAGE + AM_NW * 2048)
 
 #ifdef EPNN_CPU_EMU
 __device__ __forceinline__ void am_mma(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
     const unsigned b[2] = {b0, b1};
     emu_mma_m16n8k8_tf32(d, a, b);
 }
-__device__ __forceinline__ void am_prefetch(const void*) {}
 struct am_u4 { unsigned x, y, z, w; };
+// bulk-copy shim: the issuing lane copies at once; the consumers' "wait" is the warp barrier that follows
+__device__ __forceinline__ void am_bar_init(void*) {}
+__device__ __forceinline__ void am_bar_expect(void*, unsigned) {}
+__device__ __forceinline__ void am_bulk(void* dst, const void* src, unsigned bytes, void*) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void am_bar_wait(void*, unsigned) { __syncwarp(); }
 #else
 __device__ __forceinline__ void am_mma(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ void am_prefetch(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 typedef uint4 am_u4;
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (one elected lane issues, all lanes wait)
+__device__ __forceinline__ unsigned am_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void am_bar_init(void* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(am_saddr(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void am_bar_expect(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(am_saddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void am_bulk(void* dst, const void* src, unsigned bytes, void* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(am_saddr(dst)), "l"(src), "r"(bytes), "r"(am_saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void am_bar_wait(void* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(am_saddr(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
 #endif
 
 // x = hi + lo: hi = x rounded to TF32 (nearest, ties away from zero: integer add on the magnitude bits), lo = x - hi (exact)
@@ -167,6 +192,21 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
     const bool first = a.mode & ATOM_FIRST, write_h = a.mode & ATOM_WRITE_H;
     const bool proj_gemm = do_proj && !a.h_is_zero;
     const int nthr = AM_NW * 32;
+    // input pipeline: the warp's NEXT tile (l2 rows and / or plane 0 of the S rows: 4 KB each, contiguous in global memory) is
+    // fetched by two bulk copies as soon as the current tile's inputs have been read out of the stage
+    float* st_l2 = reinterpret_cast<float*>(sm + AM_STAGE + warp * 2048);
+    float* st_S = st_l2 + 1024;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm + AM_BAR) + warp;
+    const bool need_l2 = (do_upd && !first) || (proj_gemm && !do_upd), need_S = do_upd;
+    const int n_tiles = (a.n_atoms + 31) / 32;
+    auto fetch = [&](int tile) {                         // one lane
+        const int rows = min(32, a.n_atoms - tile * 32);
+        const unsigned bytes = (unsigned)rows * HID * sizeof(float);
+        am_bar_expect(bar, bytes * ((need_l2 ? 1u : 0u) + (need_S ? 1u : 0u)));
+        if (need_l2) am_bulk(st_l2, a.l2 + (int64_t)tile * 32 * HID, bytes, bar);
+        if (need_S) am_bulk(st_S, a.Spart + (int64_t)tile * 32 * HID, bytes, bar);
+    };
+    if (lane == 0) am_bar_init(bar);
     if (do_upd) {
         am_stage(sm + AM_B1, a.HG, HID, 0, 8, 4, threadIdx.x, nthr);
         am_stage(sm + AM_B2, a.upd.U2, HID, 0, 4, 4, threadIdx.x, nthr);
@@ -181,18 +221,14 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
     }
     __syncthreads();
 
-    const int n_tiles = (a.n_atoms + 31) / 32;
-    for (int tile = blockIdx.x * AM_NW + warp; tile < n_tiles; tile += gridDim.x * AM_NW) {
+    const int tile0 = blockIdx.x * AM_NW + warp, tstep = gridDim.x * AM_NW;
+    if (lane == 0 && tile0 < n_tiles) fetch(tile0);
+    unsigned parity = 0;
+    for (int tile = tile0; tile < n_tiles; tile += tstep) {
         const int base = tile * 32;
         const int me = base + lane;
         const bool me_ok = me < a.n_atoms;
-        {   // this warp's NEXT tile -> L2 while the current one computes (one 128-byte row per lane)
-            const int64_t nb = (int64_t)(tile + gridDim.x * AM_NW) * 32;
-            if (nb + lane < a.n_atoms) {
-                if ((do_upd && !first) || (proj_gemm && !do_upd)) am_prefetch(a.l2 + (nb + lane) * HID);
-                if (do_upd) am_prefetch(a.Spart + (nb + lane) * HID);
-            }
-        }
+        const bool more = tile + tstep < n_tiles;
         // ---------------- per-slot scalars and the charge update (lane = slot)
         {
             int sp = 0, ns = 0; float npf = 0.f;         // ns = 0 marks a slot this launch does not touch
@@ -225,11 +261,16 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
             slot_sp[lane] = sp; slot_ns[lane] = ns; slot_np[lane] = npf; slot_q[lane] = (float)qv;
         }
         __syncwarp();
-        if (!do_upd && !do_proj) continue;
         int rns[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) rns[i] = slot_ns[g + 8 * i];
-        if (SCOPED && a.scope && !__any_sync(0xffffffffu, rns[0] | rns[1] | rns[2] | rns[3])) { __syncwarp(); continue; }
+        am_bar_wait(bar, parity);                        // the tile's inputs are in the stage
+        parity ^= 1u;
+        if (SCOPED && a.scope && !__any_sync(0xffffffffu, rns[0] | rns[1] | rns[2] | rns[3])) {      // nothing of this tile belongs to the launch
+            __syncwarp();
+            if (lane == 0 && more) fetch(tile + tstep);
+            continue;
+        }
 
         unsigned ah[2][4][4], al[2][4][4];               // A fragments of the layer about to run (k blocks 0..3)
         float z[2][2][2][4];                             // a layer's 32 output columns: two column pairs
@@ -245,12 +286,14 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
                     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
                     const int64_t at = base + g + 8 * i;
                     if (rns[i] > 0) {
-                        if (j < 2) x = am_ld4(a.l2 + at * HID + 16 * j + 4 * t);
-                        else
-                            for (int sp = 0; sp < rns[i]; ++sp) {       // partial planes summed in fixed order
+                        if (j < 2) x = am_ld4(st_l2 + (g + 8 * i) * HID + 16 * j + 4 * t);
+                        else {
+                            x = am_ld4(st_S + (g + 8 * i) * HID + 16 * (j - 2) + 4 * t);
+                            for (int sp = 1; sp < rns[i]; ++sp) {       // large systems: further partial planes, summed in fixed order
                                 const float4 p = am_ld4(a.Spart + ((int64_t)sp * a.n_atoms + at) * HID + 16 * (j - 2) + 4 * t);
                                 x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w;
                             }
+                        }
                     }
                     am_put4(zz[0], i, x);
                 }
@@ -259,6 +302,8 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
 #pragma unroll
                 for (int m = 0; m < 2; ++m) am_pair<2>(ah1, al1, sm + AM_B1, 2 * j, 4, 2 * m, lane, z[m]);
             }
+            __syncwarp();                                // every lane has read its inputs: the stage is free for the next tile
+            if (lane == 0 && more) fetch(tile + tstep);
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
                 const float4 cv = am_ld4(scb + 16 * m + 4 * t), gv = am_ld4(sg + 16 * m + 4 * t);
@@ -308,10 +353,14 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {            // l2 of the last message-passing step
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rns[i] > 0) v = am_ld4(a.l2 + (int64_t)(base + g + 8 * i) * HID + 16 * m + 4 * t);
+                    if (rns[i] > 0) v = am_ld4(st_l2 + (g + 8 * i) * HID + 16 * m + 4 * t);
                     am_put4(z[m], i, v);
                 }
+            __syncwarp();
+            if (lane == 0 && more) fetch(tile + tstep);
             am_to_a<2>(z, ah, al);
+        } else {                                         // no product in this launch: nothing was staged
+            if (lane == 0 && more) fetch(tile + tstep);
         }
 
         if (do_proj) {

@@ -63,7 +63,8 @@ typedef struct epnn_stats {
     int64_t n_gnn_far_slots;  /*   exact de-duplication applied, + pad slots) the small-system GNN kernel evaluated, summed over the T steps */
     int32_t precision_used;   /* 32, 48 (mixed) or 64: what "precision" resolved to for this call */
     float probe_err32;        /* "precision" 0 (auto): max |dq| of the FP32 / mixed kernels against the FP64 kernels on the */
-    float probe_err48;        /*   probe sample of the first call (e); -1 if no probe ran */
+    float probe_err48;        /*   probe sample of the first call (e); -1 if that candidate was not needed / no probe ran */
+    int32_t atom_tensor_used; /* 1 if the FP32 per-atom kernel of this call ran on the warp-level tensor path ("atom_tensor") */
 } epnn_stats;
 
 /* Build a context on CUDA device `device` and upload the model once.
@@ -86,8 +87,8 @@ const char* epnn_last_error(const epnn_ctx* ctx);
 /* Options: "precision" 32 (default: FP32 SIMT kernels, charges carried in FP64), 48 (mixed: FP32 pair kernels around an FP64
  * per-atom kernel -- update MLP, first-layer projections and the hidden state in FP64), 64 (every kernel in FP64) or
  * 0 (auto: the first call runs a bounded prefix of its systems -- at most 64 systems / 8192 atoms -- through all three and
- * keeps the cheapest precision whose charges are within "auto_tol", default 2.5e-6 e, of the FP64 kernels; sticky for the
- * ctx; reported in epnn_stats).  The reference's 1e-5 e tolerance needs 32 for decay_model_weights, 48 for model2_weights
+ * keeps the cheapest candidate (FP32 with the tensor per-atom kernel if "atom_tensor" is on, FP32 SIMT, mixed) whose charges
+ * are within "auto_tol", default 2.5e-6 e, of the FP64 kernels; sticky for the ctx; reported in epnn_stats).  The reference's 1e-5 e tolerance needs 32 for decay_model_weights, 48 for model2_weights
  * and 64 for model_weights (|h| reaches 150 there: FP32 pair kernels alone are 6e-5 off); "timing" 0/1; "chunk_atoms" (internal batch size);
  * "keep_hidden" 0/1 (retain the final GNN hidden state for epnn_get_hidden);
  * "dedup_far" 1 (default) / 0: far columns whose v rows are identical (same system, same species, same hidden
