@@ -21,20 +21,30 @@
 // shared memory: fragment (kb, nt) = 32 lanes x {b0 hi, b1 hi, b0 lo, b1 lo}, one conflict-free LDS.128 per lane feeds six MMAs.
 #include "epnn_internal.cuh"
 
-#ifndef AM_NW
-#define AM_NW 6
+#ifndef AM_CHAIN
+#define AM_CHAIN 1                               // 1: the hi*hi blocks of one am_pair call chain inside the tensor core; 0: each block is added on the FP32 pipe
+#endif
+#ifndef AM_ROUND_LO
+#define AM_ROUND_LO 0                            // 1: lo rounded to TF32 (nearest) instead of truncated by the tensor core
 #endif
 #define AM_FRAG 128                              // words per B fragment (32 lanes x 4)
-#define AM_B1 0                                  // [8 kb][4 nt]  first update layer  [U3 U1_h ; W3 U1_M]
-#define AM_B2 (AM_B1 + 32 * AM_FRAG)             // [4][4]        second update layer U2
-#define AM_B3 (AM_B2 + 16 * AM_FRAG)             // [4][8]        projections of the next pair kernel, U3 Ah64 (u | v)
-#define AM_BH (AM_B3 + 32 * AM_FRAG)             // [4][6]        h = U3^T l2 (last message-passing step)
-#define AM_VEC (AM_BH + 24 * AM_FRAG)            // cb[32] g[32] c2[32] c3[48] aq[64]
-#define AM_AX (AM_VEC + 208)                     // [MAX_SPECIES][64]
-#define AM_SLOT (AM_AX + MAX_SPECIES * 64)       // per warp: q[32] np[32] sp[32] ns[32]
-#define AM_BAR (AM_SLOT + AM_NW * 128)           // per warp: one mbarrier (8 bytes) -- "this warp's input tile has landed"
-#define AM_STAGE ((AM_BAR + 2 * AM_NW + 31) / 32 * 32)   // (128-byte aligned) per warp: the tile's l2 rows [32][32] | plane 0 of its S rows [32][32], filled by bulk copies
-#define AM_SMEM_WORDS (AM_STAGE + AM_NW * 2048)
+// Shared-memory layout (32-bit words) of the two instantiations: UPD = launches that finish a message-passing step (all three
+// layers, 6 warps x 168 registers, 2 CTAs per SM), !UPD = the projections between two electron-passing passes (one layer,
+// 8 warps x 128 registers, 2 CTAs per SM: the serial CSR walk of the charge update wants the warps).
+template <bool UPD> struct AmL {
+    static constexpr int NW = UPD ? 6 : 8;
+    static constexpr int B1 = 0;                                       // [8 kb][4 nt]  first update layer  [U3 U1_h ; W3 U1_M]
+    static constexpr int B2 = B1 + (UPD ? 32 * AM_FRAG : 0);           // [4][4]        second update layer U2
+    static constexpr int B3 = B2 + (UPD ? 16 * AM_FRAG : 0);           // [4][8]        projections of the next pair kernel, U3 Ah64 (u | v)
+    static constexpr int BH = B3 + 32 * AM_FRAG;                       // [4][6]        h = U3^T l2 (last message-passing step)
+    static constexpr int VEC = BH + (UPD ? 24 * AM_FRAG : 0);          // cb[32] g[32] c2[32] c3[48] aq[64]
+    static constexpr int AX = VEC + 208;                               // [MAX_SPECIES][64]
+    static constexpr int SLOT = AX + MAX_SPECIES * 64;                 // per warp: q[32] np[32] sp[32] ns[32]
+    static constexpr int BAR = SLOT + NW * 128;                        // per warp: one mbarrier (8 bytes) -- "this warp's input tile has landed"
+    static constexpr int STAGE = (BAR + 2 * NW + 31) / 32 * 32;        // per warp (128-byte aligned): the tile's l2 rows [32][32] (| plane 0 of
+    static constexpr int STAGE_W = UPD ? 2048 : 1024;                  //   its S rows [32][32]), filled by bulk copies
+    static constexpr int WORDS = STAGE + NW * STAGE_W;
+};
 
 #ifdef EPNN_CPU_EMU
 __device__ __forceinline__ void am_mma(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
@@ -80,7 +90,11 @@ __device__ __forceinline__ void am_bar_wait(void* bar, unsigned parity) {
 // rounded to TF32 the same way -- the tensor core would truncate it
 __device__ __forceinline__ void am_split(float x, unsigned& hi, unsigned& lo) {
     hi = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+#if AM_ROUND_LO
     lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xFFFFE000u;
+#else
+    lo = __float_as_uint(x - __uint_as_float(hi));
+#endif
 }
 __device__ __forceinline__ int am_map(int blk, int t, int h) { return 16 * (blk >> 1) + 4 * t + 2 * (blk & 1) + h; }
 
@@ -115,6 +129,13 @@ __device__ __forceinline__ void am_pair(const unsigned (&ah)[2][KB][4], const un
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
         for (int n = 0; n < 2; ++n) corr[mt][n][0] = corr[mt][n][1] = corr[mt][n][2] = corr[mt][n][3] = 0.f;
+#if AM_CHAIN
+    float mainacc[2][2][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int n = 0; n < 2; ++n) mainacc[mt][n][0] = mainacc[mt][n][1] = mainacc[mt][n][2] = mainacc[mt][n][3] = 0.f;
+#endif
 #pragma unroll
     for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
@@ -124,10 +145,14 @@ __device__ __forceinline__ void am_pair(const unsigned (&ah)[2][KB][4], const un
             for (int mt = 0; mt < 2; ++mt) {
                 am_mma(corr[mt][n], al[mt][kb], b.x, b.y);
                 am_mma(corr[mt][n], ah[mt][kb], b.z, b.w);
+#if AM_CHAIN
+                am_mma(mainacc[mt][n], ah[mt][kb], b.x, b.y);
+#else
                 float tmp[4] = {0.f, 0.f, 0.f, 0.f};
                 am_mma(tmp, ah[mt][kb], b.x, b.y);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) acc[mt][n][e] += tmp[e];
+#endif
             }
         }
 #pragma unroll
@@ -135,7 +160,13 @@ __device__ __forceinline__ void am_pair(const unsigned (&ah)[2][KB][4], const un
 #pragma unroll
         for (int n = 0; n < 2; ++n)
 #pragma unroll
-            for (int e = 0; e < 4; ++e) acc[mt][n][e] += corr[mt][n][e];
+            for (int e = 0; e < 4; ++e) {
+#if AM_CHAIN
+                acc[mt][n][e] += mainacc[mt][n][e] + corr[mt][n][e];
+#else
+                acc[mt][n][e] += corr[mt][n][e];
+#endif
+            }
 }
 
 // C-fragment values of NP column pairs -> A fragments of the next layer: k block 2m + n, a0 = d0, a1 = d2, a2 = d1, a3 = d3
@@ -172,31 +203,34 @@ __device__ __forceinline__ float4 am_ld4(const float* p) { return *reinterpret_c
 __device__ __forceinline__ void am_st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 __device__ __forceinline__ float am_relu(float x) { return x > 0.f ? x : 0.f; }
 
-template <bool SCOPED>
-__global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<float, float> a) {
+template <bool SCOPED, bool UPD>
+__global__ void __launch_bounds__(AmL<UPD>::NW * 32, 2) atom_mma_kernel(const AtomArgs<float, float> a) {
+    typedef AmL<UPD> L;
+    constexpr int AM_NW = L::NW;
 #ifdef EPNN_CPU_EMU
     unsigned* sm = reinterpret_cast<unsigned*>(emu_smem);
 #else
     extern __shared__ __align__(16) unsigned sm[];
 #endif
-    float* sv = reinterpret_cast<float*>(sm + AM_VEC);
+    float* sv = reinterpret_cast<float*>(sm + L::VEC);
     float* scb = sv, *sg = sv + 32, *sc2 = sv + 64, *sc3 = sv + 96, *saq = sv + 144;
-    float* sAx = reinterpret_cast<float*>(sm + AM_AX);
+    float* sAx = reinterpret_cast<float*>(sm + L::AX);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    float* slot_q = reinterpret_cast<float*>(sm + AM_SLOT + warp * 128);
+    float* slot_q = reinterpret_cast<float*>(sm + L::SLOT + warp * 128);
     float* slot_np = slot_q + 32;
     int* slot_sp = reinterpret_cast<int*>(slot_np + 32);
     int* slot_ns = slot_sp + 32;
 
-    const bool do_upd = a.mode & ATOM_UPDATE, do_q = a.mode & ATOM_QUPDATE, do_proj = a.mode & ATOM_PROJECT;
+    constexpr bool do_upd = UPD;                         // == (a.mode & ATOM_UPDATE): the launcher picks the instantiation
+    const bool do_q = a.mode & ATOM_QUPDATE, do_proj = a.mode & ATOM_PROJECT;
     const bool first = a.mode & ATOM_FIRST, write_h = a.mode & ATOM_WRITE_H;
     const bool proj_gemm = do_proj && !a.h_is_zero;
     const int nthr = AM_NW * 32;
     // input pipeline: the warp's NEXT tile (l2 rows and / or plane 0 of the S rows: 4 KB each, contiguous in global memory) is
     // fetched by two bulk copies as soon as the current tile's inputs have been read out of the stage
-    float* st_l2 = reinterpret_cast<float*>(sm + AM_STAGE + warp * 2048);
+    float* st_l2 = reinterpret_cast<float*>(sm + L::STAGE + warp * L::STAGE_W);
     float* st_S = st_l2 + 1024;
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm + AM_BAR) + warp;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm + L::BAR) + warp;
     const bool need_l2 = (do_upd && !first) || (proj_gemm && !do_upd), need_S = do_upd;
     const int n_tiles = (a.n_atoms + 31) / 32;
     auto fetch = [&](int tile) {                         // one lane
@@ -208,14 +242,14 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
     };
     if (lane == 0) am_bar_init(bar);
     if (do_upd) {
-        am_stage(sm + AM_B1, a.HG, HID, 0, 8, 4, threadIdx.x, nthr);
-        am_stage(sm + AM_B2, a.upd.U2, HID, 0, 4, 4, threadIdx.x, nthr);
-        if (write_h) am_stage(sm + AM_BH, a.upd.U3, HD, 0, 4, 6, threadIdx.x, nthr);
+        am_stage(sm + L::B1, a.HG, HID, 0, 8, 4, threadIdx.x, nthr);
+        am_stage(sm + L::B2, a.upd.U2, HID, 0, 4, 4, threadIdx.x, nthr);
+        if (write_h) am_stage(sm + L::BH, a.upd.U3, HD, 0, 4, 6, threadIdx.x, nthr);
         if (threadIdx.x < HID) { scb[threadIdx.x] = a.cb[threadIdx.x]; sg[threadIdx.x] = a.g[threadIdx.x]; sc2[threadIdx.x] = a.upd.c2[threadIdx.x]; }
         if (threadIdx.x < HD) sc3[threadIdx.x] = a.upd.c3[threadIdx.x];
     }
     if (do_proj) {
-        if (proj_gemm) am_stage(sm + AM_B3, a.Pf, 64, 0, 4, 8, threadIdx.x, nthr);
+        if (proj_gemm) am_stage(sm + L::B3, a.Pf, 64, 0, 4, 8, threadIdx.x, nthr);
         for (int f = threadIdx.x; f < MAX_SPECIES * 64; f += nthr) sAx[f] = a.Ax[f];
         if (threadIdx.x < 64) saq[threadIdx.x] = a.Aq64[threadIdx.x];
     }
@@ -300,7 +334,7 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
                 unsigned ah1[2][2][4], al1[2][2][4];
                 am_to_a<1>(zz, ah1, al1);
 #pragma unroll
-                for (int m = 0; m < 2; ++m) am_pair<2>(ah1, al1, sm + AM_B1, 2 * j, 4, 2 * m, lane, z[m]);
+                for (int m = 0; m < 2; ++m) am_pair<2>(ah1, al1, sm + L::B1, 2 * j, 4, 2 * m, lane, z[m]);
             }
             __syncwarp();                                // every lane has read its inputs: the stage is free for the next tile
             if (lane == 0 && more) fetch(tile + tstep);
@@ -321,7 +355,7 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
                 am_zero(z[m]);
-                am_pair<4>(ah, al, sm + AM_B2, 0, 4, 2 * m, lane, z[m]);
+                am_pair<4>(ah, al, sm + L::B2, 0, 4, 2 * m, lane, z[m]);
                 const float4 cv = am_ld4(sc2 + 16 * m + 4 * t);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -337,7 +371,7 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
                 for (int m = 0; m < 3; ++m) {
                     float ha[2][2][4];
                     am_zero(ha);
-                    am_pair<4>(ah, al, sm + AM_BH, 0, 6, 2 * m, lane, ha);
+                    am_pair<4>(ah, al, sm + L::BH, 0, 6, 2 * m, lane, ha);
                     const float4 cv = am_ld4(sc3 + 16 * m + 4 * t);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -368,7 +402,7 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
             for (int m = 0; m < 4; ++m) {                // column pairs 0, 1 -> u (a_i block), 2, 3 -> v (a_j block, + b1)
                 float acc[2][2][4];
                 am_zero(acc);
-                if (proj_gemm) am_pair<4>(ah, al, sm + AM_B3, 0, 8, 2 * m, lane, acc);
+                if (proj_gemm) am_pair<4>(ah, al, sm + L::B3, 0, 8, 2 * m, lane, acc);
                 float* dst = m < 2 ? a.u : a.v;
                 const float4 aq = am_ld4(saq + 16 * m + 4 * t);
 #pragma unroll
@@ -388,15 +422,20 @@ __global__ void __launch_bounds__(AM_NW * 32, 2) atom_mma_kernel(const AtomArgs<
 }
 
 #ifndef EPNN_CPU_EMU
-cudaError_t launch_atom_mma(const Workspace& w, const AtomArgs<float, float>& aa, cudaStream_t st, int* nl) {
-    const size_t smem = sizeof(unsigned) * AM_SMEM_WORDS;
-    cudaError_t e = cudaFuncSetAttribute(aa.scope ? atom_mma_kernel<true> : atom_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <bool SCOPED, bool UPD>
+static cudaError_t launch_atom_mma_t(const Workspace& w, const AtomArgs<float, float>& aa, cudaStream_t st) {
+    typedef AmL<UPD> L;
+    const size_t smem = sizeof(unsigned) * L::WORDS;
+    cudaError_t e = cudaFuncSetAttribute(atom_mma_kernel<SCOPED, UPD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int grid = div_up(div_up(w.n_atoms, 32), AM_NW);
+    int grid = div_up(div_up(w.n_atoms, 32), L::NW);
     if (grid > 2 * w.sm_count) grid = 2 * w.sm_count;
-    if (aa.scope) atom_mma_kernel<true><<<grid, AM_NW * 32, smem, st>>>(aa);
-    else atom_mma_kernel<false><<<grid, AM_NW * 32, smem, st>>>(aa);
-    ++*nl;
+    atom_mma_kernel<SCOPED, UPD><<<grid, L::NW * 32, smem, st>>>(aa);
     return cudaGetLastError();
+}
+cudaError_t launch_atom_mma(const Workspace& w, const AtomArgs<float, float>& aa, cudaStream_t st, int* nl) {
+    ++*nl;
+    if (aa.mode & ATOM_UPDATE) return aa.scope ? launch_atom_mma_t<true, true>(w, aa, st) : launch_atom_mma_t<false, true>(w, aa, st);
+    return aa.scope ? launch_atom_mma_t<true, false>(w, aa, st) : launch_atom_mma_t<false, false>(w, aa, st);
 }
 #endif

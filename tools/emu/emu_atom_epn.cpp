@@ -44,7 +44,8 @@ extern "C" int emu_atom_mma_kernel(int mode, int h_is_zero, int n_atoms, int nsp
     aa.rowptr = rowptr; aa.col = col; aa.pid = pid; aa.delta = delta; aa.q = q;
     aa.Pf = wp; aa.Aq64 = wp + HID * 64; aa.Ax = aa.Aq64 + 64;
     aa.u = u; aa.v = v; aa.q_out = q_out; aa.q_out64 = q_out64;
-    emu_launch_grid(2, AM_NW, AM_SMEM_WORDS + 8, [&] { atom_mma_kernel<false>(aa); });
+    if (mode & ATOM_UPDATE) emu_launch_grid(2, AmL<true>::NW, AmL<true>::WORDS + 8, [&] { atom_mma_kernel<false, true>(aa); });
+    else emu_launch_grid(2, AmL<false>::NW, AmL<false>::WORDS + 8, [&] { atom_mma_kernel<false, false>(aa); });
     return 0;
 }
 
