@@ -76,6 +76,7 @@ struct epnn_ctx {
     int far_tc_impl = 1;         // option "gnn_far_tensor_impl": 1 round-1 kernel (epnn_gnn_tc.cu), 2 warp-specialised (epnn_gnn_tc2.cu)
     int dedup_far = 1;           // option "dedup_far": collapse species-equivalent far columns (exact)
     int pair_tensor = 0;         // option "pair_tensor": EPN bundle kernel on mma.sync 3xTF32 (precision 32 only)
+    int fused_prep = 1;          // option "fused_prep": chunks of small systems only build their lists with the two bundle kernels of epnn_bundle_prep.cu
     int atom_tensor = 1;         // option "atom_tensor": FP32 per-atom kernel on mma.sync 3xTF32 (epnn_atom_mma.cu); 0 = the FP32 SIMT warp-tile kernel
     int auto_atom_tensor = 1;    // precision 0 (auto): what the probe decided for the FP32 per-atom kernel
     int eff_atom_tensor = 1;     // per-atom kernel of the call in flight
@@ -104,7 +105,7 @@ static thread_local std::string g_create_err;
 enum {
     B_XYZ, B_SPECIES, B_OFF, B_Q, B_NPAD, B_ATOMSYS, B_DEG, B_DEGU, B_ROWPTR, B_USTART, B_COL, B_PID, B_PI, B_PJ, B_PD,
     B_E, B_NEAR, B_BUNDLE, B_RGL, B_FARCNT, B_FAROFF, B_FARLIST, B_FAR0CNT, B_FAR0OFF, B_FAR0LIST, B_FAR0W, B_REP, B_ATOMB0, B_BNAT, B_PERM, B_LARGESYS, B_GRID, B_CELLCNT, B_CELLSTART, B_CELLATOMS, B_DTMP, B_H, B_L2, B_S, B_U, B_V, B_DELTA, B_QD, B_SCANTMP, B_CNTL, B_RGLOFF,
-    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_ROWBLK, B_ROWL, B_ARGS, B_DEGALL, B_ACTIVE, B_XYZ_1, B_SPECIES_1, B_Q_1, B_OUT32_1, B_OUT64_1, B_OFFIN_1, B_COUNT
+    B_OUT32, B_OUT64, B_MISC, B_OFFIN, B_SPTAB, B_SPSTAMP, B_ROWBLK, B_ROWL, B_ARGS, B_DEGALL, B_ACTIVE, B_XYZ_1, B_SPECIES_1, B_Q_1, B_OUT32_1, B_OUT64_1, B_OFFIN_1, B_BPMASK, B_BPTOT, B_BPOFF, B_COUNT
 };
 
 static int fail(epnn_ctx* c, int code, const char* fmt, ...) {
@@ -283,6 +284,7 @@ extern "C" int epnn_set_option(epnn_ctx* c, const char* key, double value) {
     else if (k == "dedup_far") c->dedup_far = value != 0;
     else if (k == "pair_tensor") c->pair_tensor = value != 0;
     else if (k == "atom_tensor") c->atom_tensor = value != 0;
+    else if (k == "fused_prep") c->fused_prep = value != 0;
     else if (k == "pair_const") {
         if (value != 0 && value != 1 && value != 2) return fail(c, EPNN_E_INVALID, "pair_const must be 0, 1 or 2");
         c->pair_const = (int)value;
@@ -495,14 +497,27 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     CU(c, cudaGetLastError());
     CU(c, launch_scan_i32(cnt_l, rgl_off, n_sys, scantmp, st, n_launch));
     CU(c, launch_prep(w, st, n_launch));
-    CU(c, launch_cell_build(w, cw, scantmp, st, n_launch));
-    CU(c, launch_nbr_count(w, cw, st, n_launch));
-    CU(c, launch_scan_i32(w.deg, w.rowptr, n_atoms, scantmp, st, n_launch));
-    CU(c, launch_scan_i32(w.degU, w.ustart, n_atoms, scantmp, st, n_launch));
-    CU(c, launch_far_count(w, far_cnt, atom_b0, st, n_launch));
-    CU(c, launch_scan_i32(far_cnt, w.far_off, n_atoms, scantmp, st, n_launch));
-    collect_totals_kernel<<<1, 1, 0, st>>>(w.rowptr, w.ustart, w.far_off, n_atoms, rgl_off, n_sys, c->d_flags);
-    ++*n_launch;
+    // Chunks of small systems only (the batched-molecule path): one warp per bundle builds every list from a 48-bit neighbour
+    // mask per row (epnn_bundle_prep.cu); chunks with a larger system take the general thread-per-atom kernels.
+    const bool fused = c->fused_prep && !has_large && w.n_bundles > 0;
+    BundlePrepWork bw;
+    memset(&bw, 0, sizeof(bw));
+    if (fused) {
+        ENS(B_BPMASK, sizeof(unsigned long long) * (size_t)n_atoms, bw.mask, unsigned long long*);
+        ENS(B_BPTOT, sizeof(int) * 4 * (size_t)w.n_bundles, bw.btot, int*);
+        ENS(B_BPOFF, sizeof(int) * 4 * ((size_t)w.n_bundles + 1), bw.boff, int*);
+        bw.atom_b0 = atom_b0;
+        CU(c, launch_bundle_prep_count(w, bw, scantmp, c->d_flags, st, n_launch));
+    } else {
+        CU(c, launch_cell_build(w, cw, scantmp, st, n_launch));
+        CU(c, launch_nbr_count(w, cw, st, n_launch));
+        CU(c, launch_scan_i32(w.deg, w.rowptr, n_atoms, scantmp, st, n_launch));
+        CU(c, launch_scan_i32(w.degU, w.ustart, n_atoms, scantmp, st, n_launch));
+        CU(c, launch_far_count(w, far_cnt, atom_b0, st, n_launch));
+        CU(c, launch_scan_i32(far_cnt, w.far_off, n_atoms, scantmp, st, n_launch));
+        collect_totals_kernel<<<1, 1, 0, st>>>(w.rowptr, w.ustart, w.far_off, n_atoms, rgl_off, n_sys, c->d_flags);
+        ++*n_launch;
+    }
     CU(c, cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));
     if (c->h_flags[0] & 1) return fail(c, EPNN_E_INVALID, "npad smaller than the number of atoms for at least one system");
@@ -593,14 +608,20 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
         CU(c, launch_sp_tab_build(w, st, n_launch));
         w.dedup_rows = stats ? (unsigned long long*)c->bufs[B_MISC].p + 1 : nullptr;
     }
-    if (cw.n_large) ENS(B_DTMP, sizeof(double) * (size_t)(w.nnz + 1), cw.Dtmp, double*);
-    CU(c, launch_nbr_fill(w, cw, st, n_launch));
-    CU(c, launch_far_fill(w, atom_b0, st, n_launch));
-    if (w.pair_const == 2) CU(c, launch_csr_rowl(w, atom_b0, st, n_launch));
-    // species-compressed far list (needs the filled CSR): counts -> offsets -> slots; its size is bounded, no host sync
-    CU(c, launch_far0_count(w, far0_cnt, st, n_launch));
-    CU(c, launch_scan_i32(far0_cnt, w.far0_off, n_atoms, scantmp, st, n_launch));
-    CU(c, launch_far0_fill(w, atom_b0, st, n_launch));
+    if (fused) {
+        CU(c, launch_bundle_prep_fill(w, bw, st, n_launch));
+        CU(c, launch_edge_desc(w, st, n_launch));
+        CU(c, launch_tile_perm(w, atom_b0, st, n_launch));
+    } else {
+        if (cw.n_large) ENS(B_DTMP, sizeof(double) * (size_t)(w.nnz + 1), cw.Dtmp, double*);
+        CU(c, launch_nbr_fill(w, cw, st, n_launch));
+        CU(c, launch_far_fill(w, atom_b0, st, n_launch));
+        if (w.pair_const == 2) CU(c, launch_csr_rowl(w, atom_b0, st, n_launch));
+        // species-compressed far list (needs the filled CSR): counts -> offsets -> slots; its size is bounded, no host sync
+        CU(c, launch_far0_count(w, far0_cnt, st, n_launch));
+        CU(c, launch_scan_i32(far0_cnt, w.far0_off, n_atoms, scantmp, st, n_launch));
+        CU(c, launch_far0_fill(w, atom_b0, st, n_launch));
+    }
     tm.mark(2);
     if (stats) {
         stats->n_pairs_e += w.P;

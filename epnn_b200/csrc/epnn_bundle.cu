@@ -603,13 +603,20 @@ __global__ void tile_perm_kernel(int64_t P, const int* __restrict__ pair_i, cons
 }
 
 #ifndef EPNN_CPU_EMU
-cudaError_t launch_far_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* nl) {
+cudaError_t launch_tile_perm(const Workspace& w, const int* atom_b0, cudaStream_t st, int* nl) {
     if (w.n_atoms == 0 || w.n_bundles == 0) return cudaSuccess;
     if (w.P > 0 && !(w.pair_const == 2 && w.ek == EDR)) {      // only the round-1 warp-tile GNN kernel reads perm_j
         tile_perm_kernel<<<div_up(w.P, 256), 256, 0, st>>>(w.P, w.pair_i, w.pair_j, w.atom_sys, w.sys_off, atom_b0,
                                                            w.ustart, w.bundle_nat, w.perm_j);
         ++*nl;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_far_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* nl) {
+    if (w.n_atoms == 0 || w.n_bundles == 0) return cudaSuccess;
+    cudaError_t e0 = launch_tile_perm(w, atom_b0, st, nl);
+    if (e0 != cudaSuccess) return e0;
     far_fill_kernel<<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.atom_sys, w.sys_off, w.npad, w.rowptr, w.col,
                                                             atom_b0, w.far_off, w.far_list);
     ++*nl;

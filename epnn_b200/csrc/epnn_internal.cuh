@@ -275,6 +275,13 @@ struct CellWork {
     int* cell_cnt; int* cell_start; int* cell_atoms; double* Dtmp;
 };
 
+// Scratch of the fused list building for chunks of small systems only (epnn_bundle_prep.cu)
+struct BundlePrepWork {
+    unsigned long long* mask;   // [n_atoms] neighbour mask of every row inside its bundle
+    int* btot; int* boff;       // [4][n_bundles] per-bundle totals (nnz | P | far | far0), [4][n_bundles + 1] their exclusive scans
+    int* atom_b0;               // [n_atoms] first atom of the row's bundle
+};
+
 #ifndef EPNN_CPU_EMU
 // ------------------------------------------------------------------------------------------------
 // Launchers (defined in the .cu files; every one enqueues on `st` and returns cudaGetLastError()).
@@ -287,6 +294,10 @@ cudaError_t launch_edges_dense(int n, const float* xyz, float* e, cudaStream_t s
 cudaError_t upload_rbf_centers(const double* mu);
 cudaError_t upload_rbf_basis(const double* B);      // [ED][EDR]
 
+cudaError_t launch_edge_desc(const Workspace& w, cudaStream_t st, int* n_launch);        // descriptors + near flags of the pair list
+cudaError_t launch_tile_perm(const Workspace& w, const int* atom_b0, cudaStream_t st, int* n_launch);   // only the round-1 GNN bundle kernel needs it
+cudaError_t launch_bundle_prep_count(const Workspace& w, const BundlePrepWork& bw, int* scantmp, int* flags, cudaStream_t st, int* n_launch);
+cudaError_t launch_bundle_prep_fill(const Workspace& w, const BundlePrepWork& bw, cudaStream_t st, int* n_launch);
 cudaError_t launch_far_count(const Workspace& w, int* far_cnt, int* atom_b0, cudaStream_t st, int* n_launch);
 cudaError_t launch_far_fill(const Workspace& w, const int* atom_b0, cudaStream_t st, int* n_launch);
 cudaError_t launch_far0_count(const Workspace& w, int* cnt, cudaStream_t st, int* n_launch);

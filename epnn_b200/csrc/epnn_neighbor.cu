@@ -383,6 +383,10 @@ cudaError_t launch_nbr_fill(const Workspace& w, const CellWork& cw, cudaStream_t
     ++*nl;
     nbr_rev_kernel<<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.rowptr, w.ustart, w.degU, w.col, w.pid);
     ++*nl;
+    return launch_edge_desc(w, st, nl);
+}
+
+cudaError_t launch_edge_desc(const Workspace& w, cudaStream_t st, int* nl) {
     if (w.P > 0) {
         if (w.ek == ED) edge_desc_kernel<ED><<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near, w.near_counter);
         else            edge_desc_kernel<EDR><<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near, w.near_counter);
