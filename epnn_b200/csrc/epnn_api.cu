@@ -610,7 +610,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     }
     if (fused) {
         CU(c, launch_bundle_prep_fill(w, bw, st, n_launch));
-        CU(c, launch_edge_desc(w, st, n_launch));
+        CU(c, launch_edge_desc(w, st, n_launch, true));
         CU(c, launch_tile_perm(w, atom_b0, st, n_launch));
     } else {
         if (cw.n_large) ENS(B_DTMP, sizeof(double) * (size_t)(w.nnz + 1), cw.Dtmp, double*);

@@ -9,8 +9,9 @@
 //                        pairs, far slots, species-compressed far slots)
 //   4 scans over BUNDLES (not atoms) -> the bundle's base offsets; the last entries are the chunk totals the host needs
 //   bundle_fill_kernel   per row: popcounts of the mask -> its four counts, a warp prefix sum -> rowptr / ustart / far_off /
-//                        far0_off; then the CSR (col, pid, rowl), the unordered pair list (pair_i, pair_j, D), the far list,
+//                        far0_off; then the CSR (col, pid, rowl), the unordered pair list (pair_i, pair_j), the far list,
 //                        the species-compressed far list (one popcount per species) and rep -- in one pass.
+//   edge_desc_kernel     (epnn_neighbor.cu, one thread per pair) evaluates the pair's float64 distance itself.
 // Same definitions, same order, same float64 distance arithmetic as the general path (reference charge_gn.py:122-163,
 // :90-94): the lists are bit-identical to it (tests/test_gpu_parity.py neighbour tests, tests/test_emu_bundle_prep.py).
 #include "epnn_internal.cuh"
@@ -24,7 +25,7 @@ struct BundlePrepArgs {
     int* btot;                           // count pass:  [4][n_bundles]      nnz | P | far | far0 per bundle
     const int* boff;                     // fill pass:   [4][n_bundles + 1]  their exclusive scans
     int* deg; int* degU; int* rowptr; int* ustart; int* far_off; int* far0_off; int* rep; int* atom_b0; int* bundle_nat;
-    int* col; int* pid; unsigned char* rowl; int* pair_i; int* pair_j; double* pair_D;
+    int* col; int* pid; unsigned char* rowl; int* pair_i; int* pair_j;
     unsigned short* far_list; unsigned short* far0_list; unsigned char* far0_w;
 };
 
@@ -35,10 +36,6 @@ __device__ __forceinline__ double bp_dist64(float xi, float yi, float zi, float 
     const double dz = fabs(__dsub_rn((double)zj, (double)zi));
     const double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     return __dsqrt_rn(s);
-}
-__device__ __forceinline__ bool bp_far_reject(float xi, float yi, float zi, float xj, float yj, float zj) {
-    const float dx = xj - xi, dy = yj - yi, dz = zj - zi;
-    return dx * dx + dy * dy + dz * dz > 9.001f;
 }
 __device__ __forceinline__ int bp_popc(unsigned long long m) { return __popc((unsigned)m) + __popc((unsigned)(m >> 32)); }
 __device__ __forceinline__ int bp_ffs(unsigned long long m) { const unsigned lo = (unsigned)m; return lo ? __ffs(lo) : 32 + __ffs((unsigned)(m >> 32)); }   // 1-based
@@ -94,9 +91,13 @@ __global__ void __launch_bounds__(BP_NW * 32) bundle_count_kernel(const BundlePr
             unsigned long long m = 0ull;
             for (int j = w.a0; j < w.a1; ++j) {
                 if (j == r) continue;
+                // float32 squared distance (relative error < 1e-6) decides all but a thin shell around the cutoff; only there
+                // the reference's own float64 arithmetic (scipy distance_matrix, charge_gn.py:124) is evaluated
                 const float xj = sx[3 * j], yj = sx[3 * j + 1], zj = sx[3 * j + 2];
-                if (bp_far_reject(xi, yi, zi, xj, yj, zj)) continue;
-                if (bp_dist64(xi, yi, zi, xj, yj, zj) < 3.0) m |= 1ull << j;
+                const float dx = xj - xi, dy = yj - yi, dz = zj - zi;
+                const float d2 = dx * dx + dy * dy + dz * dz;
+                if (d2 > 9.001f) continue;
+                if (d2 < 8.999f || bp_dist64(xi, yi, zi, xj, yj, zj) < 3.0) m |= 1ull << j;
             }
             a.mask[b0 + r] = m;
             const int deg = bp_popc(m);
@@ -117,13 +118,11 @@ __global__ void __launch_bounds__(BP_NW * 32) bundle_count_kernel(const BundlePr
 }
 
 __global__ void __launch_bounds__(BP_NW * 32) bundle_fill_kernel(const BundlePrepArgs a) {
-    __shared__ float s_xyz[BP_NW][3 * BUNDLE_ATOMS];
     __shared__ int s_sp[BP_NW][BUNDLE_ATOMS];
     __shared__ unsigned long long s_spm[BP_NW][MAX_SPECIES];
     __shared__ unsigned long long s_mask[BP_NW][BUNDLE_ATOMS];
     __shared__ int s_ust[BP_NW][BUNDLE_ATOMS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* sx = s_xyz[warp];
     int* ssp = s_sp[warp];
     unsigned long long* spm = s_spm[warp];
     unsigned long long* smask = s_mask[warp];
@@ -132,7 +131,6 @@ __global__ void __launch_bounds__(BP_NW * 32) bundle_fill_kernel(const BundlePre
     for (int b = blockIdx.x * BP_NW + warp; b < nb; b += gridDim.x * BP_NW) {
         const int2 bd = a.bundle[b];
         const int b0 = bd.x, nat = bd.y;
-        for (int f = lane; f < 3 * nat; f += 32) sx[f] = a.xyz[3 * (int64_t)b0 + f];
         for (int f = lane; f < nat; f += 32) { ssp[f] = a.species[b0 + f] & (MAX_SPECIES - 1); smask[f] = a.mask[b0 + f]; }
         __syncwarp();
         bp_species_masks(ssp, nat, lane, spm);
@@ -185,7 +183,6 @@ __global__ void __launch_bounds__(BP_NW * 32) bundle_fill_kernel(const BundlePre
             const int i = b0 + r;
             const BpRow w = bp_row(a, b0, r);
             const unsigned long long m = smask[r];
-            const float xi = sx[3 * r], yi = sx[3 * r + 1], zi = sx[3 * r + 2];
             // CSR row (columns ascending) + this row's unordered pairs (its uppers, ascending)
             int k = my_rp[rd], pu = my_us[rd];
             for (unsigned long long rest = m; rest; rest &= rest - 1ull) {
@@ -194,8 +191,7 @@ __global__ void __launch_bounds__(BP_NW * 32) bundle_fill_kernel(const BundlePre
                 a.rowl[k] = (unsigned char)r;
                 if (j > r) {
                     a.pid[k] = pu;
-                    a.pair_i[pu] = i; a.pair_j[pu] = b0 + j;
-                    a.pair_D[pu] = bp_dist64(xi, yi, zi, sx[3 * j], sx[3 * j + 1], sx[3 * j + 2]);
+                    a.pair_i[pu] = i; a.pair_j[pu] = b0 + j;      // (its distance: edge_desc_kernel, one thread per pair)
                     ++pu;
                 } else {                // the pair is listed under row j: rank of r among j's uppers
                     a.pid[k] = sust[j] + bp_popc(smask[j] & ~bp_below(j + 1) & bp_below(r));
@@ -240,7 +236,7 @@ static BundlePrepArgs bp_args(const Workspace& w, const BundlePrepWork& bw) {
     a.mask = bw.mask; a.btot = bw.btot; a.boff = bw.boff;
     a.deg = w.deg; a.degU = w.degU; a.rowptr = w.rowptr; a.ustart = w.ustart; a.far_off = w.far_off; a.far0_off = w.far0_off;
     a.rep = w.rep; a.atom_b0 = bw.atom_b0; a.bundle_nat = w.bundle_nat;
-    a.col = w.col; a.pid = w.pid; a.rowl = w.rowl; a.pair_i = w.pair_i; a.pair_j = w.pair_j; a.pair_D = w.pair_D;
+    a.col = w.col; a.pid = w.pid; a.rowl = w.rowl; a.pair_i = w.pair_i; a.pair_j = w.pair_j;
     a.far_list = w.far_list; a.far0_list = w.far0_list; a.far0_w = w.far0_w;
     return a;
 }

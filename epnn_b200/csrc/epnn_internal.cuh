@@ -294,7 +294,7 @@ cudaError_t launch_edges_dense(int n, const float* xyz, float* e, cudaStream_t s
 cudaError_t upload_rbf_centers(const double* mu);
 cudaError_t upload_rbf_basis(const double* B);      // [ED][EDR]
 
-cudaError_t launch_edge_desc(const Workspace& w, cudaStream_t st, int* n_launch);        // descriptors + near flags of the pair list
+cudaError_t launch_edge_desc(const Workspace& w, cudaStream_t st, int* n_launch, bool gather);   // descriptors + near flags of the pair list (gather: D from the coordinates)
 cudaError_t launch_tile_perm(const Workspace& w, const int* atom_b0, cudaStream_t st, int* n_launch);   // only the round-1 GNN bundle kernel needs it
 cudaError_t launch_bundle_prep_count(const Workspace& w, const BundlePrepWork& bw, int* scantmp, int* flags, cudaStream_t st, int* n_launch);
 cudaError_t launch_bundle_prep_fill(const Workspace& w, const BundlePrepWork& bw, cudaStream_t st, int* n_launch);

@@ -317,16 +317,24 @@ __global__ void nbr_rev_kernel(int n_atoms, const int* __restrict__ rowptr, cons
 // EKOUT == EDR: their EDR coefficients c = B^T e in the orthonormal basis B (float64 dot products of the float32-rounded
 //               e, rounded once to float32): what the FP32 pair kernels consume (C^T e = (B^T C)^T c up to 5e-10).
 #define EDGE_PAIRS 128
+// gather_i != NULL: the distance is not read from pair_D but evaluated here from the pair's coordinates (fused list building of
+// small-system chunks, epnn_bundle_prep.cu: one thread per pair, no divergence around the float64 arithmetic).
 template <int EKOUT>
 __global__ void __launch_bounds__(EDGE_PAIRS) edge_desc_kernel(int64_t P, const double* __restrict__ pair_D,
                                                                float* __restrict__ e, unsigned char* __restrict__ near,
-                                                               unsigned long long* __restrict__ near_count) {
+                                                               unsigned long long* __restrict__ near_count,
+                                                               const int* __restrict__ gather_i, const int* __restrict__ gather_j,
+                                                               const float* __restrict__ xyz) {
     __shared__ float tile[EDGE_PAIRS][ED + 1];
     const int64_t p0 = (int64_t)blockIdx.x * EDGE_PAIRS;
     const int64_t p = p0 + threadIdx.x;
     bool is_near = false;
     if (p < P) {
-        const double D = pair_D[p];
+        double D;
+        if (gather_i) {
+            const int i = gather_i[p], j = gather_j[p];
+            D = dist64(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2]);
+        } else D = pair_D[p];
         const double C = cutoff_fn(D);
         const double dmu = c_mu[1] - c_mu[0];
         const double t = D - c_mu[0];
@@ -383,13 +391,14 @@ cudaError_t launch_nbr_fill(const Workspace& w, const CellWork& cw, cudaStream_t
     ++*nl;
     nbr_rev_kernel<<<div_up(w.n_atoms, 128), 128, 0, st>>>(w.n_atoms, w.rowptr, w.ustart, w.degU, w.col, w.pid);
     ++*nl;
-    return launch_edge_desc(w, st, nl);
+    return launch_edge_desc(w, st, nl, false);
 }
 
-cudaError_t launch_edge_desc(const Workspace& w, cudaStream_t st, int* nl) {
+cudaError_t launch_edge_desc(const Workspace& w, cudaStream_t st, int* nl, bool gather) {
     if (w.P > 0) {
-        if (w.ek == ED) edge_desc_kernel<ED><<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near, w.near_counter);
-        else            edge_desc_kernel<EDR><<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near, w.near_counter);
+        const int* gi = gather ? w.pair_i : nullptr;
+        if (w.ek == ED) edge_desc_kernel<ED><<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near, w.near_counter, gi, w.pair_j, w.xyz);
+        else            edge_desc_kernel<EDR><<<div_up(w.P, EDGE_PAIRS), EDGE_PAIRS, 0, st>>>(w.P, w.pair_D, w.e, w.near, w.near_counter, gi, w.pair_j, w.xyz);
         ++*nl;
     }
     return cudaGetLastError();

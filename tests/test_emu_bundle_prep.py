@@ -1,6 +1,6 @@
 """CPU warp emulation of the fused list building for chunks of small systems (epnn_bundle_prep.cu: one warp per bundle, a
-48-bit neighbour mask per row): every list it writes -- CSR, pair ids, local rows, unordered pairs with their float64
-distances, far list, species-compressed far list, representatives, offsets -- against the host construction that follows the
+48-bit neighbour mask per row): every list it writes -- CSR, pair ids, local rows, unordered pairs and their
+descriptors, far list, species-compressed far list, representatives, offsets -- against the host construction that follows the
 definitions of the general kernels (tests/emu_common.py) and the oracle's distances."""
 import ctypes as C
 import os
@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from emu_common import build_lists, csr, large_system_tables
-from oracle import epnn_oracle as O
+from epnn_b200 import _capi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "build", "libemu_bundle_prep.so")
@@ -22,7 +22,7 @@ def emu():
     subprocess.check_call(["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-pthread", "-DEPNN_CPU_EMU", "-Wno-unknown-pragmas",
                            "-o", LIB, os.path.join(ROOT, "tools", "emu", "emu_bundle_prep.cpp")])
     lib = C.CDLL(LIB)
-    lib.emu_bundle_prep.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 25 + [C.c_int]
+    lib.emu_bundle_prep.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 28 + [C.c_int]
     return lib
 
 
@@ -45,12 +45,15 @@ def test_fused_lists_match_the_definitions(emu, mixed, seed, n_sys, pad):
     i32 = lambda k: np.full(k, -7, np.int32)
     tot, deg, degU, rowptr, ustart, far_off, far0_off, rep, atom_b0, bnat = i32(4), i32(n), i32(n), i32(n + 1), i32(n + 1), i32(n + 1), i32(n + 1), i32(n), i32(n), i32(n)
     col, pid, pair_i, pair_j = i32(cap), i32(cap), i32(cap), i32(cap)
-    rowl = np.full(cap, 255, np.uint8); pair_D = np.full(cap, np.nan)
+    rowl = np.full(cap, 255, np.uint8); coef = np.full((cap, 16), np.nan, np.float32); near = np.full(cap, 255, np.uint8)
+    mu, B = np.zeros(48), np.zeros((48, 16))
+    lib = _capi.load()
+    assert lib.epnn_rbf_centers(_p(mu)) == 0 and lib.epnn_rbf_basis(_p(B)) == 0
     far_list = np.zeros(cap, np.uint16); far0_list = np.zeros(cap, np.uint16); far0_w = np.full(cap, 255, np.uint8)
     bundles = np.ascontiguousarray(L["bundles"], np.int32)
     assert emu.emu_bundle_prep(nb, n, _p(bundles), _p(L["atom_sys"]), _p(L["offs"]), _p(L["npad"]), _p(L["sp"]), _p(np.ascontiguousarray(xyz, np.float32)),
                                _p(tot), _p(deg), _p(degU), _p(rowptr), _p(ustart), _p(far_off), _p(far0_off), _p(rep), _p(atom_b0), _p(bnat),
-                               _p(col), _p(pid), _p(rowl), _p(pair_i), _p(pair_j), _p(pair_D), _p(far_list), _p(far0_list), _p(far0_w), cap) == 0
+                               _p(col), _p(pid), _p(rowl), _p(pair_i), _p(pair_j), _p(mu), _p(B), _p(coef), _p(near), _p(far_list), _p(far0_list), _p(far0_w), cap) == 0
     ref_rowptr, ref_col = csr(L)
     _, _, _, ref_pid, ref_deg = large_system_tables(L)
     nnz, P = int(ref_rowptr[-1]), L["P"]
@@ -69,9 +72,6 @@ def test_fused_lists_match_the_definitions(emu, mixed, seed, n_sys, pad):
     assert np.array_equal(far_off, L["far_off"]) and np.array_equal(far_list[:len(L["far_list"])], L["far_list"])
     assert np.array_equal(far0_off, L["far0_off"]) and np.array_equal(far0_list[:len(L["far0_list"])], L["far0_list"])
     assert np.array_equal(far0_w[:len(L["far0_w"])], L["far0_w"]) and np.array_equal(rep, L["rep"])
-    # float64 distances: scipy's arithmetic (charge_gn.py:124), bit for bit
-    for s in range(len(idx)):
-        a0, a1 = offs[s], offs[s + 1]
-        D = O.distance_matrix(xyz[a0:a1])
-        sel = (L["pair_i"] >= a0) & (L["pair_i"] < a1)
-        assert np.array_equal(pair_D[:P][sel], D[L["pair_i"][sel] - a0, L["pair_j"][sel] - a0])
+    # the pair's distance is evaluated by the descriptor kernel itself (one thread per pair): near flags bit-exact, coefficients
+    # = B^T e of the float32 descriptors to float32 round-off (build_lists follows the oracle's get_init_edges)
+    assert np.array_equal(near[:P], L["near"]) and np.abs(coef[:P] - L["coef"]).max() < 2e-7

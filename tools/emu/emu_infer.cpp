@@ -98,7 +98,7 @@ extern "C" int emu_infer(int T, int n_x, const float* w_packed, size_t n_w, int 
                                 pair_D.data(), grid.data(), cell_start.data(), cell_atoms.data(), Dtmp.data(), 0, n); });
     emu_launch_simple(div_up(n, 128), 128, [&] { k_nbr::nbr_rev_kernel(n, rowptr.data(), ustart.data(), degU.data(), col.data(), pid.data()); });
     if (Pn > 0)
-        emu_launch_grid(div_up(Pn, EDGE_PAIRS), EDGE_PAIRS / 32, 0, [&] { k_nbr::edge_desc_kernel<EDR>((int64_t)Pn, pair_D.data(), e.data(), near.data(), nullptr); });
+        emu_launch_grid(div_up(Pn, EDGE_PAIRS), EDGE_PAIRS / 32, 0, [&] { k_nbr::edge_desc_kernel<EDR>((int64_t)Pn, pair_D.data(), e.data(), near.data(), nullptr, nullptr, nullptr, nullptr); });
 
     // ---------------------------------------------------------------- bundles, far lists, row groups, species tables
     std::vector<int2> bundles;
@@ -180,7 +180,7 @@ extern "C" int emu_infer(int T, int n_x, const float* w_packed, size_t n_w, int 
             emu_launch_grid(2, ACONST_NW, (size_t)ACONST_NW * 32 * ATS, [&] { k_aconst::atom_const_kernel(W, aa); });
             return;
         }
-        k_atom::AtomArgs<float, float> aa;
+        AtomArgs<float, float> aa;
         memset(&aa, 0, sizeof(aa));
         aa.n_atoms = n; aa.mode = mode; aa.nsplit = nsplit; aa.h_is_zero = h_is_zero;
         aa.atom_sys = atom_sys.data(); aa.sys_off = off; aa.npad = npad.data(); aa.species = species;

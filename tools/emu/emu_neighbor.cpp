@@ -46,8 +46,8 @@ extern "C" int emu_neighbor_fill(int n_atoms, const int* atom_sys, const int* sy
     emu_launch_simple(div_up(n_atoms, 128), 128, [&] { nbr_rev_kernel(n_atoms, rowptr, ustart, degU, col, pid); });
     const int64_t P = ustart[n_atoms];
     if (P > 0) {
-        if (ek == ED) emu_launch_grid(div_up(P, EDGE_PAIRS), EDGE_PAIRS / 32, 0, [&] { edge_desc_kernel<ED>(P, pair_D, e, near, nullptr); });
-        else          emu_launch_grid(div_up(P, EDGE_PAIRS), EDGE_PAIRS / 32, 0, [&] { edge_desc_kernel<EDR>(P, pair_D, e, near, nullptr); });
+        if (ek == ED) emu_launch_grid(div_up(P, EDGE_PAIRS), EDGE_PAIRS / 32, 0, [&] { edge_desc_kernel<ED>(P, pair_D, e, near, nullptr, nullptr, nullptr, nullptr); });
+        else          emu_launch_grid(div_up(P, EDGE_PAIRS), EDGE_PAIRS / 32, 0, [&] { edge_desc_kernel<EDR>(P, pair_D, e, near, nullptr, nullptr, nullptr, nullptr); });
     }
     return 0;
 }
