@@ -68,7 +68,7 @@ __device__ __forceinline__ void bp_species_masks(const int* ssp, int nat, int la
     }
 }
 
-__global__ void __launch_bounds__(BP_NW * 32) bundle_count_kernel(const BundlePrepArgs a) {
+__global__ void __launch_bounds__(BP_NW * 32, 3) bundle_count_kernel(const BundlePrepArgs a) {
     __shared__ float s_xyz[BP_NW][3 * BUNDLE_ATOMS];
     __shared__ int s_sp[BP_NW][BUNDLE_ATOMS];
     __shared__ unsigned long long s_spm[BP_NW][MAX_SPECIES];
@@ -117,16 +117,48 @@ __global__ void __launch_bounds__(BP_NW * 32) bundle_count_kernel(const BundlePr
     }
 }
 
+// k-th (0-based) set bit of a 64-bit mask (k < popcount): halving steps on popcounts
+__device__ __forceinline__ int bp_select(unsigned long long m, int k) {
+    unsigned w = (unsigned)m;
+    int pos = 0;
+    const int c = __popc(w);
+    if (k >= c) { k -= c; w = (unsigned)(m >> 32); pos = 32; }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const unsigned part = w & ((1u << s) - 1u);
+        const int cc = __popc(part);
+        if (k >= cc) { k -= cc; w >>= s; pos += s; } else w = part;
+    }
+    return pos;
+}
+// row that owns list entry e: the last r in [0, nat) with off[r] <= e (off[nat] = the bundle's total > e)
+__device__ __forceinline__ int bp_find(const int* off, int nat, int e) {
+    int lo = 0, hi = nat;
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (off[mid] <= e) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// Fill pass.  Phase 1 (lane = row): the rows' four counts and offsets -> the per-atom arrays (coalesced) and shared memory.
+// Phase 2 (lane = LIST ENTRY): every list of the bundle is one contiguous range of global memory, so entry e of a list is
+// written by lane e mod 32 -- whole 128-byte lines per warp store instead of one 4-byte store per row and instruction (the
+// first version: 200 us per 50 k molecules, bound by partial-sector writes); the entry finds its row by bisection of the
+// row offsets and its column as the k-th set bit of the row's mask.
 __global__ void __launch_bounds__(BP_NW * 32) bundle_fill_kernel(const BundlePrepArgs a) {
     __shared__ int s_sp[BP_NW][BUNDLE_ATOMS];
     __shared__ unsigned long long s_spm[BP_NW][MAX_SPECIES];
-    __shared__ unsigned long long s_mask[BP_NW][BUNDLE_ATOMS];
-    __shared__ int s_ust[BP_NW][BUNDLE_ATOMS];
+    __shared__ unsigned long long s_mask[BP_NW][BUNDLE_ATOMS], s_farm[BP_NW][BUNDLE_ATOMS], s_sysm[BP_NW][BUNDLE_ATOMS];
+    __shared__ int s_off[BP_NW][4][BUNDLE_ATOMS + 1];          // local offsets of the rows: CSR | pairs | far | far0; [nat] = total
+    __shared__ unsigned short s_spres[BP_NW][BUNDLE_ATOMS];    // species with far columns (bit = species)
+    __shared__ unsigned char s_pad[BP_NW][BUNDLE_ATOMS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* ssp = s_sp[warp];
     unsigned long long* spm = s_spm[warp];
     unsigned long long* smask = s_mask[warp];
-    int* sust = s_ust[warp];
+    unsigned long long* sfar = s_farm[warp];
+    unsigned long long* ssys = s_sysm[warp];
+    int* o_rp = s_off[warp][0]; int* o_us = s_off[warp][1]; int* o_fo = s_off[warp][2]; int* o_f0 = s_off[warp][3];
+    unsigned short* spres = s_spres[warp];
+    unsigned char* spad = s_pad[warp];
     const int nb = a.n_bundles;
     for (int b = blockIdx.x * BP_NW + warp; b < nb; b += gridDim.x * BP_NW) {
         const int2 bd = a.bundle[b];
@@ -135,20 +167,25 @@ __global__ void __launch_bounds__(BP_NW * 32) bundle_fill_kernel(const BundlePre
         __syncwarp();
         bp_species_masks(ssp, nat, lane, spm);
         __syncwarp();
-        // ---- the rows' offsets: bundle base (scan over bundles) + warp prefix sum over the rows, 32 rows per round
-        int base_nnz = a.boff[b], base_p = a.boff[(nb + 1) + b], base_far = a.boff[2 * (nb + 1) + b], base_far0 = a.boff[3 * (nb + 1) + b];
-        int my_rp[2] = {0, 0}, my_us[2] = {0, 0}, my_fo[2] = {0, 0}, my_f0[2] = {0, 0};
+        // ---- phase 1: bundle base (scan over bundles) + warp prefix sum over the rows, 32 rows per round
+        const int base_nnz = a.boff[b], base_p = a.boff[(nb + 1) + b], base_far = a.boff[2 * (nb + 1) + b], base_far0 = a.boff[3 * (nb + 1) + b];
+        int c0 = 0, c1 = 0, c2 = 0, c3 = 0;                   // running totals of the rounds done
 #pragma unroll
         for (int rd = 0; rd < (BUNDLE_ATOMS + 31) / 32; ++rd) {
             if (rd * 32 >= nat) break;
             const int r = rd * 32 + lane;
-            int deg = 0, dU = 0, far = 0, far0 = 0;
+            int deg = 0, dU = 0, far = 0, far0 = 0, rep = 0;
             if (r < nat) {
                 const BpRow w = bp_row(a, b0, r);
-                const unsigned long long m = smask[r];
+                const unsigned long long m = smask[r], fm = ~m & w.sysmask;
                 deg = bp_popc(m); dU = bp_popc(m & ~bp_below(r + 1));
                 far = (w.a1 - w.a0 - deg) + w.pad;
-                far0 = bp_far0_count(spm, ~m & w.sysmask, w.pad);
+                unsigned pres = 0u;
+#pragma unroll
+                for (int k = 0; k < MAX_SPECIES; ++k) pres |= (unsigned)((spm[k] & fm) != 0ull) << k;
+                far0 = __popc(pres) + w.pad;
+                sfar[r] = fm; ssys[r] = w.sysmask; spres[r] = (unsigned short)pres; spad[r] = (unsigned char)w.pad;
+                rep = b0 + bp_ffs(spm[w.sp] & w.sysmask) - 1;
             }
             int x0 = deg, x1 = dU, x2 = far, x3 = far0;
             for (int o = 1; o < 32; o <<= 1) {
@@ -156,18 +193,18 @@ __global__ void __launch_bounds__(BP_NW * 32) bundle_fill_kernel(const BundlePre
                 const int y2 = __shfl_up_sync(0xffffffffu, x2, o), y3 = __shfl_up_sync(0xffffffffu, x3, o);
                 if (lane >= o) { x0 += y0; x1 += y1; x2 += y2; x3 += y3; }
             }
-            my_rp[rd] = base_nnz + x0 - deg; my_us[rd] = base_p + x1 - dU; my_fo[rd] = base_far + x2 - far; my_f0[rd] = base_far0 + x3 - far0;
             if (r < nat) {
                 const int i = b0 + r;
+                o_rp[r] = c0 + x0 - deg; o_us[r] = c1 + x1 - dU; o_fo[r] = c2 + x2 - far; o_f0[r] = c3 + x3 - far0;
                 a.deg[i] = deg; a.degU[i] = dU;
-                a.rowptr[i] = my_rp[rd]; a.ustart[i] = my_us[rd]; a.far_off[i] = my_fo[rd]; a.far0_off[i] = my_f0[rd];
-                a.atom_b0[i] = b0;
-                sust[r] = my_us[rd];
+                a.rowptr[i] = base_nnz + o_rp[r]; a.ustart[i] = base_p + o_us[r]; a.far_off[i] = base_far + o_fo[r]; a.far0_off[i] = base_far0 + o_f0[r];
+                a.atom_b0[i] = b0; a.rep[i] = rep;
             }
-            base_nnz += __shfl_sync(0xffffffffu, x0, 31); base_p += __shfl_sync(0xffffffffu, x1, 31);
-            base_far += __shfl_sync(0xffffffffu, x2, 31); base_far0 += __shfl_sync(0xffffffffu, x3, 31);
+            c0 += __shfl_sync(0xffffffffu, x0, 31); c1 += __shfl_sync(0xffffffffu, x1, 31);
+            c2 += __shfl_sync(0xffffffffu, x2, 31); c3 += __shfl_sync(0xffffffffu, x3, 31);
         }
         if (lane == 0) {
+            o_rp[nat] = c0; o_us[nat] = c1; o_fo[nat] = c2; o_f0[nat] = c3;
             a.bundle_nat[b0] = nat;
             if (b == nb - 1) {          // closing entries of the offset arrays = the chunk totals
                 a.rowptr[a.n_atoms] = a.boff[nb]; a.ustart[a.n_atoms] = a.boff[(nb + 1) + nb];
@@ -175,48 +212,42 @@ __global__ void __launch_bounds__(BP_NW * 32) bundle_fill_kernel(const BundlePre
             }
         }
         __syncwarp();
-        // ---- the lists
-#pragma unroll
-        for (int rd = 0; rd < (BUNDLE_ATOMS + 31) / 32; ++rd) {
-            const int r = rd * 32 + lane;
-            if (r >= nat) continue;
-            const int i = b0 + r;
-            const BpRow w = bp_row(a, b0, r);
+        // ---- phase 2: the lists, lane = entry
+        // CSR (columns ascending inside a row) with the pair id and the local row of every entry
+        for (int e = lane; e < c0; e += 32) {
+            const int r = bp_find(o_rp, nat, e), k = e - o_rp[r];
             const unsigned long long m = smask[r];
-            // CSR row (columns ascending) + this row's unordered pairs (its uppers, ascending)
-            int k = my_rp[rd], pu = my_us[rd];
-            for (unsigned long long rest = m; rest; rest &= rest - 1ull) {
-                const int j = bp_ffs(rest) - 1;
-                a.col[k] = b0 + j;
-                a.rowl[k] = (unsigned char)r;
-                if (j > r) {
-                    a.pid[k] = pu;
-                    a.pair_i[pu] = i; a.pair_j[pu] = b0 + j;      // (its distance: edge_desc_kernel, one thread per pair)
-                    ++pu;
-                } else {                // the pair is listed under row j: rank of r among j's uppers
-                    a.pid[k] = sust[j] + bp_popc(smask[j] & ~bp_below(j + 1) & bp_below(r));
-                }
-                ++k;
+            const int j = bp_select(m, k);
+            a.col[base_nnz + e] = b0 + j;
+            a.rowl[base_nnz + e] = (unsigned char)r;
+            // j > r: the pair is among the row's own uppers (the tail of the row); else it is listed under row j
+            a.pid[base_nnz + e] = base_p + (j > r ? o_us[r] + (k - bp_popc(m & bp_below(r)))
+                                                  : o_us[j] + bp_popc(smask[j] & ~bp_below(j + 1) & bp_below(r)));
+        }
+        // unordered pairs: the uppers of every row, ascending (their distances: edge_desc_kernel, one thread per pair)
+        for (int e = lane; e < c1; e += 32) {
+            const int r = bp_find(o_us, nat, e);
+            a.pair_i[base_p + e] = b0 + r;
+            a.pair_j[base_p + e] = b0 + bp_select(smask[r] & ~bp_below(r + 1), e - o_us[r]);
+        }
+        // far list: the complement of the row inside its system, ascending (the row itself included), then the pad slot
+        for (int e = lane; e < c2; e += 32) {
+            const int r = bp_find(o_fo, nat, e), k = e - o_fo[r];
+            const unsigned long long fm = sfar[r];
+            a.far_list[base_far + e] = (unsigned short)((r << 8) | (k < bp_popc(fm) ? bp_select(fm, k) : 0xFF));
+        }
+        // species-compressed far list: one slot per species with far columns, species ascending; weight = their number
+        for (int e = lane; e < c3; e += 32) {
+            const int r = bp_find(o_f0, nat, e), k = e - o_f0[r];
+            const unsigned pres = spres[r];
+            int code = 0xFF, wgt = 0;
+            if (k < __popc(pres)) {
+                const int sp = bp_select((unsigned long long)pres, k);
+                code = bp_ffs(spm[sp] & ssys[r]) - 1;
+                wgt = bp_popc(spm[sp] & sfar[r]);
             }
-            // far list: the complement of the row inside its system, ascending (the row itself included), then the pad slot
-            const int hi = r << 8;
-            int wf = my_fo[rd];
-            for (unsigned long long rest = ~m & w.sysmask; rest; rest &= rest - 1ull) a.far_list[wf++] = (unsigned short)(hi | (bp_ffs(rest) - 1));
-            if (w.pad) a.far_list[wf] = (unsigned short)(hi | 0xFF);
-            // species-compressed far list: one slot per species with far columns, species ascending; weight = their number
-            int w0 = my_f0[rd];
-            const unsigned long long farmask = ~m & w.sysmask;
-#pragma unroll
-            for (int sp = 0; sp < MAX_SPECIES; ++sp) {
-                const int c = bp_popc(spm[sp] & farmask);
-                if (c > 0) {
-                    a.far0_list[w0] = (unsigned short)(hi | (bp_ffs(spm[sp] & w.sysmask) - 1));
-                    a.far0_w[w0] = (unsigned char)c;
-                    ++w0;
-                }
-            }
-            if (w.pad) { a.far0_list[w0] = (unsigned short)(hi | 0xFF); a.far0_w[w0] = 0; }
-            a.rep[i] = b0 + bp_ffs(spm[w.sp] & w.sysmask) - 1;
+            a.far0_list[base_far0 + e] = (unsigned short)((r << 8) | code);
+            a.far0_w[base_far0 + e] = (unsigned char)wgt;
         }
         __syncwarp();
     }
