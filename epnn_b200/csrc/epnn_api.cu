@@ -63,6 +63,11 @@ struct epnn_ctx {
     int device = 0, T = 0, n_x = 0, n_species = 0, sm_count = 0;
     cudaStream_t stream = nullptr;           // the stream every kernel / copy of the ctx is enqueued on (own_stream, or the caller's: epnn_set_stream)
     cudaStream_t own_stream = nullptr;
+    // multi-chunk calls keep two chunks in flight: even chunks on `stream`, odd chunks on `stream2`, each with its own set of
+    // workspaces (bufs[slot * B_COUNT + ...]) and flags -- the list building of one chunk runs beside the pair kernels of the other
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int chunk_streams = 2;       // option "chunk_streams": 1 = one chunk at a time
     // host-buffer calls: chunk k + 1 is uploaded and chunk k - 1 downloaded while chunk k computes (two staging slots)
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -129,7 +134,7 @@ static int fail(epnn_ctx* c, int code, const char* fmt, ...) {
 static int ensure(epnn_ctx* c, int which, size_t bytes, void** out) {
     DevBuf& b = c->bufs[which];
     if (bytes > b.cap) {
-        if (b.p) { CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+        if (b.p) { CU(c, cudaStreamSynchronize(c->stream)); CU(c, cudaStreamSynchronize(c->stream2)); CU(c, cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
         size_t want = bytes + bytes / 8 + 256;
         CU(c, cudaMalloc(&b.p, want));
         b.cap = want;
@@ -176,7 +181,7 @@ extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_
     epnn_ctx* c = new (std::nothrow) epnn_ctx();
     if (!c) return fail(nullptr, EPNN_E_NOMEM, "epnn_create: out of host memory");
     c->device = device; c->T = T; c->n_x = n_x; c->n_species = n_x - 1;
-    c->bufs.resize(B_COUNT);
+    c->bufs.resize(2 * B_COUNT);
 #define CUC(call)                                                                                               \
     do {                                                                                                        \
         cudaError_t _e = (call);                                                                                \
@@ -190,6 +195,9 @@ extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_
     CUC(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
     CUC(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    CUC(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CUC(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUC(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     CUC(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     CUC(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     for (int k = 0; k < 2; ++k) {
@@ -197,8 +205,8 @@ extern "C" int epnn_create(int device, int T, int n_x, const float* w, size_t n_
         CUC(cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming));
         CUC(cudaEventCreateWithFlags(&c->ev_d2h[k], cudaEventDisableTiming));
     }
-    CUC(cudaMalloc(&c->d_flags, 8 * sizeof(int)));
-    CUC(cudaMallocHost(&c->h_flags, 8 * sizeof(int)));
+    CUC(cudaMalloc(&c->d_flags, 16 * sizeof(int)));          // 8 per workspace slot
+    CUC(cudaMallocHost(&c->h_flags, 16 * sizeof(int)));
     double mu[48];
     epnn_rbf_centers(mu);
     CUC(upload_rbf_centers(mu));
@@ -240,6 +248,9 @@ extern "C" void epnn_destroy(epnn_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     if (c->comm) { g_nccl.CommDestroy(c->comm); c->comm = nullptr; }
     for (DevBuf& b : c->bufs) if (b.p) cudaFree(b.p);
     if (c->wf) cudaFree(c->wf);
@@ -285,6 +296,10 @@ extern "C" int epnn_set_option(epnn_ctx* c, const char* key, double value) {
     else if (k == "pair_tensor") c->pair_tensor = value != 0;
     else if (k == "atom_tensor") c->atom_tensor = value != 0;
     else if (k == "fused_prep") c->fused_prep = value != 0;
+    else if (k == "chunk_streams") {
+        if (value != 1 && value != 2) return fail(c, EPNN_E_INVALID, "chunk_streams must be 1 or 2");
+        c->chunk_streams = (int)value;
+    }
     else if (k == "pair_const") {
         if (value != 0 && value != 1 && value != 2) return fail(c, EPNN_E_INVALID, "pair_const must be 0, 1 or 2");
         c->pair_const = (int)value;
@@ -377,8 +392,11 @@ struct Timer {
 template <typename R>
 static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, const int* d_off_in, int base, const float* d_xyz,
                      const int* d_species, const float* d_Q, const int* d_npad_in, float* d_out32, double* d_out64,
-                     epnn_stats* stats, Timer& tm, int* n_launch, bool neighbors_only, Workspace* ws_out) {
-    cudaStream_t st = c->stream;
+                     epnn_stats* stats, Timer& tm, int* n_launch, bool neighbors_only, Workspace* ws_out, int slot = 0) {
+    cudaStream_t st = slot ? c->stream2 : c->stream;      // workspace slot 1 belongs to the second chunk stream
+    const int sb = slot * B_COUNT;
+    int* d_flags = c->d_flags + 8 * slot;
+    int* h_flags = c->h_flags + 8 * slot;
     // mixed precision (48): FP32 pair kernels around an FP64 per-atom kernel (state l2 / h in FP64, S / u / v / delta in FP32)
     const bool mixed = sizeof(R) == 4 && c->eff_precision == 48;
     Workspace w;
@@ -407,14 +425,14 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     w.pair_const = sizeof(R) == 4 ? c->pair_const : 0;
     w.atom_tensor = c->eff_atom_tensor;
     w.wf_host = c->wf_host.data(); w.wf_dev = c->wf;
-    w.work_counter = c->d_flags + 7;
+    w.work_counter = d_flags + 7;
     w.near_counter = stats && !neighbors_only && c->bufs[B_MISC].p ? (unsigned long long*)c->bufs[B_MISC].p : nullptr;
     w.slot_counter = stats && c->bufs[B_MISC].p ? (unsigned long long*)c->bufs[B_MISC].p + 2 : nullptr;
-    { void* pa; int rca = ensure(c, B_ARGS, 1024, &pa); if (rca != EPNN_OK) return rca; w.args_dev = pa; }
+    { void* pa; int rca = ensure(c, sb + B_ARGS, 1024, &pa); if (rca != EPNN_OK) return rca; w.args_dev = pa; }
     w.xyz = d_xyz; w.species = d_species; w.Qsys = d_Q;
     void* p;
     int rc;
-#define ENS(which, bytes, field, type) do { if ((rc = ensure(c, which, (bytes), &p)) != EPNN_OK) return rc; field = (type)p; } while (0)
+#define ENS(which, bytes, field, type) do { if ((rc = ensure(c, sb + (which), (bytes), &p)) != EPNN_OK) return rc; field = (type)p; } while (0)
     int *off_local, *npad_local, *cnt_l, *rgl_off, *scantmp, *far_cnt, *atom_b0;
     ENS(B_OFF, sizeof(int) * ((size_t)n_sys + 1), off_local, int*);
     ENS(B_NPAD, sizeof(int) * ((size_t)n_sys + 1), npad_local, int*);
@@ -490,9 +508,9 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
         }
     }
 
-    CU(c, cudaMemsetAsync(c->d_flags, 0, 8 * sizeof(int), st));
-    sys_prep_kernel<<<div_up(n_sys + 1, 256), 256, 0, st>>>(n_sys, d_off_in, base, off_local, d_npad_in, npad_local, cnt_l, c->d_flags);
-    species_check_kernel<<<div_up(n_atoms, 256), 256, 0, st>>>(n_atoms, d_species, c->n_species, c->d_flags);
+    CU(c, cudaMemsetAsync(d_flags, 0, 8 * sizeof(int), st));
+    sys_prep_kernel<<<div_up(n_sys + 1, 256), 256, 0, st>>>(n_sys, d_off_in, base, off_local, d_npad_in, npad_local, cnt_l, d_flags);
+    species_check_kernel<<<div_up(n_atoms, 256), 256, 0, st>>>(n_atoms, d_species, c->n_species, d_flags);
     *n_launch += 2;
     CU(c, cudaGetLastError());
     CU(c, launch_scan_i32(cnt_l, rgl_off, n_sys, scantmp, st, n_launch));
@@ -507,7 +525,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
         ENS(B_BPTOT, sizeof(int) * 4 * (size_t)w.n_bundles, bw.btot, int*);
         ENS(B_BPOFF, sizeof(int) * 4 * ((size_t)w.n_bundles + 1), bw.boff, int*);
         bw.atom_b0 = atom_b0;
-        CU(c, launch_bundle_prep_count(w, bw, scantmp, c->d_flags, st, n_launch));
+        CU(c, launch_bundle_prep_count(w, bw, scantmp, d_flags, st, n_launch));
     } else {
         CU(c, launch_cell_build(w, cw, scantmp, st, n_launch));
         CU(c, launch_nbr_count(w, cw, st, n_launch));
@@ -515,15 +533,15 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
         CU(c, launch_scan_i32(w.degU, w.ustart, n_atoms, scantmp, st, n_launch));
         CU(c, launch_far_count(w, far_cnt, atom_b0, st, n_launch));
         CU(c, launch_scan_i32(far_cnt, w.far_off, n_atoms, scantmp, st, n_launch));
-        collect_totals_kernel<<<1, 1, 0, st>>>(w.rowptr, w.ustart, w.far_off, n_atoms, rgl_off, n_sys, c->d_flags);
+        collect_totals_kernel<<<1, 1, 0, st>>>(w.rowptr, w.ustart, w.far_off, n_atoms, rgl_off, n_sys, d_flags);
         ++*n_launch;
     }
-    CU(c, cudaMemcpyAsync(c->h_flags, c->d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(c, cudaMemcpyAsync(h_flags, d_flags, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU(c, cudaStreamSynchronize(st));
-    if (c->h_flags[0] & 1) return fail(c, EPNN_E_INVALID, "npad smaller than the number of atoms for at least one system");
-    if (c->h_flags[0] & 2) return fail(c, EPNN_E_INVALID, "a system with zero (or negative) atoms was passed");
-    if (c->h_flags[0] & 4) return fail(c, EPNN_E_INVALID, "species index outside the element table (n_x=%d has %d species)", c->n_x, c->n_species);
-    w.nnz = c->h_flags[1]; w.P = c->h_flags[2]; w.n_far = c->h_flags[3]; w.n_rg_large = c->h_flags[4];
+    if (h_flags[0] & 1) return fail(c, EPNN_E_INVALID, "npad smaller than the number of atoms for at least one system");
+    if (h_flags[0] & 2) return fail(c, EPNN_E_INVALID, "a system with zero (or negative) atoms was passed");
+    if (h_flags[0] & 4) return fail(c, EPNN_E_INVALID, "species index outside the element table (n_x=%d has %d species)", c->n_x, c->n_species);
+    w.nnz = h_flags[1]; w.P = h_flags[2]; w.n_far = h_flags[3]; w.n_rg_large = h_flags[4];
     w.n_far0 = (int64_t)(MAX_SPECIES + 1) * n_atoms;      // capacity: at most one slot per species + the pad slot per row
     if (w.nnz < 0 || w.P < 0 || w.n_far < 0) return fail(c, EPNN_E_UNSUPPORTED, "pair lists of one chunk exceed 2^31 entries; lower chunk_atoms");
     w.nsplit = 1;
@@ -664,7 +682,7 @@ static int run_chunk(epnn_ctx* c, int n_sys, int n_atoms, const int32_t* h_off, 
     const int own = sharded ? 1 : 0, act = sharded ? 2 : 0;
     if (sharded) {
         unsigned char* am;
-        if ((rc = ensure(c, B_ACTIVE, (size_t)n_atoms + 16, &p)) != EPNN_OK) return rc;
+        if ((rc = ensure(c, sb + B_ACTIVE, (size_t)n_atoms + 16, &p)) != EPNN_OK) return rc;
         am = (unsigned char*)p;
         active_mark_kernel<0><<<div_up(n_atoms, 256), 256, 0, st>>>(n_atoms, w.row_lo, w.row_hi, w.rowptr, w.col, am);
         active_mark_kernel<1><<<div_up(n_atoms, 256), 256, 0, st>>>(n_atoms, w.row_lo, w.row_hi, w.rowptr, w.col, am);
@@ -852,8 +870,18 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
         if (q_out64) { if ((rc = ensure(c, k ? B_OUT64_1 : B_OUT64, sizeof(double) * (size_t)max_na, &p)) != EPNN_OK) return rc; slot[k].o64 = (double*)p; }
     }
     const bool piped = n_slots == 2;
-    cudaStream_t up = piped ? c->h2d_stream : st, down = piped ? c->d2h_stream : st;
+    // two chunks in flight (even chunks: ctx stream + workspace slot 0, odd chunks: second stream + slot 1): the list building
+    // of chunk k + 1 -- latency-bound, and followed by the call's one host sync per chunk -- runs beside the pair kernels of
+    // chunk k.  Not for sharded contexts (their collectives share one communicator).
+    const bool two = c->chunk_streams == 2 && n_chunks > 1 && c->shard_world <= 1;
+    Timer tm2{c->timing != 0, c->stream2, {}, {}};
+    if (two) {
+        CU(c, cudaEventRecord(c->ev_fork, st));      // the second stream starts after whatever precedes this call on the ctx stream
+        CU(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
+    }
+    cudaStream_t down = piped ? c->d2h_stream : st;
     auto upload = [&](size_t ci, int k) -> int {      // offsets / npad always come from the host: they drive launch geometry
+        cudaStream_t up = piped ? c->h2d_stream : (two && (ci & 1) ? c->stream2 : st);
         const int64_t s0 = bounds[ci], s1 = bounds[ci + 1];
         const int ns = (int)(s1 - s0), a0 = off[s0], na = off[s1] - off[s0];
         CU(c, cudaMemcpyAsync(slot[k].off, off + s0, sizeof(int) * ((size_t)ns + 1), cudaMemcpyHostToDevice, up));
@@ -866,7 +894,6 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
         if (piped) CU(c, cudaEventRecord(c->ev_h2d[k], up));
         return EPNN_OK;
     };
-    if (piped) CU(c, cudaStreamWaitEvent(up, c->ev_done[0], 0));      // (events of an earlier call: already complete)
     if ((rc = upload(0, 0)) != EPNN_OK) return rc;
     for (size_t ci = 0; ci < n_chunks; ++ci) {
         const int k = piped ? (int)(ci & 1) : 0;
@@ -874,8 +901,11 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
         const int ns = (int)(s1 - s0);
         const int a0 = off[s0], a1 = off[s1];
         const int na = a1 - a0;
+        const int ws = two ? (int)(ci & 1) : 0;
+        cudaStream_t cs = ws ? c->stream2 : st;
+        Timer& tmc = ws ? tm2 : tm;
         if (!piped && ci > 0 && (rc = upload(ci, 0)) != EPNN_OK) return rc;
-        if (piped) CU(c, cudaStreamWaitEvent(st, c->ev_h2d[k], 0));
+        if (piped) CU(c, cudaStreamWaitEvent(cs, c->ev_h2d[k], 0));
         int* d_off = slot[k].off;
         int* d_npad_in = npad_host ? d_off + ns + 1 : nullptr;
         const float* d_xyz; const int* d_species; const float* d_Q; float* d_o32 = nullptr; double* d_o64 = nullptr;
@@ -885,17 +915,17 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
             d_xyz = xyz + 3 * (size_t)a0; d_species = species + a0; d_Q = Q + s0;
             d_o32 = q_out ? q_out + a0 : nullptr; d_o64 = q_out64 ? q_out64 + a0 : nullptr;
         }
-        tm.mark(1);
+        tmc.mark(1);
         Workspace w;
         if (c->eff_precision == 64)
-            rc = run_chunk<double>(c, ns, na, off + s0, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
+            rc = run_chunk<double>(c, ns, na, off + s0, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tmc, &n_launch, false, &w, ws);
         else
-            rc = run_chunk<float>(c, ns, na, off + s0, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tm, &n_launch, false, &w);
-        if (rc != EPNN_OK) { cudaStreamSynchronize(up); cudaStreamSynchronize(down); return rc; }
+            rc = run_chunk<float>(c, ns, na, off + s0, d_off, a0, d_xyz, d_species, d_Q, d_npad_in, d_o32, d_o64, stats, tmc, &n_launch, false, &w, ws);
+        if (rc != EPNN_OK) { cudaStreamSynchronize(c->h2d_stream); cudaStreamSynchronize(down); cudaStreamSynchronize(c->stream2); cudaStreamSynchronize(st); return rc; }
         if (piped) {
             // run_chunk returned after its one host sync (neighbour count): chunk ci - 1 is complete, the bulk of chunk ci is
             // queued.  Its results go down on their own stream; the other slot is free for chunk ci + 1 once ITS download is done.
-            CU(c, cudaEventRecord(c->ev_done[k], st));
+            CU(c, cudaEventRecord(c->ev_done[k], cs));
             CU(c, cudaStreamWaitEvent(down, c->ev_done[k], 0));
         }
         if (host_io) {
@@ -909,11 +939,15 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
                 if ((rc = upload(ci + 1, k ^ 1)) != EPNN_OK) return rc;
             }
         } else if (host_io) {
-            CU(c, cudaStreamSynchronize(st));      // the single staging slot is reused by the next chunk
+            CU(c, cudaStreamSynchronize(cs));      // the single staging slot is reused by the next chunk
         }
-        tm.mark(7);
+        tmc.mark(7);
     }
-    if (piped) { CU(c, cudaStreamSynchronize(up)); CU(c, cudaStreamSynchronize(down)); }
+    if (piped) { CU(c, cudaStreamSynchronize(c->h2d_stream)); CU(c, cudaStreamSynchronize(down)); }
+    if (two) {
+        CU(c, cudaEventRecord(c->ev_join, c->stream2));      // later work on the ctx stream is ordered after the odd chunks too
+        CU(c, cudaStreamWaitEvent(st, c->ev_join, 0));
+    }
     CU(c, cudaStreamSynchronize(st));
     if (stats) {
         unsigned long long nn[4] = {0, 0, 0, 0};
@@ -928,6 +962,7 @@ static int infer_impl(epnn_ctx* c, int64_t n_sys, const int32_t* off, bool host_
         stats->atom_tensor_used = c->eff_precision == 32 ? c->eff_atom_tensor : 0;
     }
     tm.finish(stats);
+    tm2.finish(stats);          // (two chunk streams: the phase times of both are added up; they overlap in wall-clock time)
     if (bounds.size() != 2) c->hidden_atoms = 0;       // hidden state only meaningful for single-chunk calls
     return EPNN_OK;
 }

@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of an engine option at 300 k molecules:  gpurun -- '[CKPT=model2_weights] bash tools/gpu_ab_opt.sh atom_tensor 0 1'
+# A/B of an engine option at NMOL (default 300 k) molecules:  gpurun -- '[CKPT=model2_weights] bash tools/gpu_ab_opt.sh atom_tensor 0 1'
 mkdir -p gpurun_out
 OPT=$1; shift
 cat > /tmp/ab_opt.py <<'PY'
@@ -10,8 +10,9 @@ from epnn_b200.engine import Engine
 from epnn_b200 import synth
 opt, vals = sys.argv[1], [float(x) for x in sys.argv[2:]]
 w = load_weights("tests/golden/checkpoints/" + os.environ.get("CKPT", "decay_model_weights"))
-offs, xyz, sp, Q = synth.qm9_shaped(300000, w.n_x, seed=0)
-npad = np.full(300000, 29, np.int32)
+NMOL = int(os.environ.get("NMOL", "300000"))
+offs, xyz, sp, Q = synth.qm9_shaped(NMOL, w.n_x, seed=0)
+npad = np.full(NMOL, 29, np.int32)
 outs = []
 for v in vals:
     eng = Engine(w, 0); eng.set_option("timing", 1); eng.set_option(opt, v)
