@@ -634,6 +634,11 @@ def run_b200(args):
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)",
                 "neighbor_build": {"achieved": (20.0 * n_atoms + 4.0 * nnz) / (phases["ms_neighbor"] * 1e-3) * 1e-9},
                 "charge_reduction": {"achieved": w.T * (4.0 * nnz + 8.0 * n_atoms) / (phases["ms_epn_atom"] * 1e-3) * 1e-9},
+                # the per-atom kernels (update MLP + projections on the tensor path, charge reduction): bytes they have to move per
+                # launch (l2 / S rows in, l2 / u / v rows out at 128 B each; q 16 B; 12 B per CSR entry and pass)
+                # over the CUDA-event time of their phases
+                "per_atom_gnn_phase": {"achieved": n_atoms * (256.0 + 512.0 + max(w.T - 2, 0) * 640.0) / (phases["ms_gnn_atom"] * 1e-3) * 1e-9},
+                "per_atom_epn_phase": {"achieved": (n_atoms * (832.0 + (w.T - 1) * 400.0 + 20.0) + w.T * 12.0 * nnz) / (phases["ms_epn_atom"] * 1e-3) * 1e-9},
             },
         }
         if args.workload == "protein":
@@ -664,7 +669,7 @@ def run_b200(args):
                 for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "peak_source"):
                     roofline[k] = roofline["tensor_far"][k]
                 roofline["achieved_is"] = "EXECUTED tensor FLOPs (three TF32 MMAs of the 3xTF32 split per far pair) / CUDA-event time of the message-passing phase"
-        for k in ("neighbor_build", "charge_reduction"):
+        for k in ("neighbor_build", "charge_reduction", "per_atom_gnn_phase", "per_atom_epn_phase"):
             roofline["hbm_side"][k]["frac"] = roofline["hbm_side"][k]["achieved"] / hbm_peak
         par = (f"one system sharded x{world}" if sharded_system else f"molecule-shards x{world}, no collective")
         desc.update({"checkpoint": args.checkpoint, "parallelism": par,

@@ -110,6 +110,12 @@ const char* epnn_last_error(const epnn_ctx* ctx);
  * projections: GEMMs over all atoms of a chunk) on the warp-level tensor path, 3xTF32 split with FP32 accumulation
  * (epnn_atom_mma.cu), which leaves that kernel bound by its HBM traffic; 0 = the FP32 SIMT warp-tile kernel.  Same
  * formulas; results differ at the level of FP32 round-off.  Mixed / FP64 calls are not affected;
+ * "fused_prep" 1 (default) / 0: chunks that hold only systems of at most 48 atoms build all their lists (CSR, pair list, far
+ * lists) with two warp-per-bundle kernels from one 48-bit neighbour mask per row (epnn_bundle_prep.cu) instead of the general
+ * thread-per-atom kernels; identical lists (0 = A/B);
+ * "chunk_streams" 1 (default) / 2: multi-chunk calls keep two chunks in flight on two streams with separate workspaces, so
+ * the list building and host sync of one chunk run beside the pair kernels of the other (identical results; +2 % throughput
+ * on a million molecules, but the per-phase times of epnn_stats then overlap and add up to more than the wall clock);
  * "pair_const": the FP32 kernel set.  2 (default): row-run GNN bundle kernel (epnn_bundle_run.cu: one contiguous run of
  * pair slots per lane, row sums in registers) + pair-per-thread EPN bundle kernel + row-per-thread far kernel for large
  * systems, all with the weights as uniform FFMA2 operands (kernel parameters); 1: pair-per-thread kernels everywhere

@@ -278,9 +278,13 @@ def test_chunking_is_invisible(engines, weights, mixed):
     try:
         b = eng.infer_batch(offs, xyz, sp, Q, 41).copy()
         assert eng.last_stats["n_chunks"] > 5
+        eng.set_option("chunk_streams", 2)               # two chunks in flight on two streams, each with its own workspaces
+        c2 = eng.infer_batch(offs, xyz, sp, Q, 41).copy()
+        assert eng.last_stats["n_chunks"] > 5
     finally:
         eng.set_option("chunk_atoms", 4 * 1024 * 1024)
-    assert np.array_equal(a, b)
+        eng.set_option("chunk_streams", 1)
+    assert np.array_equal(a, b) and np.array_equal(a, c2)
 
 
 def test_caller_stream_and_device_pointers(weights, mixed):
