@@ -14,12 +14,14 @@
 #define ACONST_NW 8
 #define ATS 68                            // row stride of the transpose tile: 64 + 4 floats
 
-struct AtomW {
+struct alignas(16) AtomW {      // (read with 8-byte loads: keep every member offset a multiple of 8)
     float HG[64 * HID]; float cb[HID]; float g[HID];          // first update layer on [l2_prev | S], its bias, U1_M^T b3 (times npad)
     float U2[HID * HID]; float c2[HID];                        // second update layer
     float U3[HID * HD]; float c3[HD];                          // h = U3^T l2 + c3 (last step only)
     float Pf[HID * 64]; float Aq[64];                          // projections of the next pair kernel: U3 . Ah64, q row
 };
+
+static_assert(sizeof(AtomW) % 16 == 0 && sizeof(AtomW) < 32000, "AtomW is a __grid_constant__ kernel parameter: 32 764 bytes at most (CUDA >= 12.1)");
 
 struct AtomConstArgs {
     int n_atoms, mode, nsplit, h_is_zero;

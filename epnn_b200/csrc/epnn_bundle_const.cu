@@ -38,7 +38,7 @@
 // uniform-operand path drops from 64.7 to 41 TFLOP/s as soon as a loop's constants exceed it).  C rows, b2 and x32 (b1 for
 // the GNN variant, w3 for the EPN variant) are staged in shared memory, the kernel arguments come through global memory
 // (as parameters ptxas re-reads them from the constant bank inside the loop).
-struct PairW { float W2[HID * HID]; };
+struct alignas(16) PairW { float W2[HID * HID]; };      // read with 8- / 16-byte loads
 
 struct ConstArgs {
     int n_bundles; const int2* bundle; int* work_counter;

@@ -38,7 +38,7 @@ constexpr int kRunUnroll = RUN_UNROLL;     // unroll factor of the slot loop (2 
 #define VST 36                          // row stride of the staged v rows: 32 + 4 floats (rows start in different bank groups)
 #define RUN_PAD_ROW BUNDLE_ATOMS
 
-struct RunW { float W2[HID * HID]; };      // the ONLY constants the slot loop walks: exactly 4 KB (see bundle_run_kernel)
+struct alignas(16) RunW { float W2[HID * HID]; };      // the ONLY constants the slot loop walks: exactly 4 KB (see bundle_run_kernel)
 
 struct RunArgs {
     int n_bundles; const int2* bundle; int* work_counter;

@@ -19,7 +19,7 @@
 #define FARC_NW 8
 #define FARC_COLS 32                       // columns (v rows) staged per chunk
 
-struct FarW { float W2[HID * HID]; float b2[HID]; };
+struct alignas(16) FarW { float W2[HID * HID]; float b2[HID]; };
 
 struct FarConstArgs {
     const int2* blk; int unit_begin, unit_end, nsplit, n_atoms;      // blk: (first atom of a 32-row block, system index)

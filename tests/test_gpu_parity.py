@@ -24,7 +24,7 @@ from oracle import epnn_oracle as O
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-5
-TOL_FP32 = {"decay_model_weights": 2e-6, "model2_weights": 1e-5, "model_weights": 2e-4}     # measured 7.8e-7 / 3.9e-6 / 1.0e-4
+TOL_FP32 = {"decay_model_weights": 2e-6, "model2_weights": 1e-5, "model_weights": 2e-4}     # measured 7.8e-7 / 5.4e-6 / 1.1e-4 (tensor per-atom kernel; SIMT: 3.9e-6 / 1.0e-4)
 TOL_MIXED = {"decay_model_weights": 2e-6, "model2_weights": 4e-6, "model_weights": 2e-4}    # measured 7.9e-7 / 1.3e-6 / 9.0e-5
 TOL_FP64 = 1e-9                                                                              # measured <= 3.5e-10
 
@@ -285,6 +285,51 @@ def test_chunking_is_invisible(engines, weights, mixed):
         eng.set_option("chunk_atoms", 4 * 1024 * 1024)
         eng.set_option("chunk_streams", 1)
     assert np.array_equal(a, b) and np.array_equal(a, c2)
+
+
+def test_fused_list_building_equals_the_general_path(weights, mixed):
+    """Chunks of small systems build their lists with the warp-per-bundle kernels (epnn_bundle_prep.cu); "fused_prep" 0 sends
+    them through the general thread-per-atom kernels: identical neighbour lists (both sets) and bit-identical charges."""
+    from epnn_b200.engine import Engine
+    w = weights["model2_weights"]
+    idx = mixed.usable(w.n_x)[0:1500:2].tolist()
+    offs, xyz, sp, Q = mixed.batch(idx, w.n_x)
+    out = []
+    for fused in (1, 0):
+        eng = Engine(w, device=0)
+        try:
+            eng.set_option("fused_prep", fused)
+            q64 = eng.infer_batch(offs, xyz, sp, Q, 41, want_f64=True)[1].copy()
+            out.append((q64, eng.neighbors(offs, xyz, which=0), eng.neighbors(offs, xyz, which=1), eng.last_stats["n_launches"]))
+        finally:
+            eng.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    for k in (1, 2):
+        assert np.array_equal(out[0][k][0], out[1][k][0]) and np.array_equal(out[0][k][1], out[1][k][1])
+
+
+def test_tensor_per_atom_kernel_against_simt(weights, mixed):
+    """FP32 calls run the per-atom GEMMs (update MLP, projections) on the warp-level tensor path (3xTF32, epnn_atom_mma.cu);
+    "atom_tensor" 0 is the FP32 SIMT kernel.  Same formulas: the charges differ by FP32 round-off only, and both stay inside
+    the checkpoint's FP32 tolerance against the float64 oracle."""
+    from epnn_b200.engine import Engine
+    w = weights["model2_weights"]
+    idx = mixed.usable(w.n_x)[5:1205:3].tolist()
+    offs, xyz, sp, Q = mixed.batch(idx, w.n_x)
+    ref = O.predict_batch(w, offs, xyz, sp, Q, np.full(len(idx), 41))
+    q = {}
+    for tensor in (1, 0):
+        eng = Engine(w, device=0)
+        try:
+            eng.set_option("atom_tensor", tensor)
+            q[tensor] = eng.infer_batch(offs, xyz, sp, Q, 41, want_f64=True)[1].copy()
+            assert eng.last_stats["atom_tensor_used"] == tensor
+        finally:
+            eng.close()
+    assert not np.array_equal(q[0], q[1])                         # two different kernels really ran
+    assert np.abs(q[1] - q[0]).max() < TOL_FP32["model2_weights"]
+    for tensor in (1, 0):
+        assert np.abs(q[tensor] - ref).max() < TOL_FP32["model2_weights"]
 
 
 def test_caller_stream_and_device_pointers(weights, mixed):
