@@ -4,11 +4,15 @@
 // the first-layer projections of :62-68 / :101-110), but the three dense layers of a step
 //     [l2_prev | S] (64) -> l1 (32) -> l2 (32) -> u | v (64)      (+ h = U3^T l2 + c3 (48) at the last message-passing step)
 // are real GEMMs over all atoms of the chunk (M = atoms, K / N = 32 .. 64), so they run as mma.sync.m16n8k8 (TF32 inputs,
-// FP32 accumulation) with the 3xTF32 error-compensated split  x = hi + lo:  lo*hi + hi*lo + hi*hi.  hi and lo are rounded to
-// TF32 (nearest, ties away): representation error of an operand <= 2^-22 |x|, the dropped lo*lo term <= 2^-22 |x||w|; the
-// hi*hi blocks are summed on the FP32 pipe (am_pair) -- the same order of error as the FP32 rounding of the SIMT kernel
-// (tests/test_gpu_parity.py keeps its tolerances; noise-floor log in profiles/r02).  With the FP32 pipe out of the way the
-// kernel is bound by its HBM traffic (640 B per atom and step) instead of by shared-memory operand reads.
+// FP32 accumulation) on the two-term split  x = hi + lo  of both operands, hi and lo rounded to TF32 (nearest, ties away):
+// (hi + lo)(hi + lo) = hi*hi + lo*hi + hi*lo + lo*lo, FOUR MMAs per block.  The usual 3xTF32 scheme drops lo*lo (2^-22 of a
+// product) and lets the tensor core truncate lo; measured over all 4 374 systems of data/mixed with model2_weights (pad 41,
+// profiles/r02/call63_*, call64_*) that left a tail 1.5x the FP32 SIMT kernel's -- one system at 1.12e-5 e, above north_star's
+// 1e-5 -- while the full product with rounded lo is at 9.2e-6 / p99.9 4.7e-6 against 7.9e-6 / 4.0e-6 for SIMT, for 0.7 ms
+// more per 300 k molecules.  The three correction terms chain in their own accumulator (2^-11 of the main term: the tensor
+// core's round-toward-zero is irrelevant there), the hi*hi blocks of one am_pair call chain for at most four k blocks and
+// are added on the FP32 pipe (round to nearest).  With the FP32 pipe out of the way the kernel is bound by its HBM traffic
+// (640 B per atom and step) and by instruction issue, not by shared-memory operand reads.
 //
 // A warp owns a tile of 32 consecutive atoms = two 16-row m-tiles; thread (g = lane >> 2, t = lane & 3) owns rows
 // g, g + 8, g + 16, g + 24.  ONE index map serves every operand,
@@ -18,14 +22,17 @@
 // columns 16m + 4t .. + 3 of its rows, so every global load and store is a 128-bit access and a warp instruction touches
 // 8 rows x 64 contiguous bytes; (2) the C fragments a layer leaves behind ARE the A fragments of the next layer (after bias,
 // ReLU and the split) -- no shared-memory stage between layers; (3) the weights are permuted once per CTA into B fragments in
-// shared memory: fragment (kb, nt) = 32 lanes x {b0 hi, b1 hi, b0 lo, b1 lo}, one conflict-free LDS.128 per lane feeds six MMAs.
+// shared memory: fragment (kb, nt) = 32 lanes x {b0 hi, b1 hi, b0 lo, b1 lo}, one conflict-free LDS.128 per lane feeds eight MMAs.
 #include "epnn_internal.cuh"
 
 #ifndef AM_CHAIN
 #define AM_CHAIN 1                               // 1: the hi*hi blocks of one am_pair call chain inside the tensor core; 0: each block is added on the FP32 pipe
 #endif
+#ifndef AM_LOLO
+#define AM_LOLO 1                                // fourth MMA lo*lo (2^-22 of the product): see the header, 0 only for A/B
+#endif
 #ifndef AM_ROUND_LO
-#define AM_ROUND_LO 0                            // 1: lo rounded to TF32 (nearest) instead of truncated by the tensor core
+#define AM_ROUND_LO 1                            // lo rounded to TF32 (nearest) instead of truncated by the tensor core; 0 only for A/B
 #endif
 #define AM_FRAG 128                              // words per B fragment (32 lanes x 4)
 // Shared-memory layout (32-bit words) of the two instantiations: UPD = launches that finish a message-passing step (all three
@@ -116,11 +123,11 @@ __device__ __forceinline__ void am_stage(unsigned* dst, const float* __restrict_
 // d3 (row + 8, 2t + 1)) of m-tile mt and n tile 2m + n.
 //
 // acc[mt][n] += A (two m-tiles, KB k blocks, hi / lo) * B fragments (kb0 + kb, nt0 + n) for one column pair.  The tensor core
-// rounds its FP32 accumulator toward zero, a bias that grows linearly with the length of an accumulation chain (first GPU
-// run of this kernel: model2_weights 3.9e-6 -> 9.8e-6 from the oracle).  So, as in Ootomo & Yokota's error-corrected TF32 GEMM,
-// every hi*hi product block is an MMA into a ZERO accumulator that is added to the running sum on the FP32 pipe (round to
-// nearest), and only the two small correction terms lo*hi + hi*lo chain inside the tensor core (2^-11 of the main term: their
-// rounding is irrelevant) and are added once at the end.
+// rounds its FP32 accumulator toward zero, a bias that grows with the length of an accumulation chain (first GPU run of this
+// kernel, everything in one chain: model2_weights 3.9e-6 -> 9.8e-6 from the oracle).  So the small correction terms chain in
+// their own accumulator, and the hi*hi blocks either chain for the k blocks of this one call (AM_CHAIN, default) or -- as in
+// Ootomo & Yokota's error-corrected TF32 GEMM -- go into a ZERO accumulator each and are added on the FP32 pipe (measured: the
+// same noise, 600 more FADDs per tile).
 template <int KB>
 __device__ __forceinline__ void am_pair(const unsigned (&ah)[2][KB][4], const unsigned (&al)[2][KB][4], const unsigned* __restrict__ sB,
                                         int kb0, int ntot, int nt0, int lane, float (&acc)[2][2][4]) {
@@ -145,6 +152,9 @@ __device__ __forceinline__ void am_pair(const unsigned (&ah)[2][KB][4], const un
             for (int mt = 0; mt < 2; ++mt) {
                 am_mma(corr[mt][n], al[mt][kb], b.x, b.y);
                 am_mma(corr[mt][n], ah[mt][kb], b.z, b.w);
+#if AM_LOLO
+                am_mma(corr[mt][n], al[mt][kb], b.z, b.w);
+#endif
 #if AM_CHAIN
                 am_mma(mainacc[mt][n], ah[mt][kb], b.x, b.y);
 #else
