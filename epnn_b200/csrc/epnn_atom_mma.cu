@@ -128,14 +128,19 @@ __device__ __forceinline__ void am_stage(unsigned* dst, const float* __restrict_
 // their own accumulator, and the hi*hi blocks either chain for the k blocks of this one call (AM_CHAIN, default) or -- as in
 // Ootomo & Yokota's error-corrected TF32 GEMM -- go into a ZERO accumulator each and are added on the FP32 pipe (measured: the
 // same noise, 600 more FADDs per tile).
-template <int KB>
+template <int KB, bool SET = false>        // SET: acc = product (acc need not be initialised), else acc += product
 __device__ __forceinline__ void am_pair(const unsigned (&ah)[2][KB][4], const unsigned (&al)[2][KB][4], const unsigned* __restrict__ sB,
                                         int kb0, int ntot, int nt0, int lane, float (&acc)[2][2][4]) {
     float corr[2][2][4];
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int n = 0; n < 2; ++n) corr[mt][n][0] = corr[mt][n][1] = corr[mt][n][2] = corr[mt][n][3] = 0.f;
+        for (int n = 0; n < 2; ++n) {
+            corr[mt][n][0] = corr[mt][n][1] = corr[mt][n][2] = corr[mt][n][3] = 0.f;
+#if !AM_CHAIN
+            if (SET) acc[mt][n][0] = acc[mt][n][1] = acc[mt][n][2] = acc[mt][n][3] = 0.f;
+#endif
+        }
 #if AM_CHAIN
     float mainacc[2][2][4];
 #pragma unroll
@@ -172,7 +177,8 @@ __device__ __forceinline__ void am_pair(const unsigned (&ah)[2][KB][4], const un
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
 #if AM_CHAIN
-                acc[mt][n][e] += mainacc[mt][n][e] + corr[mt][n][e];
+                if (SET) acc[mt][n][e] = mainacc[mt][n][e] + corr[mt][n][e];
+                else acc[mt][n][e] += mainacc[mt][n][e] + corr[mt][n][e];
 #else
                 acc[mt][n][e] += corr[mt][n][e];
 #endif
@@ -319,32 +325,37 @@ __global__ void __launch_bounds__(AmL<UPD>::NW * 32, 2) atom_mma_kernel(const At
         unsigned ah[2][4][4], al[2][4][4];               // A fragments of the layer about to run (k blocks 0..3)
         float z[2][2][2][4];                             // a layer's 32 output columns: two column pairs
         if (do_upd) {
-            // ---- first layer: relu([U3 U1_h ; W3 U1_M]^T [l2_prev | S] + cb + npad g), 16 input columns (two k blocks) at a time
-            am_zero(z[0]); am_zero(z[1]);
+            // ---- first layer: relu([U3 U1_h ; W3 U1_M]^T [l2_prev | S] + cb + npad g), 32 input columns (four k blocks) at a time:
+            // the l2 half (skipped at the first step: h = 0), then the S half
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (j < 2 && first) continue;            // h = 0: no previous l2
-                float zz[1][2][2][4];
+            for (int jj = 0; jj < 2; ++jj) {
+                if (jj == 0 && first) continue;
+                float zz[2][2][2][4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const int64_t at = base + g + 8 * i;
-                    if (rns[i] > 0) {
-                        if (j < 2) x = am_ld4(st_l2 + (g + 8 * i) * HID + 16 * j + 4 * t);
-                        else {
-                            x = am_ld4(st_S + (g + 8 * i) * HID + 16 * (j - 2) + 4 * t);
-                            for (int sp = 1; sp < rns[i]; ++sp) {       // large systems: further partial planes, summed in fixed order
-                                const float4 p = am_ld4(a.Spart + ((int64_t)sp * a.n_atoms + at) * HID + 16 * (j - 2) + 4 * t);
-                                x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w;
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (rns[i] > 0) {
+                            if (jj == 0) x = am_ld4(st_l2 + (g + 8 * i) * HID + 16 * m + 4 * t);
+                            else {
+                                x = am_ld4(st_S + (g + 8 * i) * HID + 16 * m + 4 * t);
+                                for (int sp = 1; sp < rns[i]; ++sp) {       // large systems: further partial planes, summed in fixed order
+                                    const float4 p = am_ld4(a.Spart + ((int64_t)sp * a.n_atoms + base + g + 8 * i) * HID + 16 * m + 4 * t);
+                                    x.x += p.x; x.y += p.y; x.z += p.z; x.w += p.w;
+                                }
                             }
                         }
+                        am_put4(zz[m], i, x);
                     }
-                    am_put4(zz[0], i, x);
-                }
-                unsigned ah1[2][2][4], al1[2][2][4];
-                am_to_a<1>(zz, ah1, al1);
+                am_to_a<2>(zz, ah, al);
+                if (jj == 0 || first) {
 #pragma unroll
-                for (int m = 0; m < 2; ++m) am_pair<2>(ah1, al1, sm + L::B1, 2 * j, 4, 2 * m, lane, z[m]);
+                    for (int m = 0; m < 2; ++m) am_pair<4, true>(ah, al, sm + L::B1, 4 * jj, 4, 2 * m, lane, z[m]);
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 2; ++m) am_pair<4, false>(ah, al, sm + L::B1, 4 * jj, 4, 2 * m, lane, z[m]);
+                }
             }
             __syncwarp();                                // every lane has read its inputs: the stage is free for the next tile
             if (lane == 0 && more) fetch(tile + tstep);
@@ -364,8 +375,7 @@ __global__ void __launch_bounds__(AmL<UPD>::NW * 32, 2) atom_mma_kernel(const At
             // ---- second layer: l2 = relu(U2^T l1 + c2), one column pair at a time
 #pragma unroll
             for (int m = 0; m < 2; ++m) {
-                am_zero(z[m]);
-                am_pair<4>(ah, al, sm + L::B2, 0, 4, 2 * m, lane, z[m]);
+                am_pair<4, true>(ah, al, sm + L::B2, 0, 4, 2 * m, lane, z[m]);
                 const float4 cv = am_ld4(sc2 + 16 * m + 4 * t);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -380,8 +390,7 @@ __global__ void __launch_bounds__(AmL<UPD>::NW * 32, 2) atom_mma_kernel(const At
             if (write_h) {
                 for (int m = 0; m < 3; ++m) {
                     float ha[2][2][4];
-                    am_zero(ha);
-                    am_pair<4>(ah, al, sm + L::BH, 0, 6, 2 * m, lane, ha);
+                    am_pair<4, true>(ah, al, sm + L::BH, 0, 6, 2 * m, lane, ha);
                     const float4 cv = am_ld4(sc3 + 16 * m + 4 * t);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -411,8 +420,8 @@ __global__ void __launch_bounds__(AmL<UPD>::NW * 32, 2) atom_mma_kernel(const At
 #pragma unroll
             for (int m = 0; m < 4; ++m) {                // column pairs 0, 1 -> u (a_i block), 2, 3 -> v (a_j block, + b1)
                 float acc[2][2][4];
-                am_zero(acc);
-                if (proj_gemm) am_pair<4>(ah, al, sm + L::B3, 0, 8, 2 * m, lane, acc);
+                if (proj_gemm) am_pair<4, true>(ah, al, sm + L::B3, 0, 8, 2 * m, lane, acc);
+                else am_zero(acc);
                 float* dst = m < 2 ? a.u : a.v;
                 const float4 aq = am_ld4(saq + 16 * m + 4 * t);
 #pragma unroll
