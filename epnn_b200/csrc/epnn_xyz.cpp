@@ -9,6 +9,8 @@
 //            numpy's np.array(list_of_strings, dtype=np.float32)
 // Element symbols index the table chosen by n_x (9: H C N O F S Cl Br, infer.py:13-30; 10: H C N O F P S Cl Br,
 // charge_gn.py:9-28); an unknown symbol is an error (the reference raises KeyError, charge_gn.py:326-327).
+#include <locale.h>
+#include <cmath>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -59,9 +61,12 @@ bool parse_float32(const char* tok, size_t len, float& out) {
     if (len == 0 || len >= sizeof buf) return false;
     memcpy(buf, tok, len);
     buf[len] = 0;
+    for (size_t i = 0; i < len; ++i)        // hex floats ("0x1p3") are not part of the dialect (Python's float() rejects them too)
+        if (buf[i] == 'x' || buf[i] == 'X' || buf[i] == 'p' || buf[i] == 'P') return false;
+    static const locale_t c_loc = newlocale(LC_NUMERIC_MASK, "C", (locale_t)0);      // '.' is the decimal point whatever the process locale says
     char* e = nullptr;
-    const double d = strtod(buf, &e);       // correctly rounded float64, then one rounding to float32 (numpy semantics)
-    if (e != buf + len) return false;
+    const double d = c_loc ? strtod_l(buf, &e, c_loc) : strtod(buf, &e);       // correctly rounded float64, then one rounding to float32 (numpy semantics)
+    if (e != buf + len || !std::isfinite(d)) return false;                     // a nan / inf coordinate or charge is an input error, not a number
     out = (float)d;
     return true;
 }

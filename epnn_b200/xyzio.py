@@ -39,6 +39,8 @@ def parse_xyz_text(text: str, name: str = "") -> System:
         symbols.append(data[0])
         coords.append([data[1], data[2], data[3]])
     xyz = np.array(coords, dtype=np.float32)
+    if not (np.isfinite(xyz).all() and np.isfinite(Q)):      # same rule as the native parser: nan / inf is an input error
+        raise ValueError(f"{name}: non-finite coordinate or charge")
     return System(name=name, symbols=symbols, xyz=xyz, Q=Q)
 
 

@@ -51,6 +51,14 @@ def test_errors_match_the_reference_behaviour(tmp_path):
         xyzio.parse_packed("1\nfoo\nH 0 0 0\n", 9)    # charge is not a number
     with pytest.raises(ValueError):
         xyzio.parse_packed("1\n0 1\n", 9)             # no atoms
+    for bad in ("nan", "inf", "-Infinity", "0x1p3", "0X10", "1,5"):      # non-finite, hex floats, locale decimal commas
+        with pytest.raises(ValueError):
+            xyzio.parse_packed(f"1\n0 1\nH 0 {bad} 0\n", 9)
+    for bad in ("nan", "inf"):
+        with pytest.raises(ValueError):
+            xyzio.parse_xyz_text(f"1\n0 1\nH 0 {bad} 0\n")
+        with pytest.raises(ValueError):
+            xyzio.parse_packed(f"1\n{bad}\nH 0 0 0\n", 9)
     with pytest.raises(FileNotFoundError):
         xyzio.load_packed([str(tmp_path / "missing.xyz")], 9)
 
