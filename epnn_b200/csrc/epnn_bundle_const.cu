@@ -174,10 +174,22 @@ __global__ void __launch_bounds__(CONST_NW * 32, EPN ? CONST_CTAS_EPN : 1) bundl
             }
         }
         __syncwarp();
-        for (int f = lane; f < nat * 16; f += 32) {                // stage u | v (coalesced 16-byte loads)
-            const int row = f >> 4, c4 = f & 15;
-            const float* src = (c4 < 8 ? a.u : a.v) + (int64_t)(atom0 + row) * HID + (c4 & 7) * 4;
-            *reinterpret_cast<float4*>(uv + row * CUVS + c4 * 4) = *reinterpret_cast<const float4*>(src);
+        // stage u | v (coalesced 16-byte loads), eight loads in flight per lane: with one load per loop trip a bundle waited out
+        // 24 L2 latencies one after the other (ncu source view, call77: 17 % of the kernel's stall samples on that one line)
+        for (int f0 = 0; f0 < nat * 16; f0 += 8 * 32) {
+            float4 x[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int f = f0 + q * 32 + lane;
+                const int fc = f < nat * 16 ? f : nat * 16 - 1;
+                const int row = fc >> 4, c4 = fc & 15;
+                x[q] = __ldg(reinterpret_cast<const float4*>((c4 < 8 ? a.u : a.v) + (int64_t)(atom0 + row) * HID + (c4 & 7) * 4));
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int f = f0 + q * 32 + lane;
+                if (f < nat * 16) *reinterpret_cast<float4*>(uv + (f >> 4) * CUVS + (f & 15) * 4) = x[q];
+            }
         }
         if (!EPN) {
             for (int f = lane; f < nat * HID; f += 32) S[f] = 0.f;
