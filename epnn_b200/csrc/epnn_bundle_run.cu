@@ -165,10 +165,22 @@ __global__ void __launch_bounds__(RUN_NW * 32, RUN_CTAS) bundle_run_kernel(const
                 rprefetch_l2(reinterpret_cast<const char*>(a.e) + o);
         }
         __syncwarp();
-        for (int f = lane; f < nat * 8; f += 32) {                   // stage v (coalesced 16-byte loads), zero S
-            const int row = f >> 3, c4 = f & 7;
-            *reinterpret_cast<float4*>(vS + row * VST + c4 * 4) = *reinterpret_cast<const float4*>(a.v + (int64_t)(atom0 + row) * HID + c4 * 4);
-            *reinterpret_cast<float4*>(S + row * HID + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        // stage v (coalesced 16-byte loads, six in flight per lane instead of one load per loop trip), zero S
+        for (int f0 = 0; f0 < nat * 8; f0 += 6 * 32) {
+            float4 x[6];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int f = f0 + q * 32 + lane;
+                x[q] = __ldg(reinterpret_cast<const float4*>(a.v + (int64_t)atom0 * HID) + (f < nat * 8 ? f : nat * 8 - 1));
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const int f = f0 + q * 32 + lane;
+                if (f < nat * 8) {
+                    *reinterpret_cast<float4*>(vS + (f >> 3) * VST + (f & 7) * 4) = x[q];
+                    *reinterpret_cast<float4*>(S + f * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
         }
         for (int r = lane; r < nat; r += 32) {
             const int sys = a.atom_sys[atom0 + r];
