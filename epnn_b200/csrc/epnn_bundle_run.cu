@@ -71,11 +71,16 @@ struct RunSmem {
 // S[row][0..31] += acc (one lane, 8 x 16-byte read-modify-write)
 __device__ __forceinline__ void flush_row(float* __restrict__ S, int row, const r2_t (&sacc)[HID / 2]) {
     float4* p = reinterpret_cast<float4*>(S + row * HID);
+    // 16-byte chunk c of row r lives at chunk c ^ (r & 7): lanes whose rows end at the same slot flush in one (divergent)
+    // instruction, and with a row stride of 128 B they would all hit the same four banks (ncu: 7.4 wavefronts per flush
+    // access, a third of the kernel's shared-memory wavefronts; A/B call81: 27.50 -> 26.25 ms)
+    const int sw = row & 7;
 #pragma unroll
-    for (int c = 0; c < HID / 4; ++c) {
+    for (int cc = 0; cc < HID / 4; ++cc) {
+        const int c = cc ^ sw;
         float4 s = p[c];
         float a0, a1, a2, a3;
-        runpack2(sacc[2 * c], a0, a1); runpack2(sacc[2 * c + 1], a2, a3);
+        runpack2(sacc[2 * cc], a0, a1); runpack2(sacc[2 * cc + 1], a2, a3);
         s.x += a0; s.y += a1; s.z += a2; s.w += a3;
         p[c] = s;
     }
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(RUN_NW * 32, RUN_CTAS) bundle_run_kernel(const
             auto fetch = [&](int k) {
                 if (k < s1) {
                     if (near) {
-                        n_a = a.rowl[k]; n_b = a.col[k]; n_c = a.pid[k];
+                        n_a = a.rowl[k]; n_b = a.col[k]; n_c = a.pid[k];       // (fetching the pair index a second slot ahead costs a register: +12 %, call81)
                         rprefetch_l1(a.e + (int64_t)n_c * EDR);
                     } else {
                         n_a = flist[k]; n_b = use0 ? (int)a.far0_w[k] : 1;
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(RUN_NW * 32, RUN_CTAS) bundle_run_kernel(const
         }
         // ---- S -> global (plane 0 of the partial-sum planes the per-atom kernel reads)
         for (int f = lane; f < nat * (HID / 4); f += 32)
-            *reinterpret_cast<float4*>(a.S + (int64_t)atom0 * HID + f * 4) = *reinterpret_cast<const float4*>(S + f * 4);
+            *reinterpret_cast<float4*>(a.S + (int64_t)atom0 * HID + f * 4) = *reinterpret_cast<const float4*>(S + (f ^ ((f >> 3) & 7)) * 4);   // undo flush_row's chunk swizzle
         __syncwarp();
     }
 }
